@@ -1,0 +1,184 @@
+// Parameter packing for the fused field-network kernel, and the hoisted view-direction term.
+//
+// nerf_pack_model: the 24 fp32 nn.Linear tensors of one Model (/root/reference/model.py:57-71)
+//   -> BF16 stage images in UMMA K-major SWIZZLE_128B layout + fp32 tail (see mlp_layout.h).
+// nerf_viewdir_term: l10's view-direction columns applied to PE4(viewdir) once per ray
+//   (/root/reference/model.py:103-104 computes the same product once per *sample*).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "mlp_layout.h"
+
+namespace {
+
+using namespace nerf;
+
+struct ParamPtrs {
+    const float* w[12];  // l1..l9, l_alpha, l10, l11
+    const float* b[12];
+};
+
+// (stage) -> (layer, chunk, half)
+__device__ __forceinline__ void stage_coords(int stage, int& l, int& chunk, int& half) {
+    l = 0;
+    int first = 0;
+    while (l + 1 < kNumMmaLayers && first + layer_chunks(l) * layer_halves(l) <= stage) {
+        first += layer_chunks(l) * layer_halves(l);
+        ++l;
+    }
+    int local = stage - first;
+    chunk = local / layer_halves(l);
+    half = local % layer_halves(l);
+}
+
+// Source column of (layer l, K chunk, column k in chunk) in the nn.Linear weight, or -1 (zero pad).
+__device__ __forceinline__ int source_col(int l, int chunk, int k) {
+    if (l == 0) return k < kPeDim ? k : -1;                       // l1: [256,63]
+    if (l == 5) return chunk == 0 ? (k < kPeDim ? k : -1)         // l6: PE columns first
+                                  : kPeDim + (chunk - 1) * 64 + k;  //     then h5 columns 63..318
+    return chunk * 64 + k;                                        // square layers, l10[:, :256]
+}
+
+__device__ __forceinline__ int param_index(int l) {  // MMA layer -> index in ParamPtrs
+    return l <= 8 ? l : 10;                          // L1..L9 -> 0..8, L10 -> 10 (l10)
+}
+
+__device__ __forceinline__ int in_features(int l) {
+    return l == 0 ? 63 : (l == 5 ? 319 : (l == 9 ? 283 : 256));
+}
+
+// one thread = one 16-byte chunk (8 consecutive k) of one stage row
+__global__ void pack_weights_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= kNumStages * kStageRows * 8) return;
+    int stage = gid / (kStageRows * 8);
+    int r = (gid / 8) % kStageRows;
+    int c16 = gid % 8;
+    int l, chunk, half;
+    stage_coords(stage, l, chunk, half);
+    const float* W = p.w[param_index(l)];
+    const int ld = in_features(l);
+    const int out_row = half * kStageRows + r;
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int col = source_col(l, chunk, c16 * 8 + e);
+        float x = col >= 0 ? W[(size_t)out_row * ld + col] : 0.f;
+        v[e] = __float2bfloat16_rn(x);
+    }
+    uint4 q;
+    q.x = (uint32_t)__bfloat16_as_ushort(v[0]) | ((uint32_t)__bfloat16_as_ushort(v[1]) << 16);
+    q.y = (uint32_t)__bfloat16_as_ushort(v[2]) | ((uint32_t)__bfloat16_as_ushort(v[3]) << 16);
+    q.z = (uint32_t)__bfloat16_as_ushort(v[4]) | ((uint32_t)__bfloat16_as_ushort(v[5]) << 16);
+    q.w = (uint32_t)__bfloat16_as_ushort(v[6]) | ((uint32_t)__bfloat16_as_ushort(v[7]) << 16);
+    *reinterpret_cast<uint4*>(blob + (size_t)stage * kStageBytes + swz128_offset(r, c16 * 8)) = q;
+}
+
+__global__ void pack_tail_kernel(ParamPtrs p, float* __restrict__ tail) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kTailFloats) return;
+    float v = 0.f;
+    if (i < kTailWAlpha) {                       // biases b1..b9
+        v = p.b[i / kHidden][i % kHidden];
+    } else if (i < kTailBAlpha) {
+        v = p.w[9][i - kTailWAlpha];
+    } else if (i < kTailW11) {
+        v = (i == kTailBAlpha) ? p.b[9][0] : 0.f;
+    } else if (i < kTailB11) {
+        v = p.w[11][i - kTailW11];
+    } else if (i < kTailW10View) {
+        int k = i - kTailB11;
+        v = k < 3 ? p.b[11][k] : 0.f;
+    } else if (i < kTailB10) {
+        int k = i - kTailW10View;
+        int n = k / 28, c = k % 28;
+        v = c < kViewPeDim ? p.w[10][(size_t)n * 283 + 256 + c] : 0.f;
+    } else {
+        v = p.b[10][i - kTailB10];
+    }
+    tail[i] = v;
+}
+
+// block = 128 threads = one row (ray); thread n produces out[row][n]
+__global__ void __launch_bounds__(128)
+viewdir_term_kernel(const float* __restrict__ tail, const float* __restrict__ dirs, int dir_stride,
+                    int embedded, long count, float* __restrict__ out) {
+    __shared__ float pe[28];
+    const long row = blockIdx.x;
+    const int t = threadIdx.x;
+    const float* d = dirs + row * dir_stride;
+    if (embedded) {
+        if (t < kViewPeDim) pe[t] = __ldg(d + t);
+    } else {
+        // [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^3), cos(x 2^3)], model.py:15-31
+        if (t < 3) pe[t] = __ldg(d + t);
+        if (t >= 32 && t < 32 + 12) {
+            int k = (t - 32) / 3, a = (t - 32) % 3;
+            float s, c;
+            sincosf(__ldg(d + a) * (float)(1 << k), &s, &c);
+            pe[3 + 6 * k + a] = s;
+            pe[3 + 6 * k + 3 + a] = c;
+        }
+    }
+    __syncthreads();
+    const float* w = tail + kTailW10View + t * 28;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < kViewPeDim; ++c) acc = fmaf(__ldg(w + c), pe[c], acc);
+    out[row * kL10Out + t] = acc + __ldg(tail + kTailB10 + t);
+}
+
+// FreqEmbedding.embed as a standalone op: one thread per (row, input component).
+__global__ void freq_encode_kernel(const float* __restrict__ x, long n, int dim, int n_freq,
+                                   float* __restrict__ out) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * dim) return;
+    long row = idx / dim;
+    int a = (int)(idx % dim);
+    float v = x[idx];
+    float* o = out + row * (long)(dim * (1 + 2 * n_freq));
+    o[a] = v;
+    for (int k = 0; k < n_freq; ++k) {
+        float s, c;
+        sincosf(v * exp2f((float)k), &s, &c);
+        o[dim + 2 * dim * k + a] = s;
+        o[dim + 2 * dim * k + dim + a] = c;
+    }
+}
+
+}  // namespace
+
+extern "C" int nerf_freq_encode(const float* x, long n, int dim, int n_freq, float* out, void* stream) {
+    if (n < 0 || dim < 1 || n_freq < 0 || (n > 0 && (!x || !out))) return nerf::arg_error("nerf_freq_encode");
+    if (n == 0) return 0;
+    freq_encode_kernel<<<nerf::blocks_for(n * dim, 256), 256, 0, (cudaStream_t)stream>>>(x, n, dim, n_freq, out);
+    return nerf::check_launch("nerf_freq_encode");
+}
+
+extern "C" size_t nerf_packed_model_bytes(void) { return nerf::kPackedBytes; }
+
+extern "C" int nerf_pack_model(const float* const* host_params, void* packed_out, void* stream) {
+    if (!host_params || !packed_out) return nerf::arg_error("nerf_pack_model");
+    ParamPtrs p;
+    for (int i = 0; i < 12; ++i) {
+        p.w[i] = host_params[2 * i];
+        p.b[i] = host_params[2 * i + 1];
+        if (!p.w[i] || !p.b[i]) return nerf::arg_error("nerf_pack_model: null parameter");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int n = kNumStages * kStageRows * 8;
+    pack_weights_kernel<<<nerf::blocks_for(n, 256), 256, 0, st>>>(p, (uint8_t*)packed_out);
+    pack_tail_kernel<<<nerf::blocks_for(kTailFloats, 256), 256, 0, st>>>(
+        p, (float*)((uint8_t*)packed_out + kWeightBytes));
+    return nerf::check_launch("nerf_pack_model");
+}
+
+extern "C" int nerf_viewdir_term(const void* packed, const float* dirs, int dir_stride, int embedded,
+                                 long count, float* out, void* stream) {
+    if (count < 0 || (count > 0 && (!packed || !dirs || !out))) return nerf::arg_error("nerf_viewdir_term");
+    if (count == 0) return 0;
+    const float* tail = (const float*)((const uint8_t*)packed + kWeightBytes);
+    viewdir_term_kernel<<<(unsigned)count, 128, 0, (cudaStream_t)stream>>>(tail, dirs, dir_stride, embedded,
+                                                                          count, out);
+    return nerf::check_launch("nerf_viewdir_term");
+}

@@ -1,0 +1,201 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/nerf_b200.h).
+
+Each wrapper checks devices/shapes, allocates outputs with torch (device memory + streams are
+PyTorch's job here, nothing else) and launches on the tensor's current stream.  Nothing in this
+file computes anything on the host.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, f32c, ptr, stream_of
+
+RAY_STRIDE = 11
+IN_RAYS, IN_POINTS, IN_EMBEDDED = 0, 1, 2
+
+
+def _ndc_consts(height, width, focal):
+    """cw, ch folded exactly as the reference's Python expression folds them
+    (data_helpers.py:332-333: ``-1./(width/(2.*focal))``), then rounded to fp32."""
+    cw = -1. / (width / (2. * focal))
+    ch = -1. / (height / (2. * focal))
+    return float(np.float32(cw)), float(np.float32(ch))
+
+
+def _f32(x):
+    return float(np.float32(x))
+
+
+def compute_rays(h, w, f, pose, row0=0, row1=None, want_origins=False):
+    """main.py:19-46 -> (origins or None, dirs [(row1-row0), W, 3])."""
+    lib = _lib.load()
+    pose = f32c(pose[:3, :4])
+    row1 = h if row1 is None else row1
+    dirs = torch.empty((row1 - row0, w, 3), dtype=torch.float32, device=pose.device)
+    origins = torch.empty_like(dirs) if want_origins else None
+    check(lib.nerf_compute_rays(h, w, _f32(f), ptr(pose), row0, row1, ptr(origins), ptr(dirs),
+                                stream_of(pose)), "nerf_compute_rays")
+    return origins, dirs
+
+
+def get_ndc(height, width, focal, near, o, d):
+    lib = _lib.load()
+    o, d = f32c(o), f32c(d)
+    cw, ch = _ndc_consts(height, width, focal)
+    o_out, d_out = torch.empty_like(o), torch.empty_like(d)
+    n = o.numel() // 3
+    check(lib.nerf_get_ndc(cw, ch, _f32(near), ptr(o), ptr(d), n, ptr(o_out), ptr(d_out), stream_of(o)),
+          "nerf_get_ndc")
+    return o_out, d_out
+
+
+def pack_rays(height, width, focal, *, pose=None, row0=0, row1=None, rays_o=None, rays_d=None,
+              ndc=True, near=0., far=1.):
+    """render() front end (main.py:55-76) -> rays [n,11]."""
+    lib = _lib.load()
+    cw, ch = _ndc_consts(height, width, focal)
+    if pose is not None:
+        pose = f32c(pose[:3, :4])
+        row1 = height if row1 is None else row1
+        n = (row1 - row0) * width
+        dev, o, d = pose.device, None, None
+    else:
+        o, d = f32c(rays_o.reshape(-1, 3)), f32c(rays_d.reshape(-1, 3))
+        n, dev, row1 = o.shape[0], o.device, 0
+    out = torch.empty((n, RAY_STRIDE), dtype=torch.float32, device=dev)
+    check(lib.nerf_pack_rays(height, width, _f32(focal), cw, ch, ptr(pose), row0, row1, ptr(o), ptr(d), n,
+                             int(bool(ndc)), _f32(near), _f32(far), ptr(out),
+                             torch.cuda.current_stream(dev).cuda_stream), "nerf_pack_rays")
+    return out
+
+
+def sample_coarse(rays, n_samples, t_rand=None):
+    lib = _lib.load()
+    n = rays.shape[0]
+    z = torch.empty((n, n_samples), dtype=torch.float32, device=rays.device)
+    if t_rand is not None:
+        t_rand = f32c(t_rand, rays.device)
+        assert t_rand.shape == z.shape
+    check(lib.nerf_sample_coarse(ptr(rays), n, n_samples, ptr(t_rand), ptr(z), stream_of(rays)),
+          "nerf_sample_coarse")
+    return z
+
+
+def _dir_arg(dirs):
+    """Accept a [n,3] tensor or a packed [n,11] ray tensor (uses columns 3:6)."""
+    if dirs.shape[-1] == RAY_STRIDE:
+        return dirs, dirs.data_ptr() + 12, RAY_STRIDE
+    dirs = f32c(dirs)
+    return dirs, dirs.data_ptr(), 3
+
+
+def composite_fwd(raw, z, dirs, noise=None, white_bkg=False, want_weights=True):
+    lib = _lib.load()
+    raw, z = f32c(raw), f32c(z)
+    n, s = z.shape
+    keep, dptr, dstride = _dir_arg(dirs)
+    noise = None if noise is None else f32c(noise, raw.device)
+    rgb = torch.empty((n, 3), dtype=torch.float32, device=raw.device)
+    w = torch.empty((n, s), dtype=torch.float32, device=raw.device) if want_weights else None
+    check(lib.nerf_composite_fwd(ptr(raw), ptr(z), dptr, dstride, ptr(noise), n, s, int(bool(white_bkg)),
+                                 ptr(rgb), ptr(w), stream_of(raw)), "nerf_composite_fwd")
+    return rgb, w
+
+
+def composite_bwd(raw, z, dirs, noise, white_bkg, grad_rgb, grad_w=None):
+    lib = _lib.load()
+    raw, z = f32c(raw), f32c(z)
+    n, s = z.shape
+    keep, dptr, dstride = _dir_arg(dirs)
+    noise = None if noise is None else f32c(noise, raw.device)
+    grad_rgb = f32c(grad_rgb)
+    grad_w = None if grad_w is None else f32c(grad_w)
+    grad_raw = torch.empty_like(raw)
+    check(lib.nerf_composite_bwd(ptr(raw), ptr(z), dptr, dstride, ptr(noise), n, s, int(bool(white_bkg)),
+                                 ptr(grad_rgb), ptr(grad_w), ptr(grad_raw), stream_of(raw)),
+          "nerf_composite_bwd")
+    return grad_raw
+
+
+def sample_pdf(bins, weights, u):
+    lib = _lib.load()
+    bins, weights, u = f32c(bins), f32c(weights), f32c(u)
+    n, b = bins.shape
+    m = u.shape[-1]
+    out = torch.empty((n, m), dtype=torch.float32, device=bins.device)
+    check(lib.nerf_sample_pdf(ptr(bins), ptr(weights), ptr(u), n, b, m, ptr(out), stream_of(bins)),
+          "nerf_sample_pdf")
+    return out
+
+
+def resample_merge(z_c, w_c, u):
+    lib = _lib.load()
+    z_c, w_c, u = f32c(z_c), f32c(w_c), f32c(u)
+    n, s = z_c.shape
+    m = u.shape[-1]
+    z_f = torch.empty((n, s + m), dtype=torch.float32, device=z_c.device)
+    check(lib.nerf_resample_merge(ptr(z_c), ptr(w_c), ptr(u), n, s, m, ptr(z_f), stream_of(z_c)),
+          "nerf_resample_merge")
+    return z_f
+
+
+def packed_model_bytes():
+    return int(_lib.load().nerf_packed_model_bytes())
+
+
+def pack_model(params, out=None):
+    """params: the 24 tensors in registration order (weight, bias per layer) -> uint8 blob."""
+    lib = _lib.load()
+    params = [f32c(p.detach()) for p in params]
+    assert len(params) == 24
+    dev = params[0].device
+    if out is None:
+        out = torch.empty(packed_model_bytes(), dtype=torch.uint8, device=dev)
+    arr = (ctypes.c_void_p * 24)(*[ptr(p) for p in params])
+    check(lib.nerf_pack_model(arr, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+          "nerf_pack_model")
+    return out
+
+
+def viewdir_term(packed, dirs, embedded=False):
+    """dirs: [count,3] tensor, packed rays [count,11] (uses columns 8:11) or, with
+    embedded=True, rows whose first 27 columns are PE4(dir)."""
+    lib = _lib.load()
+    count = dirs.shape[0]
+    if not embedded and dirs.shape[-1] == RAY_STRIDE:
+        dptr, stride = dirs.data_ptr() + 32, RAY_STRIDE
+    else:
+        dirs = f32c(dirs)
+        dptr, stride = dirs.data_ptr(), dirs.shape[-1]
+    out = torch.empty((count, 128), dtype=torch.float32, device=dirs.device)
+    check(lib.nerf_viewdir_term(packed.data_ptr(), dptr, stride, int(embedded), count, ptr(out),
+                                stream_of(dirs)), "nerf_viewdir_term")
+    return out
+
+
+def freq_encode(x, n_freq):
+    lib = _lib.load()
+    flat = f32c(x.reshape(-1, x.shape[-1]))
+    n, dim = flat.shape
+    out = torch.empty((n, dim * (1 + 2 * n_freq)), dtype=torch.float32, device=flat.device)
+    check(lib.nerf_freq_encode(ptr(flat), n, dim, n_freq, ptr(out), stream_of(flat)), "nerf_freq_encode")
+    return out.reshape(*x.shape[:-1], out.shape[-1])
+
+
+def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_stride=0,
+            probe_layer=None):
+    """-> raw [rows,4] (and the probed layer's FP32 activations when probe_layer is given)."""
+    lib = _lib.load()
+    raw = torch.empty((rows, 4), dtype=torch.float32, device=in0.device)
+    st = stream_of(in0)
+    if probe_layer is None:
+        check(lib.nerf_mlp_fwd(packed.data_ptr(), mode, ptr(in0), ptr(in1), in_stride, rows, samples_per_ray,
+                               ptr(vterm), vterm_div, ptr(raw), None, st), "nerf_mlp_fwd")
+        return raw
+    probe = torch.zeros((rows, 256), dtype=torch.float32, device=in0.device)
+    check(lib.nerf_mlp_fwd_probe(packed.data_ptr(), mode, ptr(in0), ptr(in1), in_stride, rows, samples_per_ray,
+                                 ptr(vterm), vterm_div, ptr(raw), probe_layer, ptr(probe), st),
+          "nerf_mlp_fwd_probe")
+    return raw, probe

@@ -1,0 +1,132 @@
+/*
+ * nerf_b200.h -- C ABI of the B200-native NeRF ray-render hot path.
+ *
+ * This is the drop-in boundary: the reference (johnfay11/CV-Nerf) is pure Python/PyTorch and has
+ * no FFI of its own, so each entry point below names the reference *function* it replaces
+ * (file:line in /root/reference).  The Python host in cv-nerf_b200/ binds these with ctypes and
+ * re-exposes the reference's call surface (compute_rays, get_ndc, render, render_rays,
+ * process_volume_info, inv_transform_sampling, Model, net_forward, create_model).
+ *
+ * Conventions
+ *  - every pointer is a CUDA *device* pointer owned by the caller unless the name says `host`;
+ *    the library never allocates or frees caller-visible memory;
+ *  - all tensors are contiguous fp32, row-major, shapes in the comments;
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream;
+ *  - return value 0 = ok; negative = argument error; positive = cudaError_t of the launch.
+ *    nerf_b200_last_error() returns a static description of the last failure on this thread.
+ *  - there is no CPU path: without a CUDA device every call fails with a cudaError_t.
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERF_B200_ABI_VERSION 1
+
+#define NERF_RAY_STRIDE 11      /* [o(3) d(3) near far viewdir(3)], main.py:71-76 */
+#define NERF_N_PARAM_TENSORS 24 /* 12 x (weight, bias) in Model registration order, model.py:57-71 */
+
+/* argument-error codes */
+#define NERF_ERR_ARG (-1)
+#define NERF_ERR_UNSUPPORTED (-2)
+
+int nerf_b200_abi_version(void);
+const char* nerf_b200_last_error(void);
+/* number of SMs of the current device (grid sizing for callers that want to report it) */
+int nerf_b200_sm_count(void);
+
+/* ---------------------------------------------------------------- K1: rays (bit-exact fp32) */
+
+/* compute_rays, main.py:19-46.  pose: [3,4] row-major (device).  Rows [row0,row1) of the H x W
+ * image are generated; dirs_out / origins_out are [(row1-row0)*W, 3] (origins_out may be NULL:
+ * the reference returns a stride-0 view of pose[:,3]). */
+int nerf_compute_rays(int H, int W, float focal, const float* pose, int row0, int row1,
+                      float* origins_out, float* dirs_out, void* stream);
+
+/* get_ndc, data_helpers.py:327-344 (quirks reproduced).  cw = fp32(-1/(W/(2 focal))) and ch are
+ * folded by the host exactly as Python/numpy folds them.  o,d,o_out,d_out: [n,3]. */
+int nerf_get_ndc(float cw, float ch, float near_plane, const float* o, const float* d, long n,
+                 float* o_out, float* d_out, void* stream);
+
+/* render() front end, main.py:55-76, fused: ray generation for rows [row0,row1) (pose != NULL) or
+ * a caller-provided batch (rays_o/rays_d [n,3], pose == NULL), view-dir normalisation from the
+ * pre-NDC direction, optional NDC warp (plane near = 1), packing to rays_out [n,11]. */
+int nerf_pack_rays(int H, int W, float focal, float cw, float ch, const float* pose, int row0,
+                   int row1, const float* rays_o, const float* rays_d, long n, int ndc,
+                   float near, float far, float* rays_out, void* stream);
+
+/* coarse depths, main.py:221-234.  rays [n,11] (near/far read from columns 6,7), t_rand [n,S]
+ * or NULL (perturb == 0), z_out [n,S]. */
+int nerf_sample_coarse(const float* rays, long n, int S, const float* t_rand, float* z_out,
+                       void* stream);
+
+/* ---------------------------------------------------------------- K3/K4: compositing, resampling */
+
+/* process_volume_info, main.py:174-204.  raw [n,S,4], z [n,S], dirs: row i at dirs + i*dir_stride
+ * (3 floats; pass rays+3 with stride 11, or a [n,3] tensor with stride 3), noise [n,S] already
+ * multiplied by the noise scale or NULL, rgb_out [n,3], weights_out [n,S] or NULL. */
+int nerf_composite_fwd(const float* raw, const float* z, const float* dirs, int dir_stride,
+                       const float* noise, long n, int S, int white_bkg, float* rgb_out,
+                       float* weights_out, void* stream);
+
+/* backward of the above w.r.t. raw: grad_rgb [n,3], grad_weights [n,S] or
+ * NULL -> grad_raw [n,S,4].  grad_scale multiplies the result (loss normalisation). */
+int nerf_composite_bwd(const float* raw, const float* z, const float* dirs, int dir_stride,
+                       const float* noise, long n, int S, int white_bkg, const float* grad_rgb,
+                       const float* grad_weights, float* grad_raw, void* stream);
+
+/* inv_transform_sampling, utils.py:4-53, with the uniform draws supplied by the caller.
+ * bins [n,B], weights [n,B-1], u [n,m] -> samples_out [n,m] (unsorted). B <= 256. */
+int nerf_sample_pdf(const float* bins, const float* weights, const float* u, long n, int B, int m,
+                    float* samples_out, void* stream);
+
+/* main.py:248-251 fused: midpoints of z_c, pdf over w_c[:,1:-1], inverse-CDF samples for u [n,m],
+ * sort(cat(z_c, samples)) -> z_f [n,S+m].  S+m <= 256. */
+int nerf_resample_merge(const float* z_c, const float* w_c, const float* u, long n, int S, int m,
+                        float* z_f, void* stream);
+
+/* ---------------------------------------------------------------- K2: the field network */
+
+/* Bytes of the packed parameter blob of one Model (BF16 UMMA-layout weight stages + fp32 tail). */
+size_t nerf_packed_model_bytes(void);
+
+/* Model parameters (model.py:57-71) -> packed blob.  host_params: HOST array of 24 DEVICE
+ * pointers in registration order l1.weight, l1.bias, ..., l9, l_alpha, l10, l11. */
+int nerf_pack_model(const float* const* host_params, void* packed_out, void* stream);
+
+/* Per-ray (or per-row) view-direction term of layer l10: W10[:,256:283] . PE4(dir) + b10,
+ * model.py:103-104 hoisted out of the per-sample loop.  dirs: row i at dirs + i*dir_stride;
+ * embedded = 0: rows are 3-vectors (PE computed here); 1: rows are 27-wide encodings.
+ * out [count,128]. */
+int nerf_viewdir_term(const void* packed, const float* dirs, int dir_stride, int embedded,
+                      long count, float* out, void* stream);
+
+/* FreqEmbedding.embed, model.py:9-31: x [n,dim] -> out [n, dim*(1+2*n_freq)] =
+ * [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)]. */
+int nerf_freq_encode(const float* x, long n, int dim, int n_freq, float* out, void* stream);
+
+#define NERF_IN_RAYS 0     /* in0 = rays [n,11], in1 = z [n,S]; point = o + d*z        */
+#define NERF_IN_POINTS 1   /* in0 = points [M,3]                                       */
+#define NERF_IN_EMBEDDED 2 /* in0 = rows [M,in_stride], first 63 columns = PE10(point) */
+
+/* net_forward + Model.forward, model.py:77-131, fused: point -> PE -> 8x256 trunk (skip at l6)
+ * -> sigma head, l9, l10 (+vterm), l11 -> raw_out [M,4] = (rgb_raw, sigma_raw).
+ * M rows; S samples per ray (row r belongs to ray r / S, only used by NERF_IN_RAYS);
+ * vterm [ceil(M / vterm_div), 128] from nerf_viewdir_term.
+ * act_save: NULL, or a buffer of nerf_mlp_act_bytes(M) bytes that receives the BF16 activations
+ * the backward pass needs. */
+int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, const float* in1, int in_stride,
+                 long M, int S, const float* vterm, int vterm_div, float* raw_out, void* act_save,
+                 void* stream);
+
+size_t nerf_mlp_act_bytes(long M);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */

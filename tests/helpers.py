@@ -1,0 +1,81 @@
+"""Shared helpers for the GPU parity tests (CPU-side emulation of the kernel's rounding points)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import nerf_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def bf16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def emulate_field(p, pe63, vterm, probe=None):
+    """The kernel's arithmetic restated on the CPU: every tensor-core operand (activations and
+    weights) rounded to BF16, FP32+ accumulation, FP32 bias/activation, FP32 sigma and rgb heads.
+    pe63 [M,63] fp32 encoding, vterm [M,128].  Returns raw [M,4] (and layer `probe`'s
+    post-activation values)."""
+    W = lambda n: bf16(p[n + ".weight"]).double()
+    b = lambda n: p[n + ".bias"].double()
+    x = bf16(pe63).double()
+    acts = []
+    h = torch.relu(x @ W("l1").T + b("l1")); acts.append(h)
+    for n in ("l2", "l3", "l4", "l5"):
+        h = torch.relu(bf16(h.float()).double() @ W(n).T + b(n)); acts.append(h)
+    w6 = W("l6")
+    h = torch.relu(x @ w6[:, :63].T + bf16(h.float()).double() @ w6[:, 63:].T + b("l6")); acts.append(h)
+    for n in ("l7", "l8"):
+        h = torch.relu(bf16(h.float()).double() @ W(n).T + b(n)); acts.append(h)
+    sigma = h @ p["l_alpha.weight"].double().T + p["l_alpha.bias"].double()      # fp32 head on fp32 h8
+    feat = bf16(h.float()).double() @ W("l9").T + b("l9"); acts.append(feat)
+    w10 = W("l10")[:, :256]
+    h10 = torch.relu(bf16(feat.float()).double() @ w10.T + vterm.double()); acts.append(h10)
+    rgb = h10 @ p["l11.weight"].double().T + p["l11.bias"].double()              # fp32 head on fp32 h10
+    raw = torch.cat([rgb, sigma], -1).float()
+    if probe is None:
+        return raw
+    return raw, acts[probe].float()
+
+
+def vterm_reference(p, dirs):
+    """W10[:,256:283] . PE4(dir) + b10 in fp64 -> fp32."""
+    pe = O.freq_encode(dirs, 4).double()
+    return (pe @ p["l10.weight"][:, 256:].double().T + p["l10.bias"].double()).float()
+
+
+def load_model_params(model, p):
+    """Copy an oracle parameter dict into a cv_nerf_b200 Model."""
+    with torch.no_grad():
+        for k, v in p.items():
+            name, kind = k.split(".")
+            getattr(getattr(model, name), kind).copy_(v)
+    return model
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def focal_of(g, prefix=""):
+    f = float(g[prefix + "hwf"][2])
+    return np.float32(f) if bool(g[prefix + "f_is_f32"]) else f
+
+
+def flip_aware_stats(got, want, sigma_last_got=None, sigma_last_want=None):
+    """max-abs over all rays, and over rays whose far-sample density did not change sign
+    (delta_last = 1e10 makes alpha_last a step function of sigma_last)."""
+    err = (got - want).abs().amax(-1)
+    out = {"max_all": err.max().item(), "n_gt_1e-2": int((err > 1e-2).sum())}
+    if sigma_last_got is not None:
+        flip = (sigma_last_got > 0) != (sigma_last_want > 0)
+        out["n_flip"] = int(flip.sum())
+        out["max_noflip"] = err[~flip].max().item() if (~flip).any() else 0.0
+    return out
+
+
+def psnr(a, b):
+    mse = torch.mean((a - b) ** 2).item()
+    return float("inf") if mse == 0 else -10. * np.log10(mse)

@@ -1,0 +1,253 @@
+"""GPU parity tests of the individual kernels, through the C ABI (ctypes), against the CPU oracle.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from tests.helpers import (bf16, emulate_field, focal_of, golden, load_model_params, vterm_reference)
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _K():
+    import cv_nerf_b200
+    return cv_nerf_b200.kernels
+
+
+def _sha(t):
+    return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()
+
+
+def _bits(t):
+    return t.detach().cpu().contiguous().view(torch.int32)
+
+
+# ------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("case", ["lego400", "lego800", "fern"])
+def test_compute_rays_bit_exact(case):
+    K = _K()
+    g = golden("rays.npz")
+    h, w = int(g[f"{case}_hwf"][0]), int(g[f"{case}_hwf"][1])
+    f = focal_of(g, case + "_")
+    pose = torch.from_numpy(g[f"{case}_pose"])
+    _, d = K.compute_rays(h, w, f, pose.to(DEV))
+    assert _sha(d) == str(g[f"{case}_d_sha"]), "ray directions differ from the reference bit pattern"
+    o_ref, d_ref = O.ray_grid(h, w, f, pose)
+    assert torch.equal(_bits(d), _bits(d_ref))
+    # row-sharded generation gives the same rows
+    _, d_part = K.compute_rays(h, w, f, pose.to(DEV), row0=h // 3, row1=h // 2)
+    assert torch.equal(_bits(d_part), _bits(d_ref[h // 3:h // 2]))
+
+
+def test_get_ndc_and_pack_bit_exact():
+    K = _K()
+    g = golden("rays.npz")
+    h, w = int(g["fern_hwf"][0]), int(g["fern_hwf"][1])
+    f = focal_of(g, "fern_")
+    pose = torch.from_numpy(g["fern_pose"])
+    o_ref, d_ref = O.ray_grid(h, w, f, pose)
+    on, dn = K.get_ndc(h, w, f, 1., o_ref.contiguous().to(DEV), d_ref.to(DEV))
+    assert _sha(on) == str(g["fern_ndc_o_sha"])
+    assert _sha(dn) == str(g["fern_ndc_d_sha"])
+    for ndc, near, far in ((True, 0., 1.), (False, 2., 6.)):
+        want = O.pack_rays(h, w, f, o_ref, d_ref, ndc, near, far)
+        got_pose = K.pack_rays(h, w, f, pose=pose.to(DEV), ndc=ndc, near=near, far=far)
+        got_rays = K.pack_rays(h, w, f, rays_o=o_ref.contiguous().to(DEV), rays_d=d_ref.to(DEV), ndc=ndc,
+                               near=near, far=far)
+        assert torch.equal(_bits(got_pose), _bits(want)), f"pack_rays(pose) ndc={ndc}"
+        assert torch.equal(_bits(got_rays), _bits(want)), f"pack_rays(rays) ndc={ndc}"
+
+
+@pytest.mark.parametrize("S", [64, 33, 128])
+def test_sample_coarse_bit_exact(S):
+    K = _K()
+    gen = torch.Generator().manual_seed(5)
+    n = 257
+    rays = torch.zeros(n, 11)
+    rays[:, 6] = 2. + torch.rand(n, generator=gen)
+    rays[:, 7] = 6. - torch.rand(n, generator=gen)
+    t_rand = torch.rand(n, S, generator=gen)
+    for tr in (None, t_rand):
+        want = O.coarse_depths(rays[:, 6:7], rays[:, 7:8], S, tr)
+        got = K.sample_coarse(rays.to(DEV), S, None if tr is None else tr.to(DEV))
+        assert torch.equal(_bits(got), _bits(want.contiguous())), f"S={S} perturb={tr is not None}"
+
+
+def test_sample_coarse_empty():
+    K = _K()
+    assert K.sample_coarse(torch.zeros(0, 11, device=DEV), 64).shape == (0, 64)
+
+
+# ------------------------------------------------------------------------------- K3 / K4
+@pytest.mark.parametrize("tag", ["c", "f"])
+def test_composite_forward_matches_golden(tag):
+    K = _K()
+    g = golden("units.npz")
+    raw, z, d = (torch.from_numpy(g[f"comp_{tag}_{k}"]) for k in ("raw", "z", "d"))
+    rgb, w = K.composite_fwd(raw.to(DEV), z.to(DEV), d.to(DEV), None, True)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g[f"comp_{tag}_rgb_white"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(w.cpu().numpy(), g[f"comp_{tag}_w_white"], rtol=0, atol=2e-6)
+    nd = torch.from_numpy(g[f"comp_{tag}_noise_draw"]) * 0.7
+    rgb, w = K.composite_fwd(raw.to(DEV), z.to(DEV), d.to(DEV), nd.to(DEV), False)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g[f"comp_{tag}_rgb_noise"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(w.cpu().numpy(), g[f"comp_{tag}_w_noise"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("S,white", [(64, True), (192, False), (40, True)])
+def test_composite_backward_matches_autograd(S, white):
+    K = _K()
+    gen = torch.Generator().manual_seed(S)
+    n = 70
+    raw = (torch.randn(n, S, 4, generator=gen) * 1.5).requires_grad_(True)
+    z, _ = torch.sort(2. + 4. * torch.rand(n, S, generator=gen), -1)
+    d = torch.randn(n, 3, generator=gen)
+    noise = torch.randn(n, S, generator=gen) * .3
+    g_rgb = torch.randn(n, 3, generator=gen)
+    g_w = torch.randn(n, S, generator=gen) * .1
+    rgb, w = O.composite(raw, z, d, noise, white)
+    ((rgb * g_rgb).sum() + (w * g_w).sum()).backward()
+    got = K.composite_bwd(raw.detach().to(DEV), z.to(DEV), d.to(DEV), noise.to(DEV), white, g_rgb.to(DEV),
+                          g_w.to(DEV))
+    want = raw.grad
+    scale = want.abs().max().item()
+    assert (got.cpu() - want).abs().max().item() <= 2e-5 * max(scale, 1.)
+    # rgb-only gradient (the path render_rays uses)
+    raw.grad = None
+    rgb, w = O.composite(raw, z, d, noise, white)
+    (rgb * g_rgb).sum().backward()
+    got = K.composite_bwd(raw.detach().to(DEV), z.to(DEV), d.to(DEV), noise.to(DEV), white, g_rgb.to(DEV))
+    assert (got.cpu() - raw.grad).abs().max().item() <= 2e-5 * max(raw.grad.abs().max().item(), 1.)
+
+
+def test_sample_pdf_matches_golden():
+    K = _K()
+    g = golden("units.npz")
+    bins, w, u = (torch.from_numpy(g[k]) for k in ("pdf_bins", "pdf_w", "pdf_u"))
+    got = K.sample_pdf(bins.to(DEV), w.to(DEV), u.to(DEV)).cpu()
+    np.testing.assert_allclose(got.numpy(), g["pdf_samples"], rtol=0, atol=2e-5)
+
+
+def test_resample_merge_matches_oracle():
+    K = _K()
+    gen = torch.Generator().manual_seed(9)
+    n = 300
+    near, far = torch.full((n, 1), 2.), torch.full((n, 1), 6.)
+    z = O.coarse_depths(near, far, 64, torch.rand(n, 64, generator=gen)).contiguous()
+    w = torch.rand(n, 64, generator=gen) ** 6
+    w[0] = 0.
+    u = torch.rand(n, 128, generator=gen)
+    mids = .5 * (z[:, 1:] + z[:, :-1])
+    s = O.inverse_cdf_sample(mids, w[:, 1:-1], u)
+    want, _ = torch.sort(torch.cat([z, s], -1), -1)
+    got = K.resample_merge(z.to(DEV), w.to(DEV), u.to(DEV)).cpu()
+    assert got.shape == (n, 192)
+    assert bool((got[:, 1:] >= got[:, :-1]).all()), "merged depths are not sorted"
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=3e-5)
+    # the 64 coarse depths survive bit-exactly inside the merged set
+    for r in (0, 7, n - 1):
+        assert set(_bits(z[r]).tolist()) <= set(_bits(got[r]).tolist())
+    # m = 0: the fine pass re-evaluates the coarse depths (reference behaviour for n_fine_samples=0)
+    got0 = K.resample_merge(z.to(DEV), w.to(DEV), torch.zeros(n, 0, device=DEV)).cpu()
+    assert torch.equal(_bits(got0), _bits(z))
+
+
+def test_freq_encode_matches_golden():
+    K = _K()
+    g = golden("units.npz")
+    x = torch.from_numpy(g["enc_x"])
+    for L, key in ((10, "enc10"), (4, "enc4")):
+        got = K.freq_encode(x.to(DEV), L).cpu().numpy()
+        np.testing.assert_allclose(got, g[key], rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------- K2
+def _packed_model(seed=0, sigma_bias=1.0, sigma_gain=5.0):
+    K = _K()
+    coarse, _ = O.init_field_params(seed, sigma_bias, sigma_gain)
+    order = ("l1", "l2", "l3", "l4", "l5", "l6", "l7", "l8", "l9", "l_alpha", "l10", "l11")
+    params = []
+    for nme in order:
+        params += [coarse[nme + ".weight"].to(DEV), coarse[nme + ".bias"].to(DEV)]
+    return coarse, K.pack_model(params)
+
+
+def test_viewdir_term():
+    K = _K()
+    p, packed = _packed_model()
+    gen = torch.Generator().manual_seed(2)
+    d = torch.nn.functional.normalize(torch.randn(500, 3, generator=gen), dim=-1)
+    got = K.viewdir_term(packed, d.to(DEV)).cpu()
+    np.testing.assert_allclose(got.numpy(), vterm_reference(p, d).numpy(), rtol=0, atol=2e-6)
+    enc = O.freq_encode(d, 4)
+    got = K.viewdir_term(packed, enc.to(DEV), embedded=True).cpu()
+    np.testing.assert_allclose(got.numpy(), vterm_reference(p, d).numpy(), rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("rows", [128, 256, 1000, 5 * 256 + 77])
+def test_field_embedded_mode_layers(rows):
+    """Embedded mode feeds the MMA chain exact BF16 inputs, so every layer must match the CPU
+    emulation of the same rounding points to accumulation-order accuracy."""
+    K = _K()
+    p, packed = _packed_model()
+    gen = torch.Generator().manual_seed(rows)
+    pts = torch.randn(rows, 3, generator=gen) * 2.
+    dirs = torch.nn.functional.normalize(torch.randn(rows, 3, generator=gen), dim=-1)
+    x = torch.cat([O.freq_encode(pts, 10), O.freq_encode(dirs, 4)], -1)
+    vt = vterm_reference(p, dirs)
+    xd = x.to(DEV).contiguous()
+    vtd = K.viewdir_term(packed, x[:, 63:].contiguous().to(DEV), embedded=True)
+    for layer in range(10):
+        raw, probe = K.mlp_fwd(packed, K.IN_EMBEDDED, xd, None, rows, 1, vtd, 1, in_stride=90, probe_layer=layer)
+        want_raw, want_act = emulate_field(p, x[:, :63], vt, probe=layer)
+        width = want_act.shape[1]
+        err = (probe.cpu()[:, :width] - want_act).abs().max().item()
+        assert err <= 2e-3, f"layer {layer}: max abs err {err}"
+    err = (raw.cpu() - want_raw).abs().max().item()
+    assert err <= 2e-3, f"raw output: max abs err {err}"
+    # and against the un-rounded fp32 reference network
+    ref = O.field_mlp(p, x)
+    assert (raw.cpu() - ref).abs().max().item() <= 3e-2
+
+
+def test_field_points_and_rays_modes():
+    K = _K()
+    p, packed = _packed_model()
+    gen = torch.Generator().manual_seed(4)
+    n, S = 37, 64
+    rays = torch.zeros(n, 11)
+    rays[:, 0:3] = torch.randn(n, 3, generator=gen)
+    rays[:, 3:6] = torch.randn(n, 3, generator=gen)
+    rays[:, 6], rays[:, 7] = 2., 6.
+    rays[:, 8:11] = torch.nn.functional.normalize(rays[:, 3:6], dim=-1)
+    z = O.coarse_depths(rays[:, 6:7], rays[:, 7:8], S, torch.rand(n, S, generator=gen)).contiguous()
+    pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
+    want = O.query_field(p, pts, rays[:, 8:11])
+    rd, zd = rays.to(DEV), z.to(DEV)
+    vt = K.viewdir_term(packed, rd)
+    raw_rays = K.mlp_fwd(packed, K.IN_RAYS, rd, zd, n * S, S, vt, S).cpu().reshape(n, S, 4)
+    raw_pts = K.mlp_fwd(packed, K.IN_POINTS, pts.reshape(-1, 3).contiguous().to(DEV), None, n * S, S, vt,
+                        S).cpu().reshape(n, S, 4)
+    assert torch.equal(raw_rays, raw_pts), "ray mode must build exactly the points the reference builds"
+    err = (raw_rays - want).abs().max().item()
+    assert err <= 3e-2, f"raw vs fp32 reference: {err}"
+
+
+def test_field_large_coordinates():
+    """The reference's NDC quirk yields |x| up to ~2e8; the encoder must not
+    produce NaNs there and must stay close to the exact encoding."""
+    K = _K()
+    p, packed = _packed_model()
+    pts = torch.tensor([[1e8, -2.3e8, 0.5], [2400., -1300., 7.], [0., 0., 0.]]).repeat(43, 1)
+    dirs = torch.nn.functional.normalize(torch.ones(pts.shape[0], 3), dim=-1)
+    vt = K.viewdir_term(packed, dirs.to(DEV))
+    raw = K.mlp_fwd(packed, K.IN_POINTS, pts.to(DEV), None, pts.shape[0], 1, vt, 1).cpu()
+    assert bool(torch.isfinite(raw).all())
+    x = O.freq_encode(pts, 10)
+    want = emulate_field(p, x, vterm_reference(p, dirs))
+    scale = want.abs().max().item()
+    assert (raw - want).abs().max().item() <= 2e-2 * max(scale, 1.)

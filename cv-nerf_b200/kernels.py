@@ -10,10 +10,33 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, f32c, ptr, stream_of
+from ._lib import f32c, ptr, stream_of
 
 RAY_STRIDE = 11
 IN_RAYS, IN_POINTS, IN_EMBEDDED = 0, 1, 2
+FLOP_PER_SAMPLE = 2 * 593408   # unpadded MACs of one Model.forward row
+
+
+class LaunchStats:
+    """Counts kernel launches made through this module; when ``timed`` is a list, the field
+    kernel additionally brackets itself with CUDA events on its launch stream (bench.py reads
+    them after the timed region -- no synchronisation happens here)."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timed = None
+
+    def reset(self, timed=False):
+        self.launches = 0
+        self.timed = [] if timed else None
+
+
+STATS = LaunchStats()
+
+
+def check(rc, what, launches=1):
+    _lib.check(rc, what)
+    STATS.launches += launches
 
 
 def _ndc_consts(height, width, focal):
@@ -155,7 +178,7 @@ def pack_model(params, out=None):
         out = torch.empty(packed_model_bytes(), dtype=torch.uint8, device=dev)
     arr = (ctypes.c_void_p * 24)(*[ptr(p) for p in params])
     check(lib.nerf_pack_model(arr, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
-          "nerf_pack_model")
+          "nerf_pack_model", launches=2)
     return out
 
 
@@ -191,8 +214,15 @@ def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_
     raw = torch.empty((rows, 4), dtype=torch.float32, device=in0.device)
     st = stream_of(in0)
     if probe_layer is None:
+        ev = None
+        if STATS.timed is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(in0.device))
         check(lib.nerf_mlp_fwd(packed.data_ptr(), mode, ptr(in0), ptr(in1), in_stride, rows, samples_per_ray,
                                ptr(vterm), vterm_div, ptr(raw), None, st), "nerf_mlp_fwd")
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(in0.device))
+            STATS.timed.append((ev[0], ev[1], rows))
         return raw
     probe = torch.zeros((rows, 256), dtype=torch.float32, device=in0.device)
     check(lib.nerf_mlp_fwd_probe(packed.data_ptr(), mode, ptr(in0), ptr(in1), in_stride, rows, samples_per_ray,

@@ -55,6 +55,8 @@ _DEBUG_SIGNATURES = {
     "nerf_mlp_fwd_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int,
                                           ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p,
                                           ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "nerf_mlp_fwd_stats": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_long, ctypes.c_int,
+                                          c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 

@@ -7,17 +7,19 @@
 // Per-sample activations never leave the SM: BF16 activations live in shared memory, FP32
 // accumulators in tensor memory.
 //
-// Structure (one persistent CTA per SM, 320 threads):
-//   warp 0      producer: streams 16 KB weight stages L2 -> smem with cp.async.bulk (TMA engine)
-//               through a 4-deep mbarrier ring, in the order mlp_layout.h stores them;
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16, BF16 -> FP32 in
-//               TMEM) and tcgen05.commit; owns the 512-column TMEM allocation;
-//   warps 2-5   epilogue group X, warps 6-9 epilogue group Y: each group owns one 128-sample
-//               sub-tile (thread = sample row = TMEM lane).  It computes the positional encoding,
-//               and after every layer reads the accumulator (tcgen05.ld), adds bias, applies ReLU,
-//               rounds to BF16 and writes the next layer's A operand back to shared memory in the
-//               UMMA K-major SWIZZLE_128B layout.  sigma (l_alpha) and rgb (l11) are evaluated in
-//               FP32 on CUDA cores from the FP32 accumulators of l8 / l10.
+// Structure (one persistent CTA per SM, 576 threads):
+//   warp 0       producer: streams 32 KB weight slots (one 64-wide K chunk, all 256 output rows)
+//                L2 -> smem with cp.async.bulk (TMA engine) through an mbarrier ring, in the order
+//                mlp_layout.h stores them;
+//   warp 1       MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16, BF16 -> FP32 in
+//                TMEM) and tcgen05.commit; owns the 512-column TMEM allocation;
+//   warps 2-9    epilogue group X, warps 10-17 epilogue group Y.  A group owns one 128-sample
+//                sub-tile; two threads share a sample row (= TMEM lane), each handling half of
+//                the columns.  The group computes the positional encoding, and after every layer
+//                reads the accumulator (tcgen05.ld), adds bias, applies ReLU, rounds to BF16 and
+//                writes the next layer's A operand back to shared memory in the UMMA K-major
+//                SWIZZLE_128B layout.  sigma (l_alpha) and rgb (l11) are evaluated in FP32 on
+//                CUDA cores from the FP32 accumulators of l8 / l10.
 // The two sub-tiles ping-pong: while the tensor core runs layer l of Y, group X runs the epilogue
 // of layer l of X, so MMA and epilogue overlap.
 #include <cuda_bf16.h>
@@ -31,14 +33,32 @@ namespace {
 using namespace nerf;
 
 constexpr int kTileM = 128;
-constexpr int kRing = 4;
-constexpr int kThreads = 320;
+constexpr int kRing = 2;                              // 32 KB weight slots in flight
+constexpr int kMaxRing = 8;
+constexpr int kSlotBytes = 2 * kStageBytes;           // one K chunk, both N halves: [256][64] bf16
+constexpr int kEpiWarpsPerGroup = 8;
+constexpr int kThreads = 64 + 2 * kEpiWarpsPerGroup * 32;   // 576
 constexpr uint32_t kOffA = 0;                         // 2 x [4][128][64] bf16
 constexpr uint32_t kOffPE = 2 * 65536;                // 2 x [128][64] bf16
-constexpr uint32_t kOffW = kOffPE + 2 * 16384;        // kRing x 16 KB
-constexpr uint32_t kOffBar = kOffW + kRing * kStageBytes;
-constexpr uint32_t kSmemBytes = kOffBar + 128 + 1024;  // + barriers + alignment slack
-constexpr uint32_t kIdesc = umma::instr_desc_bf16(128, 128);
+constexpr uint32_t kOffW = kOffPE + 2 * 16384;        // ring x 32 KB
+constexpr uint32_t kOffBar = kOffW + kRing * kSlotBytes;
+constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;  // + barriers + alignment slack
+constexpr uint32_t kIdescN256 = umma::instr_desc_bf16(128, 256);
+constexpr uint32_t kIdescN128 = umma::instr_desc_bf16(128, 128);
+
+// Kernel variants: kRing is the production ring depth.  The experiment variants (debug entry
+// only) change the ring depth; ALIAS additionally places the PE tiles on top of the A tiles to
+// free 32 KB for a deeper ring -- numerically wrong, used only to time the pipeline.
+// EXP (timing experiments, wrong numerics): bit0 skip the A-tile stores, bit1 skip the bias loads,
+// bit2 skip the TMEM loads.
+template <int RING, bool ALIAS, int EXP = 0>
+struct Cfg {
+    static constexpr int ring = RING;
+    static constexpr int exp = EXP;
+    static constexpr uint32_t off_pe = ALIAS ? 0u : kOffPE;
+    static constexpr uint32_t off_w = ALIAS ? kOffPE : kOffW;
+    static_assert(off_w + RING * kSlotBytes <= kOffBar, "ring does not fit");
+};
 
 struct FwdParams {
     const uint8_t* blob;     // packed model
@@ -53,6 +73,7 @@ struct FwdParams {
     float* raw_out;
     float* probe_out;        // debug: [M][256] post-activation of layer probe_layer (or NULL)
     int probe_layer;
+    long long* stats_out;    // debug: [grid][8] cycle counters (or NULL)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -62,50 +83,59 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // ---------------------------------------------------------------------------- input stage
 // Positional encoding of one point, model.py:15-31: [x, sin(2^k x), cos(2^k x)]_{k<10}, 63 wide,
-// written as one 128-byte swizzled row (column 63 = 0).  sin/cos(2^k x) are produced from two
-// accurate sincosf anchors (k = 0 and k = 5) by angle doubling; the accumulated error (<1e-5) is
-// far below the BF16 rounding applied next.
-__device__ __forceinline__ void encode_point(float px, float py, float pz, float (&f)[64]) {
+// stored as one 128-byte swizzled row (column 63 = 0).  The two threads of a row split it:
+// HALF 0 produces columns 0..31 (x and octaves 0..3 plus most of octave 4) from a sincosf anchor
+// at octave 0, HALF 1 columns 32..63 (cos(16 z), octaves 5..9, zero pad) from an anchor at
+// octave 5; the other octaves follow by angle doubling.  The accumulated error (<1e-5) is far
+// below the BF16 rounding applied next.
+template <int HALF>
+__device__ __forceinline__ void encode_half(float px, float py, float pz, float (&f)[32]) {
     const float p[3] = {px, py, pz};
+    if (HALF == 0) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        f[a] = p[a];
-        float s, c;
+        for (int a = 0; a < 3; ++a) {
+            f[a] = p[a];
+            float s, c;
+            sincosf(p[a], &s, &c);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            if (k == 0) sincosf(p[a], &s, &c);
-            else if (k == 5) sincosf(p[a] * 32.f, &s, &c);
-            else {
-                float s2 = 2.f * s * c;
-                float c2 = fmaf(-2.f * s, s, 1.f);
-                s = s2; c = c2;
+            for (int k = 0; k < 5; ++k) {
+                if (k > 0) {
+                    float s2 = 2.f * s * c;
+                    float c2 = fmaf(-2.f * s, s, 1.f);
+                    s = s2; c = c2;
+                }
+                if (3 + 6 * k + a < 32) f[3 + 6 * k + a] = s;
+                if (3 + 6 * k + 3 + a < 32) f[3 + 6 * k + 3 + a] = c;
             }
-            f[3 + 6 * k + a] = s;
-            f[3 + 6 * k + 3 + a] = c;
         }
-    }
-    f[63] = 0.f;
-}
-
-__device__ __forceinline__ void store_row_bf16(uint8_t* tile, int row, const float (&f)[64]) {
+    } else {
+        f[0] = cosf(pz * 16.f);                       // column 32 = cos(2^4 z)
 #pragma unroll
-    for (int c16 = 0; c16 < 8; ++c16) {
-        uint4 q;
-        q.x = pack_bf16x2(f[c16 * 8 + 0], f[c16 * 8 + 1]);
-        q.y = pack_bf16x2(f[c16 * 8 + 2], f[c16 * 8 + 3]);
-        q.z = pack_bf16x2(f[c16 * 8 + 4], f[c16 * 8 + 5]);
-        q.w = pack_bf16x2(f[c16 * 8 + 6], f[c16 * 8 + 7]);
-        *reinterpret_cast<uint4*>(tile + row * 128 + ((c16 ^ (row & 7)) << 4)) = q;
+        for (int a = 0; a < 3; ++a) {
+            float s, c;
+            sincosf(p[a] * 32.f, &s, &c);
+#pragma unroll
+            for (int k = 5; k < 10; ++k) {
+                if (k > 5) {
+                    float s2 = 2.f * s * c;
+                    float c2 = fmaf(-2.f * s, s, 1.f);
+                    s = s2; c = c2;
+                }
+                f[3 + 6 * k + a - 32] = s;
+                f[3 + 6 * k + 3 + a - 32] = c;
+            }
+        }
+        f[31] = 0.f;
     }
 }
 
+template <int HALF>
 __device__ __forceinline__ void input_stage(const FwdParams& P, long grow, uint8_t* pe_tile, int row) {
-    float f[64];
+    float f[32];
     if (P.in_mode == NERF_IN_EMBEDDED) {
-        const float* x = P.in0 + grow * P.in_stride;
+        const float* x = P.in0 + grow * P.in_stride + HALF * 32;
 #pragma unroll
-        for (int c = 0; c < 63; ++c) f[c] = __ldg(x + c);
-        f[63] = 0.f;
+        for (int c = 0; c < 32; ++c) f[c] = (HALF * 32 + c < kPeDim) ? __ldg(x + c) : 0.f;
     } else {
         float px, py, pz;
         if (P.in_mode == NERF_IN_RAYS) {
@@ -119,94 +149,118 @@ __device__ __forceinline__ void input_stage(const FwdParams& P, long grow, uint8
             const float* x = P.in0 + grow * 3;
             px = __ldg(x); py = __ldg(x + 1); pz = __ldg(x + 2);
         }
-        encode_point(px, py, pz, f);
+        encode_half<HALF>(px, py, pz, f);
     }
-    store_row_bf16(pe_tile, row, f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+        o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+        o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+        o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+        const int c16 = HALF * 4 + q;
+        *reinterpret_cast<uint4*>(pe_tile + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
+    }
 }
 
 // ---------------------------------------------------------------------------- epilogues
-// Hidden layer: h = act(acc + bias) -> BF16 -> A tile (in place).  MODE 0: ReLU; 1: ReLU and
-// accumulate the FP32 sigma head (l_alpha) ; 2: no activation (l9).
-template <int MODE, bool PROBE>
-__device__ __forceinline__ void epilogue_hidden(uint32_t tacc, uint8_t* a_tile, int row,
+__device__ __forceinline__ void load_bias16(const float* __restrict__ b, float4 (&dst)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(b) + i);
+}
+
+// Hidden layer, this thread's 128 columns [c0, c0+128): h = act(acc + bias) -> BF16 -> A tile (in
+// place).  MODE 0: ReLU; 1: ReLU and accumulate the FP32 sigma head (l_alpha); 2: no activation
+// (l9).  16 columns per step; the next step's TMEM load and bias loads are in flight while the
+// current step is processed.
+template <int MODE, bool PROBE, int EXP>
+__device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint8_t* a_tile, int row,
                                                 const float* __restrict__ bias,
                                                 const float* __restrict__ walpha, float& sigma,
                                                 float* probe_row) {
-    uint32_t v[2][32];
-    umma::tmem_ld32(tacc, v[0]);
+    uint32_t v[2][16] = {};
+    float4 b[2][4] = {};
+    if (!(EXP & 4)) umma::tmem_ld16(tacc + c0, v[0]);
+    if (!(EXP & 2)) load_bias16(bias + c0, b[0]);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-        umma::tmem_wait_ld();
-        if (it + 1 < 8) umma::tmem_ld32(tacc + (it + 1) * 32, v[(it + 1) & 1]);
-        const uint32_t(&cur)[32] = v[it & 1];
+        const int c = c0 + it * 16;
+        if (it + 1 < 8 && !(EXP & 2)) load_bias16(bias + c + 16, b[(it + 1) & 1]);
+        if (!(EXP & 4)) umma::tmem_wait_ld();
+        if (it + 1 < 8 && !(EXP & 4)) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
+        const uint32_t(&cur)[16] = v[it & 1];
+        const float4(&bc)[4] = b[it & 1];
+        float h[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int c = it * 32 + q * 8;
-            float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
-            float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
-            float h[8];
-            h[0] = __uint_as_float(cur[q * 8 + 0]) + b0.x;
-            h[1] = __uint_as_float(cur[q * 8 + 1]) + b0.y;
-            h[2] = __uint_as_float(cur[q * 8 + 2]) + b0.z;
-            h[3] = __uint_as_float(cur[q * 8 + 3]) + b0.w;
-            h[4] = __uint_as_float(cur[q * 8 + 4]) + b1.x;
-            h[5] = __uint_as_float(cur[q * 8 + 5]) + b1.y;
-            h[6] = __uint_as_float(cur[q * 8 + 6]) + b1.z;
-            h[7] = __uint_as_float(cur[q * 8 + 7]) + b1.w;
-            if (MODE != 2) {
+            h[q * 4 + 0] = __uint_as_float(cur[q * 4 + 0]) + bc[q].x;
+            h[q * 4 + 1] = __uint_as_float(cur[q * 4 + 1]) + bc[q].y;
+            h[q * 4 + 2] = __uint_as_float(cur[q * 4 + 2]) + bc[q].z;
+            h[q * 4 + 3] = __uint_as_float(cur[q * 4 + 3]) + bc[q].w;
+        }
+        if (MODE != 2) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = fmaxf(h[e], 0.f);
-            }
-            if (MODE == 1) {
-                float4 w0 = __ldg(reinterpret_cast<const float4*>(walpha + c));
-                float4 w1 = __ldg(reinterpret_cast<const float4*>(walpha + c + 4));
-                sigma = fmaf(w0.x, h[0], sigma); sigma = fmaf(w0.y, h[1], sigma);
-                sigma = fmaf(w0.z, h[2], sigma); sigma = fmaf(w0.w, h[3], sigma);
-                sigma = fmaf(w1.x, h[4], sigma); sigma = fmaf(w1.y, h[5], sigma);
-                sigma = fmaf(w1.z, h[6], sigma); sigma = fmaf(w1.w, h[7], sigma);
-            }
-            if (PROBE && probe_row) {
+            for (int e = 0; e < 16; ++e) h[e] = fmaxf(h[e], 0.f);
+        }
+        if (MODE == 1) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) probe_row[c + e] = h[e];
+            for (int q = 0; q < 4; ++q) {
+                float4 w = __ldg(reinterpret_cast<const float4*>(walpha + c) + q);
+                sigma = fmaf(w.x, h[q * 4 + 0], sigma); sigma = fmaf(w.y, h[q * 4 + 1], sigma);
+                sigma = fmaf(w.z, h[q * 4 + 2], sigma); sigma = fmaf(w.w, h[q * 4 + 3], sigma);
             }
+        }
+        if (PROBE && probe_row) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) probe_row[c + e] = h[e];
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
             uint4 o;
-            o.x = pack_bf16x2(h[0], h[1]);
-            o.y = pack_bf16x2(h[2], h[3]);
-            o.z = pack_bf16x2(h[4], h[5]);
-            o.w = pack_bf16x2(h[6], h[7]);
-            const int blk = it >> 1, c16 = (it & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(a_tile + blk * 16384 + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
+            o.x = pack_bf16x2(h[q * 8 + 0], h[q * 8 + 1]);
+            o.y = pack_bf16x2(h[q * 8 + 2], h[q * 8 + 3]);
+            o.z = pack_bf16x2(h[q * 8 + 4], h[q * 8 + 5]);
+            o.w = pack_bf16x2(h[q * 8 + 6], h[q * 8 + 7]);
+            const int cc = c + q * 8;
+            const int blk = cc >> 6, c16 = (cc & 63) >> 3;
+            if (!(EXP & 1) || o.x == 0x12345678u)
+                *reinterpret_cast<uint4*>(a_tile + blk * 16384 + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
         }
     }
 }
 
-// l10 (+ hoisted view term, ReLU) and l11 in FP32: returns rgb_raw.
+// l10 (+ hoisted view term, ReLU) and l11 in FP32 over this thread's 64 columns [c0, c0+64):
+// partial rgb_raw.
 template <bool PROBE>
-__device__ __forceinline__ void epilogue_rgb(uint32_t tacc, const float* __restrict__ vt,
+__device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float* __restrict__ vt,
                                              const float* __restrict__ w11, float (&rgb)[3],
                                              float* probe_row) {
-    uint32_t v[2][32];
-    umma::tmem_ld32(tacc, v[0]);
+    uint32_t v[2][16];
+    float4 t[2][4];
+    umma::tmem_ld16(tacc + c0, v[0]);
+    load_bias16(vt + c0, t[0]);
     rgb[0] = rgb[1] = rgb[2] = 0.f;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
+        const int c = c0 + it * 16;
+        if (it + 1 < 4) load_bias16(vt + c + 16, t[(it + 1) & 1]);
         umma::tmem_wait_ld();
-        if (it + 1 < 4) umma::tmem_ld32(tacc + (it + 1) * 32, v[(it + 1) & 1]);
-        const uint32_t(&cur)[32] = v[it & 1];
+        if (it + 1 < 4) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
+        const uint32_t(&cur)[16] = v[it & 1];
+        const float4(&tc)[4] = t[it & 1];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int c = it * 32 + q * 4;
-            float4 t = __ldg(reinterpret_cast<const float4*>(vt + c));
-            float h0 = fmaxf(__uint_as_float(cur[q * 4 + 0]) + t.x, 0.f);
-            float h1 = fmaxf(__uint_as_float(cur[q * 4 + 1]) + t.y, 0.f);
-            float h2 = fmaxf(__uint_as_float(cur[q * 4 + 2]) + t.z, 0.f);
-            float h3 = fmaxf(__uint_as_float(cur[q * 4 + 3]) + t.w, 0.f);
+        for (int q = 0; q < 4; ++q) {
+            float h0 = fmaxf(__uint_as_float(cur[q * 4 + 0]) + tc[q].x, 0.f);
+            float h1 = fmaxf(__uint_as_float(cur[q * 4 + 1]) + tc[q].y, 0.f);
+            float h2 = fmaxf(__uint_as_float(cur[q * 4 + 2]) + tc[q].z, 0.f);
+            float h3 = fmaxf(__uint_as_float(cur[q * 4 + 3]) + tc[q].w, 0.f);
             if (PROBE && probe_row) {
-                probe_row[c] = h0; probe_row[c + 1] = h1; probe_row[c + 2] = h2; probe_row[c + 3] = h3;
+                float* pr = probe_row + c + q * 4;
+                pr[0] = h0; pr[1] = h1; pr[2] = h2; pr[3] = h3;
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                float4 w = __ldg(reinterpret_cast<const float4*>(w11 + k * kL10Out + c));
+                float4 w = __ldg(reinterpret_cast<const float4*>(w11 + k * kL10Out + c) + q);
                 rgb[k] = fmaf(w.x, h0, rgb[k]); rgb[k] = fmaf(w.y, h1, rgb[k]);
                 rgb[k] = fmaf(w.z, h2, rgb[k]); rgb[k] = fmaf(w.w, h3, rgb[k]);
             }
@@ -215,17 +269,21 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, const float* __restr
 }
 
 // ---------------------------------------------------------------------------- kernel
-template <bool PROBE>
+template <bool PROBE, class CFG>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P) {
+    constexpr int kRing = CFG::ring;
+    constexpr uint32_t kOffPE = CFG::off_pe, kOffW = CFG::off_w;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte aligned tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = umma::smem_u32(smem);
-    const uint32_t bar_w_full = sbase + kOffBar;              // [kRing]
-    const uint32_t bar_w_empty = bar_w_full + 8 * kRing;      // [kRing]
-    const uint32_t bar_a_ready = bar_w_empty + 8 * kRing;     // [2]
+    const uint32_t bar_w_full = sbase + kOffBar;              // [kMaxRing]
+    const uint32_t bar_w_empty = bar_w_full + 8 * kMaxRing;   // [kMaxRing]
+    const uint32_t bar_a_ready = bar_w_empty + 8 * kMaxRing;  // [2]
     const uint32_t bar_acc_full = bar_a_ready + 16;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 4));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kMaxRing + 4));
+    long long t_wait0 = 0, t_wait1 = 0, t_begin = 0;
+    if (PROBE) t_begin = clock64();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
@@ -237,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
             umma::mbar_init(bar_w_empty + 8 * s, 1);
         }
         for (int g = 0; g < 2; ++g) {
-            umma::mbar_init(bar_a_ready + 8 * g, kTileM);
+            umma::mbar_init(bar_a_ready + 8 * g, kEpiWarpsPerGroup * 32);
             umma::mbar_init(bar_acc_full + 8 * g, 1);
         }
         umma::fence_barrier_init();
@@ -252,19 +310,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== producer: weight stages, L2 -> smem =====================
+        // ===================== producer: weight slots, L2 -> smem =====================
         if (lane == 0) {
             uint32_t it = 0;
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int first = layer_first_stage(l), cnt = layer_chunks(l) * layer_halves(l);
+                    // one slot = one K chunk with all its N halves (adjacent stages in the blob)
+                    const int first = layer_first_stage(l), chunks = layer_chunks(l);
+                    const uint32_t bytes = layer_halves(l) * kStageBytes;
                     for (int g = 0; g < 2; ++g) {
-                        for (int s = 0; s < cnt; ++s, ++it) {
+                        for (int j = 0; j < chunks; ++j, ++it) {
                             const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
+                            long long t0 = PROBE ? clock64() : 0;
                             umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
-                            umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, kStageBytes);
-                            umma::bulk_g2s(sbase + kOffW + slot * kStageBytes,
-                                           P.blob + (size_t)(first + s) * kStageBytes, kStageBytes,
+                            if (PROBE) t_wait0 += clock64() - t0;
+                            umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
+                            umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
+                                           P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes,
                                            bar_w_full + 8 * slot);
                         }
                     }
@@ -277,9 +339,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
             uint32_t it = 0, n_ready[2] = {0, 0};
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int chunks = layer_chunks(l), halves = layer_halves(l);
+                    const int chunks = layer_chunks(l);
+                    const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
                     for (int g = 0; g < 2; ++g) {
+                        long long t0 = PROBE ? clock64() : 0;
                         umma::mbar_wait(bar_a_ready + 8 * g, n_ready[g] & 1);
+                        if (PROBE) t_wait0 += clock64() - t0;
                         ++n_ready[g];
                         umma::tc_fence_after();
                         const uint32_t d_base = tmem_base + g * 256;
@@ -290,20 +355,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
                             if (l == 0) a_addr = pe_tile;
                             else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
                             else a_addr = a_tile + j * 16384;
-                            for (int h = 0; h < halves; ++h, ++it) {
-                                const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-                                umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                                umma::tc_fence_after();
-                                const uint32_t b_addr = sbase + kOffW + slot * kStageBytes;
+                            const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
+                            ++it;
+                            long long t1 = PROBE ? clock64() : 0;
+                            umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                            if (PROBE) t_wait1 += clock64() - t1;
+                            umma::tc_fence_after();
+                            // B = [N rows][64] K-major; the two 128-row halves are contiguous
+                            const uint32_t b_addr = sbase + kOffW + slot * kSlotBytes;
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {
-                                    umma::mma_bf16_ss(d_base + h * 128,
-                                                      umma::smem_desc_sw128(a_addr + kk * 32),
-                                                      umma::smem_desc_sw128(b_addr + kk * 32), kIdesc,
-                                                      (j > 0 || kk > 0) ? 1u : 0u);
-                                }
-                                umma::mma_commit(bar_w_empty + 8 * slot);
+                            for (int kk = 0; kk < 4; ++kk) {
+                                umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
+                                                  umma::smem_desc_sw128(b_addr + kk * 32), idesc,
+                                                  (j > 0 || kk > 0) ? 1u : 0u);
                             }
+                            umma::mma_commit(bar_w_empty + 8 * slot);
                         }
                         umma::mma_commit(bar_acc_full + 8 * g);
                     }
@@ -312,11 +378,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
         }
     } else {
         // ===================== epilogue groups =====================
-        const int g = (warp - 2) >> 2;
+        const int ew = warp - 2;
+        const int g = ew >> 3;                   // sub-tile / group
+        const int half = (ew >> 2) & 1;          // which half of the columns this thread handles
         const int quad = warp & 3;               // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
+        const uint32_t pair_bar = 1 + g * 4 + quad;   // named barrier of the two warps sharing rows
         uint8_t* a_tile = smem + kOffA + g * 65536;
         uint8_t* pe_tile = smem + kOffPE + g * 16384;
+        // FP32 hand-over slot between the two threads of a row, inside the row's own PE line
+        // (free between l6's MMA and the next tile's encoding)
+        float4* xchg = reinterpret_cast<float4*>(pe_tile + row * 128);
         const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
         const float* tail = reinterpret_cast<const float*>(P.blob + kWeightBytes);
         uint32_t n_full = 0;
@@ -324,26 +396,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
             const long grow_raw = (pair * 2 + g) * kTileM + row;
             const bool valid = grow_raw < P.M;
             const long grow = valid ? grow_raw : P.M - 1;
-            input_stage(P, grow, pe_tile, row);
+            if (half == 0) input_stage<0>(P, grow, pe_tile, row);
+            else input_stage<1>(P, grow, pe_tile, row);
             umma::fence_proxy_async_smem();
             umma::mbar_arrive(bar_a_ready + 8 * g);
             float sigma = 0.f;
             float* probe_row = nullptr;
 #pragma unroll 1
             for (int l = 0; l < kNumMmaLayers; ++l) {
+                long long t0 = PROBE ? clock64() : 0;
                 umma::mbar_wait(bar_acc_full + 8 * g, n_full & 1);
+                if (PROBE) t_wait0 += clock64() - t0;
                 ++n_full;
                 umma::tc_fence_after();
                 if (PROBE) probe_row = (P.probe_out && P.probe_layer == l && valid) ? P.probe_out + grow * 256 : nullptr;
                 if (l < 9) {
                     const float* bias = tail + kTailBias + l * kHidden;
+                    const int c0 = half * 128;
                     if (l == 7) {
-                        sigma = __ldg(tail + kTailBAlpha);
-                        epilogue_hidden<1, PROBE>(tacc, a_tile, row, bias, tail + kTailWAlpha, sigma, probe_row);
+                        epilogue_hidden<1, PROBE, CFG::exp>(tacc, c0, a_tile, row, bias, tail + kTailWAlpha, sigma, probe_row);
                     } else if (l == 8) {
-                        epilogue_hidden<2, PROBE>(tacc, a_tile, row, bias, nullptr, sigma, probe_row);
+                        epilogue_hidden<2, PROBE, CFG::exp>(tacc, c0, a_tile, row, bias, nullptr, sigma, probe_row);
                     } else {
-                        epilogue_hidden<0, PROBE>(tacc, a_tile, row, bias, nullptr, sigma, probe_row);
+                        epilogue_hidden<0, PROBE, CFG::exp>(tacc, c0, a_tile, row, bias, nullptr, sigma, probe_row);
                     }
                     umma::fence_proxy_async_smem();
                     umma::tc_fence_before();
@@ -351,19 +426,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
                 } else {
                     float rgb[3];
                     const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                    epilogue_rgb<PROBE>(tacc, vt, tail + kTailW11, rgb, probe_row);
+                    epilogue_rgb<PROBE>(tacc, half * 64, vt, tail + kTailW11, rgb, probe_row);
                     umma::tc_fence_before();
-                    if (valid) {
-                        float4 o;
-                        o.x = rgb[0] + __ldg(tail + kTailB11 + 0);
-                        o.y = rgb[1] + __ldg(tail + kTailB11 + 1);
-                        o.z = rgb[2] + __ldg(tail + kTailB11 + 2);
-                        o.w = sigma;
-                        reinterpret_cast<float4*>(P.raw_out)[grow] = o;
+                    // combine the two column halves of the row: half 1 hands its partial sums over
+                    if (half == 1) *xchg = make_float4(rgb[0], rgb[1], rgb[2], sigma);
+                    umma::named_bar_sync(pair_bar, 64);
+                    if (half == 0) {
+                        const float4 o2 = *xchg;
+                        if (valid) {
+                            float4 o;
+                            o.x = rgb[0] + o2.x + __ldg(tail + kTailB11 + 0);
+                            o.y = rgb[1] + o2.y + __ldg(tail + kTailB11 + 1);
+                            o.z = rgb[2] + o2.z + __ldg(tail + kTailB11 + 2);
+                            o.w = sigma + o2.w + __ldg(tail + kTailBAlpha);
+                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
+                        }
                     }
+                    // the next tile's encoding overwrites the hand-over slot: wait for the read
+                    umma::named_bar_sync(pair_bar, 64);
                 }
             }
         }
+    }
+    if (PROBE && P.stats_out && lane == 0) {
+        // [0] producer wait-empty, [1] mma wait a_ready, [2] mma wait w_full, [3] epi X wait acc,
+        // [4] epi Y wait acc, [5] total cycles
+        long long* o = P.stats_out + (long)blockIdx.x * 8;
+        const long long total = clock64() - t_begin;
+        if (warp == 0) { o[0] = t_wait0; o[5] = total; }
+        if (warp == 1) { o[1] = t_wait0; o[2] = t_wait1; }
+        if (warp == 2) o[3] = t_wait0;
+        if (warp == 2 + kEpiWarpsPerGroup) o[4] = t_wait0;
     }
     umma::tc_fence_before();
     __syncthreads();
@@ -373,25 +466,51 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
     }
 }
 
-int launch_fwd(const FwdParams& P, bool probe, void* stream) {
+using FwdKernel = void (*)(const FwdParams);
+
+// variant 0 = production; 1 = probe (production config + debug outputs);
+// 2, 3 = pipeline-timing experiments (probe kernels with other ring depths)
+FwdKernel fwd_variant(int v) {
+    switch (v) {
+        case 0: return mlp_fwd_kernel<false, Cfg<kRing, false>>;
+        case 1: return mlp_fwd_kernel<true, Cfg<kRing, false>>;
+        case 2: return mlp_fwd_kernel<true, Cfg<1, false>>;
+        case 3: return mlp_fwd_kernel<true, Cfg<3, true>>;
+        case 4: return mlp_fwd_kernel<true, Cfg<kRing, false, 1>>;
+        case 5: return mlp_fwd_kernel<true, Cfg<kRing, false, 2>>;
+        case 6: return mlp_fwd_kernel<true, Cfg<kRing, false, 4>>;
+        case 7: return mlp_fwd_kernel<true, Cfg<kRing, false, 7>>;
+        default: return nullptr;
+    }
+}
+
+int launch_fwd(const FwdParams& P, int variant, void* stream) {
     static int sm_count = 0;
+    static bool configured[8] = {};
+    FwdKernel k = fwd_variant(variant);
+    if (!k) return nerf::arg_error("nerf_mlp_fwd: variant");
     if (sm_count == 0) {
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) {
             sm_count = 0;
             nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
             return (int)e;
         }
     }
+    if (!configured[variant]) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) {
+            nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured[variant] = true;
+    }
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
     const long n_pairs = (n_tiles + 1) / 2;
     const unsigned grid = (unsigned)(n_pairs < sm_count ? n_pairs : sm_count);
-    if (probe) mlp_fwd_kernel<true><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
-    else mlp_fwd_kernel<false><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    k<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
     return nerf::check_launch("nerf_mlp_fwd");
 }
 
@@ -408,7 +527,7 @@ int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0,
     P.blob = (const uint8_t*)packed;
     P.in_mode = in_mode; P.in0 = in0; P.in1 = in1; P.in_stride = in_stride;
     P.M = M; P.S = S < 1 ? 1 : S; P.vterm = vterm; P.vterm_div = vterm_div; P.raw_out = raw_out;
-    P.probe_out = nullptr; P.probe_layer = -1;
+    P.probe_out = nullptr; P.probe_layer = -1; P.stats_out = nullptr;
     return 0;
 }
 
@@ -422,7 +541,7 @@ extern "C" int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, c
     int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out);
     if (rc) return rc;
     if (M == 0) return 0;
-    return launch_fwd(P, false, stream);
+    return launch_fwd(P, 0, stream);
 }
 
 // Debug entry (tests only): additionally dumps the FP32 post-activation output of MMA layer
@@ -435,7 +554,20 @@ extern "C" int nerf_mlp_fwd_probe(const void* packed, int in_mode, const float* 
     if (rc) return rc;
     if (M == 0) return 0;
     P.probe_out = probe_out; P.probe_layer = probe_layer;
-    return launch_fwd(P, true, stream);
+    return launch_fwd(P, 1, stream);
+}
+
+// Debug entry (tools/gpu_diag.py): run a pipeline variant and collect per-CTA cycle counters
+// (stats_out [148][8] int64).  Variants other than 1 exist to time the pipeline only.
+extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const float* z, long M, int S,
+                                  const float* vterm, float* raw_out, int variant, long long* stats_out,
+                                  void* stream) {
+    FwdParams P;
+    int rc = fill_params(P, packed, NERF_IN_RAYS, rays, z, 0, M, S, vterm, S, raw_out);
+    if (rc) return rc;
+    if (M == 0) return 0;
+    P.stats_out = stats_out;
+    return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }
 
 extern "C" size_t nerf_mlp_act_bytes(long M) { (void)M; return 0; }

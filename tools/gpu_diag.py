@@ -95,11 +95,50 @@ def timing():
               f"({n_rays * S / ms / 1e3:.2f} M samples/s)")
 
 
+def pipeline_stats(variants=(1, 3, 4, 5, 6, 7)):
+    """Per-role wait-cycle breakdown of the field kernel (debug entry nerf_mlp_fwd_stats)."""
+    from cv_nerf_b200 import _lib
+    lib = _lib.load()
+    p, packed = packed_model()
+    n_rays, S = 160000, 192
+    rays = torch.zeros(n_rays, 11, device=DEV)
+    rays[:, 0:3] = torch.randn(n_rays, 3, device=DEV) * .3
+    rays[:, 3:6] = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV), dim=-1)
+    rays[:, 6], rays[:, 7] = 2., 6.
+    rays[:, 8:11] = rays[:, 3:6]
+    z = K.sample_coarse(rays, S)
+    vt = K.viewdir_term(packed, rays)
+    raw = torch.empty(n_rays * S, 4, device=DEV)
+    names = {1: "ring 2x32KB (production layout)", 2: "ring 1x32KB", 3: "ring 3x32KB (PE aliased, timing only)",
+             4: "EXP no A-tile stores", 5: "EXP no bias loads", 6: "EXP no TMEM loads", 7: "EXP none of the three"}
+    st = torch.cuda.current_stream().cuda_stream
+    for v in variants:
+        stats = torch.zeros(148, 8, dtype=torch.int64, device=DEV)
+        for rep in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = lib.nerf_mlp_fwd_stats(packed.data_ptr(), rays.data_ptr(), z.data_ptr(), n_rays * S, S,
+                                        vt.data_ptr(), raw.data_ptr(), v, stats.data_ptr(), st)
+            e1.record()
+            torch.cuda.synchronize()
+            assert rc == 0, lib.nerf_b200_last_error()
+        ms = e0.elapsed_time(e1)
+        s = stats.double().mean(0).cpu()
+        tot = s[5].item()
+        print(f"variant {v} {names.get(v, '')}: {ms:.2f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s | "
+              f"cycles/CTA {tot:.3e}; wait fractions: producer(empty) {s[0] / tot:.2f}  mma(a_ready) {s[1] / tot:.2f}  "
+              f"mma(w_full) {s[2] / tot:.2f}  epiX(acc) {s[3] / tot:.2f}  epiY(acc) {s[4] / tot:.2f}")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=1000)
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--stats", action="store_true")
     a = ap.parse_args()
+    if a.stats:
+        pipeline_stats()
+        sys.exit(0)
     t = time.time()
     print("device:", torch.cuda.get_device_name(0), "SMs", cv_nerf_b200._lib.load().nerf_b200_sm_count())
     ok = layer_report(128) and layer_report(a.rows)

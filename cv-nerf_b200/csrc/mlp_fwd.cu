@@ -42,7 +42,9 @@ constexpr uint32_t kOffA = 0;                         // 2 x [4][128][64] bf16
 constexpr uint32_t kOffPE = 2 * 65536;                // 2 x [128][64] bf16
 constexpr uint32_t kOffW = kOffPE + 2 * 16384;        // ring x 32 KB
 constexpr uint32_t kOffBar = kOffW + kRing * kSlotBytes;
-constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;  // + barriers + alignment slack
+constexpr uint32_t kOffBias = kOffBar + 256;          // 2 x [256] fp32: the current layer's bias, per group
+constexpr uint32_t kSmemBytes = kOffBias + 2 * 1024;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 constexpr uint32_t kIdescN256 = umma::instr_desc_bf16(128, 256);
 constexpr uint32_t kIdescN128 = umma::instr_desc_bf16(128, 128);
 
@@ -77,8 +79,15 @@ struct FwdParams {
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// max(x, 0) folded into the conversion (F2FP.RELU)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 
 // ---------------------------------------------------------------------------- input stage
@@ -168,65 +177,80 @@ __device__ __forceinline__ void load_bias16(const float* __restrict__ b, float4 
 #pragma unroll
     for (int i = 0; i < 4; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(b) + i);
 }
+// 16 floats of the staged bias: warp-uniform LDS.128 (a broadcast costs one wavefront, where a
+// warp-uniform LDG.128 costs four on the same L1 data pipe the tensor core reads its operands through)
+__device__ __forceinline__ void lds_bias16(uint32_t addr, float4 (&dst)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = umma::ld_shared_v4f(addr + i * 16);
+}
 
 // Hidden layer, this thread's 128 columns [c0, c0+128): h = act(acc + bias) -> BF16 -> A tile (in
 // place).  MODE 0: ReLU; 1: ReLU and accumulate the FP32 sigma head (l_alpha); 2: no activation
 // (l9).  16 columns per step; the next step's TMEM load and bias loads are in flight while the
-// current step is processed.
+// current step is processed.  The bias add runs on packed FP32 pairs (FADD2) and the ReLU is
+// folded into the BF16 conversion (F2FP.RELU), so a column costs about one issue slot.
+// row_addr: shared-space address of this row's 128-byte line in block 0 of the A tile;
+// swz = (row & 7) << 4.
 template <int MODE, bool PROBE, int EXP>
-__device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint8_t* a_tile, int row,
-                                                const float* __restrict__ bias,
+__device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
+                                                uint32_t bias_addr,
                                                 const float* __restrict__ walpha, float& sigma,
                                                 float* probe_row) {
     uint32_t v[2][16] = {};
     float4 b[2][4] = {};
+    float2 sig2 = make_float2(0.f, 0.f);
     if (!(EXP & 4)) umma::tmem_ld16(tacc + c0, v[0]);
-    if (!(EXP & 2)) load_bias16(bias + c0, b[0]);
+    if (!(EXP & 2)) lds_bias16(bias_addr + c0 * 4, b[0]);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int c = c0 + it * 16;
-        if (it + 1 < 8 && !(EXP & 2)) load_bias16(bias + c + 16, b[(it + 1) & 1]);
+        if (it + 1 < 8 && !(EXP & 2)) lds_bias16(bias_addr + (c + 16) * 4, b[(it + 1) & 1]);
         if (!(EXP & 4)) umma::tmem_wait_ld();
         if (it + 1 < 8 && !(EXP & 4)) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
         const uint32_t(&cur)[16] = v[it & 1];
         const float4(&bc)[4] = b[it & 1];
-        float h[16];
+        float2 h[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            h[q * 4 + 0] = __uint_as_float(cur[q * 4 + 0]) + bc[q].x;
-            h[q * 4 + 1] = __uint_as_float(cur[q * 4 + 1]) + bc[q].y;
-            h[q * 4 + 2] = __uint_as_float(cur[q * 4 + 2]) + bc[q].z;
-            h[q * 4 + 3] = __uint_as_float(cur[q * 4 + 3]) + bc[q].w;
-        }
-        if (MODE != 2) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) h[e] = fmaxf(h[e], 0.f);
+            h[2 * q] = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 0]), __uint_as_float(cur[q * 4 + 1])),
+                                  make_float2(bc[q].x, bc[q].y));
+            h[2 * q + 1] = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 2]), __uint_as_float(cur[q * 4 + 3])),
+                                      make_float2(bc[q].z, bc[q].w));
         }
         if (MODE == 1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float4 w = __ldg(reinterpret_cast<const float4*>(walpha + c) + q);
-                sigma = fmaf(w.x, h[q * 4 + 0], sigma); sigma = fmaf(w.y, h[q * 4 + 1], sigma);
-                sigma = fmaf(w.z, h[q * 4 + 2], sigma); sigma = fmaf(w.w, h[q * 4 + 3], sigma);
+                const float4 w = __ldg(reinterpret_cast<const float4*>(walpha + c) + q);
+                h[2 * q].x = fmaxf(h[2 * q].x, 0.f); h[2 * q].y = fmaxf(h[2 * q].y, 0.f);
+                h[2 * q + 1].x = fmaxf(h[2 * q + 1].x, 0.f); h[2 * q + 1].y = fmaxf(h[2 * q + 1].y, 0.f);
+                sig2 = __ffma2_rn(make_float2(w.x, w.y), h[2 * q], sig2);
+                sig2 = __ffma2_rn(make_float2(w.z, w.w), h[2 * q + 1], sig2);
             }
         }
         if (PROBE && probe_row) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) probe_row[c + e] = h[e];
+            for (int e = 0; e < 8; ++e) {
+                probe_row[c + 2 * e] = MODE == 0 ? fmaxf(h[e].x, 0.f) : h[e].x;
+                probe_row[c + 2 * e + 1] = MODE == 0 ? fmaxf(h[e].y, 0.f) : h[e].y;
+            }
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(h[q * 8 + 0], h[q * 8 + 1]);
-            o.y = pack_bf16x2(h[q * 8 + 2], h[q * 8 + 3]);
-            o.z = pack_bf16x2(h[q * 8 + 4], h[q * 8 + 5]);
-            o.w = pack_bf16x2(h[q * 8 + 6], h[q * 8 + 7]);
+            uint32_t o0, o1, o2, o3;
+            if (MODE == 0) {
+                o0 = pack_relu_bf16x2(h[q * 4 + 0].x, h[q * 4 + 0].y); o1 = pack_relu_bf16x2(h[q * 4 + 1].x, h[q * 4 + 1].y);
+                o2 = pack_relu_bf16x2(h[q * 4 + 2].x, h[q * 4 + 2].y); o3 = pack_relu_bf16x2(h[q * 4 + 3].x, h[q * 4 + 3].y);
+            } else {
+                o0 = pack_bf16x2(h[q * 4 + 0].x, h[q * 4 + 0].y); o1 = pack_bf16x2(h[q * 4 + 1].x, h[q * 4 + 1].y);
+                o2 = pack_bf16x2(h[q * 4 + 2].x, h[q * 4 + 2].y); o3 = pack_bf16x2(h[q * 4 + 3].x, h[q * 4 + 3].y);
+            }
             const int cc = c + q * 8;
             const int blk = cc >> 6, c16 = (cc & 63) >> 3;
-            if (!(EXP & 1) || o.x == 0x12345678u)
-                *reinterpret_cast<uint4*>(a_tile + blk * 16384 + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
+            if (!(EXP & 1) || o0 == 0x12345678u)
+                umma::st_shared_v4(row_addr + blk * 16384 + ((uint32_t)(c16 << 4) ^ swz), o0, o1, o2, o3);
         }
     }
+    if (MODE == 1) sigma += sig2.x + sig2.y;
 }
 
 // l10 (+ hoisted view term, ReLU) and l11 in FP32 over this thread's 64 columns [c0, c0+64):
@@ -239,7 +263,7 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
     float4 t[2][4];
     umma::tmem_ld16(tacc + c0, v[0]);
     load_bias16(vt + c0, t[0]);
-    rgb[0] = rgb[1] = rgb[2] = 0.f;
+    float2 acc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int c = c0 + it * 16;
@@ -250,22 +274,26 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
         const float4(&tc)[4] = t[it & 1];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float h0 = fmaxf(__uint_as_float(cur[q * 4 + 0]) + tc[q].x, 0.f);
-            float h1 = fmaxf(__uint_as_float(cur[q * 4 + 1]) + tc[q].y, 0.f);
-            float h2 = fmaxf(__uint_as_float(cur[q * 4 + 2]) + tc[q].z, 0.f);
-            float h3 = fmaxf(__uint_as_float(cur[q * 4 + 3]) + tc[q].w, 0.f);
+            float2 ha = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 0]), __uint_as_float(cur[q * 4 + 1])),
+                                   make_float2(tc[q].x, tc[q].y));
+            float2 hb = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 2]), __uint_as_float(cur[q * 4 + 3])),
+                                   make_float2(tc[q].z, tc[q].w));
+            ha.x = fmaxf(ha.x, 0.f); ha.y = fmaxf(ha.y, 0.f);
+            hb.x = fmaxf(hb.x, 0.f); hb.y = fmaxf(hb.y, 0.f);
             if (PROBE && probe_row) {
                 float* pr = probe_row + c + q * 4;
-                pr[0] = h0; pr[1] = h1; pr[2] = h2; pr[3] = h3;
+                pr[0] = ha.x; pr[1] = ha.y; pr[2] = hb.x; pr[3] = hb.y;
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                float4 w = __ldg(reinterpret_cast<const float4*>(w11 + k * kL10Out + c) + q);
-                rgb[k] = fmaf(w.x, h0, rgb[k]); rgb[k] = fmaf(w.y, h1, rgb[k]);
-                rgb[k] = fmaf(w.z, h2, rgb[k]); rgb[k] = fmaf(w.w, h3, rgb[k]);
+                const float4 w = __ldg(reinterpret_cast<const float4*>(w11 + k * kL10Out + c) + q);
+                acc[k] = __ffma2_rn(make_float2(w.x, w.y), ha, acc[k]);
+                acc[k] = __ffma2_rn(make_float2(w.z, w.w), hb, acc[k]);
             }
         }
     }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rgb[k] = acc[k].x + acc[k].y;
 }
 
 // ---------------------------------------------------------------------------- kernel
@@ -273,15 +301,17 @@ template <bool PROBE, class CFG>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P) {
     constexpr int kRing = CFG::ring;
     constexpr uint32_t kOffPE = CFG::off_pe, kOffW = CFG::off_w;
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B atoms need 1024-byte aligned tiles
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // SWIZZLE_128B atoms need 1024-byte aligned tiles (the kernel has no static shared memory, so
+    // the dynamic segment starts at the aligned base of the CTA's window; checked below)
+    extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = umma::smem_u32(smem);
+    if ((sbase & 1023u) != 0) __trap();
     const uint32_t bar_w_full = sbase + kOffBar;              // [kMaxRing]
     const uint32_t bar_w_empty = bar_w_full + 8 * kMaxRing;   // [kMaxRing]
     const uint32_t bar_a_ready = bar_w_empty + 8 * kMaxRing;  // [2]
     const uint32_t bar_acc_full = bar_a_ready + 16;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kMaxRing + 4));
+    static_assert(8 * (2 * kMaxRing + 4) + 4 <= 256, "barrier region");
     long long t_wait0 = 0, t_wait1 = 0, t_begin = 0;
     if (PROBE) t_begin = clock64();
 
@@ -384,7 +414,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
         const int quad = warp & 3;               // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
         const uint32_t pair_bar = 1 + g * 4 + quad;   // named barrier of the two warps sharing rows
-        uint8_t* a_tile = smem + kOffA + g * 65536;
+        const uint32_t group_bar = 9 + g;              // named barrier of the group's 8 warps
+        const int gtid = (ew & 7) * 32 + lane;         // thread index within the group
+        const uint32_t bias_addr = sbase + kOffBias + g * 1024;
+        const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
+        const uint32_t swz = (uint32_t)(row & 7) << 4;
         uint8_t* pe_tile = smem + kOffPE + g * 16384;
         // FP32 hand-over slot between the two threads of a row, inside the row's own PE line
         // (free between l6's MMA and the next tile's encoding)
@@ -392,6 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
         const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
         const float* tail = reinterpret_cast<const float*>(P.blob + kWeightBytes);
         uint32_t n_full = 0;
+        umma::st_shared_f32(bias_addr + gtid * 4, __ldg(tail + kTailBias + gtid));
+        umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
         for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const long grow_raw = (pair * 2 + g) * kTileM + row;
             const bool valid = grow_raw < P.M;
@@ -411,18 +447,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
                 umma::tc_fence_after();
                 if (PROBE) probe_row = (P.probe_out && P.probe_layer == l && valid) ? P.probe_out + grow * 256 : nullptr;
                 if (l < 9) {
-                    const float* bias = tail + kTailBias + l * kHidden;
                     const int c0 = half * 128;
                     if (l == 7) {
-                        epilogue_hidden<1, PROBE, CFG::exp>(tacc, c0, a_tile, row, bias, tail + kTailWAlpha, sigma, probe_row);
+                        epilogue_hidden<1, PROBE, CFG::exp>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row);
                     } else if (l == 8) {
-                        epilogue_hidden<2, PROBE, CFG::exp>(tacc, c0, a_tile, row, bias, nullptr, sigma, probe_row);
+                        epilogue_hidden<2, PROBE, CFG::exp>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row);
                     } else {
-                        epilogue_hidden<0, PROBE, CFG::exp>(tacc, c0, a_tile, row, bias, nullptr, sigma, probe_row);
+                        epilogue_hidden<0, PROBE, CFG::exp>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row);
                     }
                     umma::fence_proxy_async_smem();
                     umma::tc_fence_before();
                     umma::mbar_arrive(bar_a_ready + 8 * g);
+                    // stage the next hidden layer's bias (after l9 comes l1 of the next tile); both
+                    // barriers fall into the time the group would wait for the tensor core anyway
+                    const float bnext = __ldg(tail + kTailBias + (l == 8 ? 0 : l + 1) * kHidden + gtid);
+                    umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+                    umma::st_shared_f32(bias_addr + gtid * 4, bnext);
+                    umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
                 } else {
                     float rgb[3];
                     const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;

@@ -73,8 +73,9 @@ def test_render_matches_reference_fixture(name):
         assert st["max_noflip"] <= RGB_TOL, (name, key, st)
         assert st["n_flip"] <= max(2, got.shape[0] // 20), (name, key, st)
     if name != "lego_test_stock":
-        acc = ref["w_f"].sum(-1).mean().item()
-        assert 0.05 < acc < 1.0, "test scene is degenerate"
+        # opacity accumulated before the far sample (delta_last = 1e10 makes that one absorb the rest)
+        acc = ref["w_f"][:, :-1].sum(-1).mean().item()
+        assert 0.05 < acc < 0.999, f"test scene is degenerate (acc {acc})"
 
 
 def test_render_c2w_full_image_and_row_shards():

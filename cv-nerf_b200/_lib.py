@@ -48,6 +48,19 @@ _SIGNATURES = {
                                     ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
     "nerf_mlp_act_bytes": (ctypes.c_size_t, [ctypes.c_long]),
+    "nerf_packed_model_bwd_bytes": (ctypes.c_size_t, []),
+    "nerf_pack_model_bwd": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p]),
+    "nerf_mlp_dz_bytes": (ctypes.c_size_t, [ctypes.c_long]),
+    "nerf_mlp_bwd_dz": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
+    "nerf_grad_blob_bytes": (ctypes.c_size_t, []),
+    "nerf_mlp_bwd_dw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, c_float_p, ctypes.c_void_p]),
+    "nerf_mlp_bwd_heads": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_long, c_float_p, ctypes.c_void_p]),
+    "nerf_viewdir_term_bwd": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                                             ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "nerf_grad_unpack": (ctypes.c_int, [c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]),
+    "nerf_mse_loss_grad": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_long, c_float_p, c_float_p,
+                                          ctypes.c_void_p]),
 }
 
 # debug / test-only symbols that are exported but not part of the public header

@@ -1,0 +1,374 @@
+// Backward of the field network, part 1: the dZ chain (gradients of every layer's pre-activation).
+//
+// Replaces what autograd does for Model.forward (/root/reference/model.py:77-107) when the train
+// loop calls loss.backward() (/root/reference/main.py:385), restricted to the activations: for
+// each 128-sample tile
+//     dZ10 = (grad_rgb . W11) * [h10 > 0]                        CUDA cores, FP32
+//     dZ9  = dZ10 . W10[:, :256]                                  (l9 has no activation)
+//     dZ8  = (dZ9 . W9 + grad_sigma * w_alpha) * [h8 > 0]
+//     dZi  = (dZ(i+1) . W(i+1)) * [hi > 0]            i = 7..1    (l6 contributes its h5 columns)
+// as BF16 tensor-core contractions against the transposed weights (mlp_bwd_layout.h) with FP32
+// accumulation in tensor memory.  Every dZ tile is dumped to HBM as a tile image (one bulk copy
+// per layer) for the dW contraction (mlp_bwd_dw.cu); the ReLU masks come from the activation
+// record the forward kernel saved.
+//
+// Same warp roles and ping-pong as mlp_fwd.cu: warp 0 streams 32 KB weight slots, warp 1 issues
+// tcgen05.mma (M=128, N=256, K=16), warps 2-9 / 10-17 own one 128-row sub-tile each.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "mlp_bwd_layout.h"
+#include "umma.cuh"
+
+namespace {
+
+using namespace nerf;
+
+constexpr int kTileM = 128;
+constexpr int kRing = 2;
+constexpr int kSlotBytes = 2 * kStageBytes;
+constexpr int kEpiWarpsPerGroup = 8;
+constexpr int kGroupThreads = kEpiWarpsPerGroup * 32;
+constexpr int kThreads = 64 + 2 * kGroupThreads;         // 576
+constexpr uint32_t kOffA = 0;                            // 2 x [4][128][64] bf16
+constexpr uint32_t kOffW = 2 * 65536;                    // ring x 32 KB
+constexpr uint32_t kOffBar = kOffW + kRing * kSlotBytes;
+constexpr uint32_t kOffTail = kOffBar + 256;             // l_alpha.weight [256], l11.weight [3][128] fp32
+constexpr uint32_t kSmemBytes = kOffTail + kBwdTailFloats * 4;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+constexpr uint32_t kIdescN256 = umma::instr_desc_bf16(128, 256);
+
+struct DzParams {
+    const uint8_t* blob;      // transposed weights + tail
+    const float* grad_raw;    // [M][4]
+    const uint8_t* act;       // activation records
+    uint8_t* dz;              // dZ records
+    long M;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// x * [h > 0] on packed BF16 pairs
+__device__ __forceinline__ uint32_t relu_mask_mul(uint32_t x, uint32_t h) {
+    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+    __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&h);
+    __nv_bfloat162 xv = *reinterpret_cast<__nv_bfloat162*>(&x);
+    __nv_bfloat162 r = __hmul2(xv, __hgt2(hv, zero));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// Head stage: dZ10 for this thread's 64 columns [half*64, half*64+64) of its row -> A tile block
+// `half` (K-major operand of the first contraction).
+__device__ __forceinline__ void head_stage(float4 g, const uint8_t* h10_row, uint32_t row_addr, uint32_t swz,
+                                           int half, uint32_t w11_addr) {
+    uint4 hv[8];
+    if (h10_row) {
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) hv[c16] = ldg_nc_v4(h10_row + (((uint32_t)c16 << 4) ^ swz));
+    } else {
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) hv[c16] = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int c16 = 0; c16 < 8; ++c16) {
+        const int c = half * 64 + c16 * 8;
+        float dh[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 w0 = umma::ld_shared_v4f(w11_addr + (0 * kL10Out + c + q * 4) * 4);
+            const float4 w1 = umma::ld_shared_v4f(w11_addr + (1 * kL10Out + c + q * 4) * 4);
+            const float4 w2 = umma::ld_shared_v4f(w11_addr + (2 * kL10Out + c + q * 4) * 4);
+            dh[q * 4 + 0] = fmaf(g.z, w2.x, fmaf(g.y, w1.x, g.x * w0.x));
+            dh[q * 4 + 1] = fmaf(g.z, w2.y, fmaf(g.y, w1.y, g.x * w0.y));
+            dh[q * 4 + 2] = fmaf(g.z, w2.z, fmaf(g.y, w1.z, g.x * w0.z));
+            dh[q * 4 + 3] = fmaf(g.z, w2.w, fmaf(g.y, w1.w, g.x * w0.w));
+        }
+        const uint32_t o0 = relu_mask_mul(pack_bf16x2(dh[0], dh[1]), hv[c16].x);
+        const uint32_t o1 = relu_mask_mul(pack_bf16x2(dh[2], dh[3]), hv[c16].y);
+        const uint32_t o2 = relu_mask_mul(pack_bf16x2(dh[4], dh[5]), hv[c16].z);
+        const uint32_t o3 = relu_mask_mul(pack_bf16x2(dh[6], dh[7]), hv[c16].w);
+        umma::st_shared_v4(row_addr + half * 16384 + (((uint32_t)c16 << 4) ^ swz), o0, o1, o2, o3);
+    }
+}
+
+// One layer's epilogue for this thread's 128 columns [c0, c0+128): accumulator (+ grad_sigma *
+// w_alpha when ADD_SIGMA) -> BF16 -> * [h > 0] (when MASK) -> A tile in place.
+// h_row: this row's line in block 0 of the saved activation (global), or NULL for zero rows.
+template <bool MASK, bool ADD_SIGMA>
+__device__ __forceinline__ void epilogue_dz(uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
+                                            const uint8_t* h_row, float dsig, uint32_t walpha_addr) {
+    constexpr int kAhead = 2;                      // activation loads in flight (x 2 chunks)
+    uint32_t v[2][16];
+    uint4 hm[kAhead + 1][2];
+    auto load_h = [&](int it, uint4 (&dst)[2]) {
+        if (!MASK) return;
+        const int c = c0 + it * 16;
+        const int blk = c >> 6, c16 = (c & 63) >> 3;
+        if (h_row) {
+            dst[0] = ldg_nc_v4(h_row + blk * 16384 + (((uint32_t)c16 << 4) ^ swz));
+            dst[1] = ldg_nc_v4(h_row + blk * 16384 + (((uint32_t)(c16 + 1) << 4) ^ swz));
+        } else {
+            dst[0] = dst[1] = make_uint4(0, 0, 0, 0);
+        }
+    };
+#pragma unroll
+    for (int a = 0; a < kAhead; ++a) load_h(a, hm[a]);
+    umma::tmem_ld16(tacc + c0, v[0]);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int c = c0 + it * 16;
+        if (it + kAhead < 8) load_h(it + kAhead, hm[(it + kAhead) % (kAhead + 1)]);
+        umma::tmem_wait_ld();
+        if (it + 1 < 8) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
+        const uint32_t(&cur)[16] = v[it & 1];
+        float2 d[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = make_float2(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1]));
+        if (ADD_SIGMA) {
+            const float2 s2 = make_float2(dsig, dsig);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w = umma::ld_shared_v4f(walpha_addr + (c + q * 4) * 4);
+                d[2 * q] = __ffma2_rn(s2, make_float2(w.x, w.y), d[2 * q]);
+                d[2 * q + 1] = __ffma2_rn(s2, make_float2(w.z, w.w), d[2 * q + 1]);
+            }
+        }
+        const uint4(&hc)[2] = hm[it % (kAhead + 1)];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            uint32_t o0 = pack_bf16x2(d[q * 4 + 0].x, d[q * 4 + 0].y), o1 = pack_bf16x2(d[q * 4 + 1].x, d[q * 4 + 1].y);
+            uint32_t o2 = pack_bf16x2(d[q * 4 + 2].x, d[q * 4 + 2].y), o3 = pack_bf16x2(d[q * 4 + 3].x, d[q * 4 + 3].y);
+            if (MASK) {
+                o0 = relu_mask_mul(o0, hc[q].x); o1 = relu_mask_mul(o1, hc[q].y);
+                o2 = relu_mask_mul(o2, hc[q].z); o3 = relu_mask_mul(o3, hc[q].w);
+            }
+            const int cc = c + q * 8;
+            const int blk = cc >> 6, c16 = (cc & 63) >> 3;
+            umma::st_shared_v4(row_addr + blk * 16384 + (((uint32_t)c16 << 4) ^ swz), o0, o1, o2, o3);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = umma::smem_u32(smem);
+    if ((sbase & 1023u) != 0) __trap();
+    const uint32_t bar_w_full = sbase + kOffBar;              // [kRing]
+    const uint32_t bar_w_empty = bar_w_full + 8 * kRing;      // [kRing]
+    const uint32_t bar_a_ready = bar_w_empty + 8 * kRing;     // [2]
+    const uint32_t bar_acc_full = bar_a_ready + 16;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kRing + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long n_tiles = (P.M + kTileM - 1) / kTileM;
+    const long n_pairs = (n_tiles + 1) / 2;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kRing; ++s) {
+            umma::mbar_init(bar_w_full + 8 * s, 1);
+            umma::mbar_init(bar_w_empty + 8 * s, 1);
+        }
+        for (int g = 0; g < 2; ++g) {
+            umma::mbar_init(bar_a_ready + 8 * g, kGroupThreads);
+            umma::mbar_init(bar_acc_full + 8 * g, 1);
+        }
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) {
+        umma::tmem_alloc(umma::smem_u32(tmem_slot), 512);
+        umma::tmem_relinquish();
+    }
+    // fp32 tail -> shared memory (read with broadcast LDS by the epilogues)
+    {
+        const float* tail = reinterpret_cast<const float*>(P.blob + kBwdWeightBytes);
+        for (int i = threadIdx.x; i < kBwdTailFloats; i += kThreads)
+            reinterpret_cast<float*>(smem + kOffTail)[i] = __ldg(tail + i);
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer: transposed weight slots, L2 -> smem =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                for (int j = 0; j < kBwdLayers; ++j) {
+                    const int first = bwd_first_stage(j), chunks = bwd_chunks(j);
+                    for (int g = 0; g < 2; ++g) {
+                        for (int c = 0; c < chunks; ++c, ++it) {
+                            const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
+                            umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                            umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, kSlotBytes);
+                            umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
+                                           P.blob + (size_t)first * kStageBytes + (size_t)c * kSlotBytes, kSlotBytes,
+                                           bar_w_full + 8 * slot);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t it = 0, n_ready[2] = {0, 0};
+            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                for (int j = 0; j < kBwdLayers; ++j) {
+                    const int chunks = bwd_chunks(j);
+                    for (int g = 0; g < 2; ++g) {
+                        umma::mbar_wait(bar_a_ready + 8 * g, n_ready[g] & 1);
+                        ++n_ready[g];
+                        umma::tc_fence_after();
+                        const uint32_t d_base = tmem_base + g * 256;
+                        const uint32_t a_tile = sbase + kOffA + g * 65536;
+                        for (int c = 0; c < chunks; ++c) {
+                            const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
+                            ++it;
+                            umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                            umma::tc_fence_after();
+                            const uint32_t a_addr = a_tile + c * 16384;
+                            const uint32_t b_addr = sbase + kOffW + slot * kSlotBytes;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
+                                                  umma::smem_desc_sw128(b_addr + kk * 32), kIdescN256,
+                                                  (c > 0 || kk > 0) ? 1u : 0u);
+                            }
+                            umma::mma_commit(bar_w_empty + 8 * slot);
+                        }
+                        umma::mma_commit(bar_acc_full + 8 * g);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue groups =====================
+        const int ew = warp - 2;
+        const int g = ew >> 3;
+        const int half = (ew >> 2) & 1;
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const uint32_t group_bar = 1 + g;
+        const int gtid = (ew & 7) * 32 + lane;
+        const uint32_t a_tile_addr = sbase + kOffA + g * 65536;
+        const uint32_t a_row_addr = a_tile_addr + row * 128;
+        const uint32_t swz = (uint32_t)(row & 7) << 4;
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
+        const uint32_t walpha_addr = sbase + kOffTail + kBwdTailWAlpha * 4;
+        const uint32_t w11_addr = sbase + kOffTail + kBwdTailW11 * 4;
+        uint32_t n_full = 0;
+        for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            const long tile = pair * 2 + g;
+            const bool tile_ok = tile < n_tiles;
+            const long grow = tile * kTileM + row;
+            const bool valid = grow < P.M;
+            const uint8_t* act_tile = P.act + (size_t)tile * kActTileBytes;
+            uint8_t* dz_tile = P.dz + (size_t)tile * kDzTileBytes;
+            const bool saver = gtid == 0 && tile_ok;
+            // rows past M carry a zero gradient, so their (duplicated) activations never reach dW
+            const float4 graw = valid ? __ldg(reinterpret_cast<const float4*>(P.grad_raw) + grow)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            head_stage(graw, tile_ok ? act_tile + kActH10 + half * 16384 + row * 128 : nullptr, a_row_addr, swz, half,
+                       w11_addr);
+            umma::fence_proxy_async_smem();
+            umma::mbar_arrive(bar_a_ready + 8 * g);
+            umma::named_bar_sync(group_bar, kGroupThreads);
+            if (gtid == 0) {
+                if (saver) {
+                    umma::bulk_s2g(dz_tile + kDz10, a_tile_addr, 32768);
+                    umma::bulk_commit();
+                }
+                umma::bulk_wait_read0();
+            }
+            umma::named_bar_sync(group_bar, kGroupThreads);
+#pragma unroll 1
+            for (int j = 0; j < kBwdLayers; ++j) {
+                umma::mbar_wait(bar_acc_full + 8 * g, n_full & 1);
+                ++n_full;
+                umma::tc_fence_after();
+                const int i = 9 - j;               // this epilogue produces dZ_i
+                const uint8_t* h_row = tile_ok ? act_tile + act_hidden(i) + row * 128 : nullptr;
+                const int c0 = half * 128;
+                if (j == 0) {
+                    epilogue_dz<false, false>(tacc, c0, a_row_addr, swz, nullptr, 0.f, walpha_addr);
+                } else if (j == 1) {
+                    epilogue_dz<true, true>(tacc, c0, a_row_addr, swz, h_row, graw.w, walpha_addr);
+                } else {
+                    epilogue_dz<true, false>(tacc, c0, a_row_addr, swz, h_row, 0.f, walpha_addr);
+                }
+                umma::fence_proxy_async_smem();
+                umma::tc_fence_before();
+                if (j + 1 < kBwdLayers) umma::mbar_arrive(bar_a_ready + 8 * g);
+                umma::named_bar_sync(group_bar, kGroupThreads);
+                if (gtid == 0) {
+                    if (saver) {
+                        umma::bulk_s2g(dz_tile + dz_hidden(i), a_tile_addr, 65536);
+                        umma::bulk_commit();
+                    }
+                    // the copy must have read the tile before the next epilogue / head stage rewrites it
+                    umma::bulk_wait_read0();
+                }
+                umma::named_bar_sync(group_bar, kGroupThreads);
+            }
+        }
+        if (gtid == 0) umma::bulk_wait_all();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+extern "C" size_t nerf_mlp_dz_bytes(long M) {
+    return M <= 0 ? 0 : (size_t)((M + kTileM - 1) / kTileM) * nerf::kDzTileBytes;
+}
+
+extern "C" int nerf_mlp_bwd_dz(const void* packed_bwd, const float* grad_raw, const void* act_save, long M,
+                               void* dz_out, void* stream) {
+    if (M < 0 || (M > 0 && (!packed_bwd || !grad_raw || !act_save || !dz_out))) return nerf::arg_error("nerf_mlp_bwd_dz");
+    if (M == 0) return 0;
+    if (((uintptr_t)act_save | (uintptr_t)dz_out | (uintptr_t)grad_raw) & 15)
+        return nerf::arg_error("nerf_mlp_bwd_dz: buffers must be 16-byte aligned");
+    static int sm_count = 0;
+    static bool configured = false;
+    if (sm_count == 0) {
+        sm_count = nerf_b200_sm_count();
+        if (sm_count <= 0) {
+            sm_count = 0;
+            nerf::set_last_error("nerf_mlp_bwd_dz: no CUDA device");
+            return (int)cudaErrorNoDevice;
+        }
+    }
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_bwd_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) {
+            nerf::set_last_error("nerf_mlp_bwd_dz setup: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    DzParams P;
+    P.blob = (const uint8_t*)packed_bwd; P.grad_raw = grad_raw; P.act = (const uint8_t*)act_save;
+    P.dz = (uint8_t*)dz_out; P.M = M;
+    const long n_pairs = ((M + kTileM - 1) / kTileM + 1) / 2;
+    const unsigned grid = (unsigned)(n_pairs < sm_count ? n_pairs : sm_count);
+    mlp_bwd_dz_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    return nerf::check_launch("nerf_mlp_bwd_dz");
+}

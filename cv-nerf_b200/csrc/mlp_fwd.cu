@@ -25,6 +25,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "mlp_bwd_layout.h"
 #include "mlp_layout.h"
 #include "umma.cuh"
 
@@ -76,6 +77,7 @@ struct FwdParams {
     float* probe_out;        // debug: [M][256] post-activation of layer probe_layer (or NULL)
     int probe_layer;
     long long* stats_out;    // debug: [grid][8] cycle counters (or NULL)
+    uint8_t* act_save;       // training: activation records, kActTileBytes per 128-row tile (or NULL)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -255,10 +257,11 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t 
 
 // l10 (+ hoisted view term, ReLU) and l11 in FP32 over this thread's 64 columns [c0, c0+64):
 // partial rgb_raw.
-template <bool PROBE>
+// SAVE: h10 (post-ReLU, BF16) is written to blocks 0..1 of the A tile for the activation record.
+template <bool PROBE, bool SAVE>
 __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float* __restrict__ vt,
                                              const float* __restrict__ w11, float (&rgb)[3],
-                                             float* probe_row) {
+                                             float* probe_row, uint32_t row_addr, uint32_t swz) {
     uint32_t v[2][16];
     float4 t[2][4];
     umma::tmem_ld16(tacc + c0, v[0]);
@@ -272,6 +275,7 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
         if (it + 1 < 4) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
         const uint32_t(&cur)[16] = v[it & 1];
         const float4(&tc)[4] = t[it & 1];
+        uint32_t pk[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float2 ha = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 0]), __uint_as_float(cur[q * 4 + 1])),
@@ -290,6 +294,19 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
                 acc[k] = __ffma2_rn(make_float2(w.x, w.y), ha, acc[k]);
                 acc[k] = __ffma2_rn(make_float2(w.z, w.w), hb, acc[k]);
             }
+            if (SAVE) {
+                pk[q * 2 + 0] = pack_bf16x2(ha.x, ha.y);
+                pk[q * 2 + 1] = pack_bf16x2(hb.x, hb.y);
+            }
+        }
+        if (SAVE) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int cc = c + q * 8;
+                const int blk = cc >> 6, c16 = (cc & 63) >> 3;
+                umma::st_shared_v4(row_addr + blk * 16384 + ((uint32_t)(c16 << 4) ^ swz), pk[q * 4 + 0], pk[q * 4 + 1],
+                                   pk[q * 4 + 2], pk[q * 4 + 3]);
+            }
         }
     }
 #pragma unroll
@@ -297,7 +314,7 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
 }
 
 // ---------------------------------------------------------------------------- kernel
-template <bool PROBE, class CFG>
+template <bool PROBE, class CFG, bool SAVE = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P) {
     constexpr int kRing = CFG::ring;
     constexpr uint32_t kOffPE = CFG::off_pe, kOffW = CFG::off_w;
@@ -436,6 +453,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
             else input_stage<1>(P, grow, pe_tile, row);
             umma::fence_proxy_async_smem();
             umma::mbar_arrive(bar_a_ready + 8 * g);
+            uint8_t* act_tile = nullptr;
+            if (SAVE) {
+                const long tile = pair * 2 + g;
+                const bool saver = gtid == 0 && tile < n_tiles;
+                act_tile = saver ? P.act_save + (size_t)tile * kActTileBytes : nullptr;
+                // the previous tile's h10 copy must have left the A tile before l1's epilogue
+                // rewrites it; every thread passes the barrier after thread 0 has seen that
+                if (gtid == 0) umma::bulk_wait_read0();
+                umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+                if (act_tile) {
+                    umma::bulk_s2g(act_tile + kActPE, sbase + kOffPE + g * 16384, 16384);
+                    umma::bulk_commit();
+                }
+            }
             float sigma = 0.f;
             float* probe_row = nullptr;
 #pragma unroll 1
@@ -462,13 +493,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
                     // barriers fall into the time the group would wait for the tensor core anyway
                     const float bnext = __ldg(tail + kTailBias + (l == 8 ? 0 : l + 1) * kHidden + gtid);
                     umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+                    if (SAVE && gtid == 0) {
+                        // activation record: h_{l+1} (l9's output for l == 8) straight from the A tile;
+                        // the copy must have read the tile before the next epilogue overwrites it
+                        if (act_tile) {
+                            umma::bulk_s2g(act_tile + act_hidden(l + 1), sbase + kOffA + g * 65536, 65536);
+                            umma::bulk_commit();
+                        }
+                        umma::bulk_wait_read0();
+                    }
                     umma::st_shared_f32(bias_addr + gtid * 4, bnext);
                     umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
                 } else {
                     float rgb[3];
                     const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                    epilogue_rgb<PROBE>(tacc, half * 64, vt, tail + kTailW11, rgb, probe_row);
+                    epilogue_rgb<PROBE, SAVE>(tacc, half * 64, vt, tail + kTailW11, rgb, probe_row, a_row_addr, swz);
                     umma::tc_fence_before();
+                    if (SAVE) {
+                        umma::fence_proxy_async_smem();
+                        umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+                        if (act_tile) {
+                            umma::bulk_s2g(act_tile + kActH10, sbase + kOffA + g * 65536, 32768);
+                            umma::bulk_commit();
+                        }
+                    }
                     // combine the two column halves of the row: half 1 hands its partial sums over
                     if (half == 1) *xchg = make_float4(rgb[0], rgb[1], rgb[2], sigma);
                     umma::named_bar_sync(pair_bar, 64);
@@ -488,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
                 }
             }
         }
+        if (SAVE && gtid == 0) umma::bulk_wait_all();
     }
     if (PROBE && P.stats_out && lane == 0) {
         // [0] producer wait-empty, [1] mma wait a_ready, [2] mma wait w_full, [3] epi X wait acc,
@@ -521,13 +570,14 @@ FwdKernel fwd_variant(int v) {
         case 5: return mlp_fwd_kernel<true, Cfg<kRing, false, 2>>;
         case 6: return mlp_fwd_kernel<true, Cfg<kRing, false, 4>>;
         case 7: return mlp_fwd_kernel<true, Cfg<kRing, false, 7>>;
+        case 8: return mlp_fwd_kernel<false, Cfg<kRing, false>, true>;   // training: saves activations
         default: return nullptr;
     }
 }
 
 int launch_fwd(const FwdParams& P, int variant, void* stream) {
     static int sm_count = 0;
-    static bool configured[8] = {};
+    static bool configured[9] = {};
     FwdKernel k = fwd_variant(variant);
     if (!k) return nerf::arg_error("nerf_mlp_fwd: variant");
     if (sm_count == 0) {
@@ -568,7 +618,7 @@ int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0,
     P.blob = (const uint8_t*)packed;
     P.in_mode = in_mode; P.in0 = in0; P.in1 = in1; P.in_stride = in_stride;
     P.M = M; P.S = S < 1 ? 1 : S; P.vterm = vterm; P.vterm_div = vterm_div; P.raw_out = raw_out;
-    P.probe_out = nullptr; P.probe_layer = -1; P.stats_out = nullptr;
+    P.probe_out = nullptr; P.probe_layer = -1; P.stats_out = nullptr; P.act_save = nullptr;
     return 0;
 }
 
@@ -577,12 +627,13 @@ int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0,
 extern "C" int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, const float* in1,
                             int in_stride, long M, int S, const float* vterm, int vterm_div,
                             float* raw_out, void* act_save, void* stream) {
-    if (act_save) { nerf::set_last_error("nerf_mlp_fwd: act_save not supported by this entry"); return NERF_ERR_UNSUPPORTED; }
     FwdParams P;
     int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out);
     if (rc) return rc;
     if (M == 0) return 0;
-    return launch_fwd(P, 0, stream);
+    if (act_save && ((uintptr_t)act_save & 15)) return nerf::arg_error("nerf_mlp_fwd: act_save must be 16-byte aligned");
+    P.act_save = (uint8_t*)act_save;
+    return launch_fwd(P, act_save ? 8 : 0, stream);
 }
 
 // Debug entry (tests only): additionally dumps the FP32 post-activation output of MMA layer
@@ -611,4 +662,6 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
     return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }
 
-extern "C" size_t nerf_mlp_act_bytes(long M) { (void)M; return 0; }
+extern "C" size_t nerf_mlp_act_bytes(long M) {
+    return M <= 0 ? 0 : (size_t)((M + kTileM - 1) / kTileM) * nerf::kActTileBytes;
+}

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "mlp_bwd_layout.h"
 #include "mlp_layout.h"
 
 namespace {
@@ -72,6 +73,39 @@ __global__ void pack_weights_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
     q.z = (uint32_t)__bfloat16_as_ushort(v[4]) | ((uint32_t)__bfloat16_as_ushort(v[5]) << 16);
     q.w = (uint32_t)__bfloat16_as_ushort(v[6]) | ((uint32_t)__bfloat16_as_ushort(v[7]) << 16);
     *reinterpret_cast<uint4*>(blob + (size_t)stage * kStageBytes + swz128_offset(r, c16 * 8)) = q;
+}
+
+// Transposed weights for the dZ chain (mlp_bwd_layout.h): stage row = input feature n, stage
+// column = output feature k, value W[k][col_off + n].
+__global__ void pack_weights_bwd_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= kBwdStages * kStageRows * 8) return;
+    const int stage = gid / (kStageRows * 8);
+    const int r = (gid / 8) % kStageRows;
+    const int c16 = gid % 8;
+    const int j = stage < 4 ? 0 : 1 + (stage - 4) / 8;
+    const int local = stage - bwd_first_stage(j);
+    const int chunk = local / 2, half = local % 2;
+    const int pi = j == 0 ? 10 : 9 - j;                 // l10, l9, l8, l7, l6, l5, l4, l3, l2
+    const int ld = pi == 10 ? 283 : (pi == 5 ? 319 : 256);
+    const int col_off = pi == 5 ? kPeDim : 0;           // l6: the h5 columns follow the 63 PE columns
+    const float* W = p.w[pi];
+    const int n = half * kStageRows + r;
+    uint32_t q[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int k = chunk * 64 + c16 * 8 + 2 * e;
+        __nv_bfloat162 h = __floats2bfloat162_rn(W[(size_t)k * ld + col_off + n], W[(size_t)(k + 1) * ld + col_off + n]);
+        q[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(blob + (size_t)stage * kStageBytes + swz128_offset(r, c16 * 8)) =
+        make_uint4(q[0], q[1], q[2], q[3]);
+}
+
+__global__ void pack_tail_bwd_kernel(ParamPtrs p, float* __restrict__ tail) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kBwdTailFloats) return;
+    tail[i] = i < kBwdTailW11 ? p.w[9][i] : p.w[11][i - kBwdTailW11];
 }
 
 __global__ void pack_tail_kernel(ParamPtrs p, float* __restrict__ tail) {
@@ -171,6 +205,24 @@ extern "C" int nerf_pack_model(const float* const* host_params, void* packed_out
     pack_tail_kernel<<<nerf::blocks_for(kTailFloats, 256), 256, 0, st>>>(
         p, (float*)((uint8_t*)packed_out + kWeightBytes));
     return nerf::check_launch("nerf_pack_model");
+}
+
+extern "C" size_t nerf_packed_model_bwd_bytes(void) { return nerf::kBwdPackedBytes; }
+
+extern "C" int nerf_pack_model_bwd(const float* const* host_params, void* packed_out, void* stream) {
+    if (!host_params || !packed_out) return nerf::arg_error("nerf_pack_model_bwd");
+    ParamPtrs p;
+    for (int i = 0; i < 12; ++i) {
+        p.w[i] = host_params[2 * i];
+        p.b[i] = host_params[2 * i + 1];
+        if (!p.w[i] || !p.b[i]) return nerf::arg_error("nerf_pack_model_bwd: null parameter");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int n = kBwdStages * kStageRows * 8;
+    pack_weights_bwd_kernel<<<nerf::blocks_for(n, 256), 256, 0, st>>>(p, (uint8_t*)packed_out);
+    pack_tail_bwd_kernel<<<nerf::blocks_for(kBwdTailFloats, 256), 256, 0, st>>>(
+        p, (float*)((uint8_t*)packed_out + kBwdWeightBytes));
+    return nerf::check_launch("nerf_pack_model_bwd");
 }
 
 extern "C" int nerf_viewdir_term(const void* packed, const float* dirs, int dir_stride, int embedded,

@@ -89,6 +89,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
         : "memory");
 }
 
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed entirely (writes visible)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------ TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
@@ -137,6 +149,15 @@ __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
     return r;
 }
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
+}
+// fire-and-forget FP32 vector add into global memory (one L2 atomic per 16 bytes)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -159,11 +180,29 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Same, MN-major operand (the layout of a K-major tile read "sideways"): the image is
+// [K rows][64 MN elements] with 128-byte rows; 8 K rows (one swizzle atom) are SBO = 1024 B
+// apart, successive groups of 64 MN elements are LBO bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 // Instruction descriptor for kind::f16: BF16 x BF16 -> FP32, both operands K-major.
 // bits [4,6) D format (1 = F32), [7,10) A format (1 = BF16), [10,13) B format (1 = BF16),
 // bit 15 / 16 A / B major (0 = K), [17,23) N >> 3, [24,29) M >> 4.
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// both operands MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t instr_desc_bf16_mn(int M, int N) {
+    return instr_desc_bf16(M, N) | (1u << 15) | (1u << 16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.

@@ -208,8 +208,9 @@ def freq_encode(x, n_freq):
 
 
 def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_stride=0,
-            probe_layer=None):
-    """-> raw [rows,4] (and the probed layer's FP32 activations when probe_layer is given)."""
+            probe_layer=None, act_save=None):
+    """-> raw [rows,4] (and the probed layer's FP32 activations when probe_layer is given).
+    act_save: uint8 buffer of act_bytes(rows) that receives the activation records (training)."""
     lib = _lib.load()
     raw = torch.empty((rows, 4), dtype=torch.float32, device=in0.device)
     st = stream_of(in0)
@@ -219,7 +220,8 @@ def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream(in0.device))
         check(lib.nerf_mlp_fwd(packed.data_ptr(), mode, ptr(in0), ptr(in1), in_stride, rows, samples_per_ray,
-                               ptr(vterm), vterm_div, ptr(raw), None, st), "nerf_mlp_fwd")
+                               ptr(vterm), vterm_div, ptr(raw), None if act_save is None else act_save.data_ptr(),
+                               st), "nerf_mlp_fwd")
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(in0.device))
             STATS.timed.append((ev[0], ev[1], rows))
@@ -229,3 +231,85 @@ def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_
                                  ptr(vterm), vterm_div, ptr(raw), probe_layer, ptr(probe), st),
           "nerf_mlp_fwd_probe")
     return raw, probe
+
+
+# ---------------------------------------------------------------------- training (backward)
+GRAD_BLOB_FLOATS = None
+
+
+def act_bytes(rows):
+    return int(_lib.load().nerf_mlp_act_bytes(rows))
+
+
+def dz_bytes(rows):
+    return int(_lib.load().nerf_mlp_dz_bytes(rows))
+
+
+def grad_blob_floats():
+    global GRAD_BLOB_FLOATS
+    if GRAD_BLOB_FLOATS is None:
+        GRAD_BLOB_FLOATS = int(_lib.load().nerf_grad_blob_bytes()) // 4
+    return GRAD_BLOB_FLOATS
+
+
+def pack_model_bwd(params, out=None):
+    """Transposed BF16 weights (+ fp32 heads) for the dZ chain."""
+    lib = _lib.load()
+    params = [f32c(p.detach()) for p in params]
+    assert len(params) == 24
+    dev = params[0].device
+    if out is None:
+        out = torch.empty(int(lib.nerf_packed_model_bwd_bytes()), dtype=torch.uint8, device=dev)
+    arr = (ctypes.c_void_p * 24)(*[ptr(p) for p in params])
+    check(lib.nerf_pack_model_bwd(arr, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+          "nerf_pack_model_bwd", launches=2)
+    return out
+
+
+def mlp_bwd_dz(packed_bwd, grad_raw, act, rows, dz=None):
+    lib = _lib.load()
+    grad_raw = f32c(grad_raw)
+    if dz is None:
+        dz = torch.empty(dz_bytes(rows), dtype=torch.uint8, device=grad_raw.device)
+    check(lib.nerf_mlp_bwd_dz(packed_bwd.data_ptr(), ptr(grad_raw), act.data_ptr(), rows, dz.data_ptr(),
+                              stream_of(grad_raw)), "nerf_mlp_bwd_dz")
+    return dz
+
+
+def mlp_bwd_params(act, dz, grad_raw, rows, dirs, vterm_div, embedded, blob):
+    """dW/db of every layer accumulated into the fp32 gradient blob (3 launches)."""
+    lib = _lib.load()
+    grad_raw = f32c(grad_raw)
+    st = stream_of(grad_raw)
+    check(lib.nerf_mlp_bwd_dw(act.data_ptr(), dz.data_ptr(), rows, ptr(blob), st), "nerf_mlp_bwd_dw")
+    check(lib.nerf_mlp_bwd_heads(act.data_ptr(), ptr(grad_raw), rows, ptr(blob), st), "nerf_mlp_bwd_heads")
+    if not embedded and dirs.shape[-1] == RAY_STRIDE:
+        dptr, stride = dirs.data_ptr() + 32, RAY_STRIDE
+    else:
+        dirs = f32c(dirs)
+        dptr, stride = dirs.data_ptr(), dirs.shape[-1]
+    check(lib.nerf_viewdir_term_bwd(dz.data_ptr(), dptr, stride, int(embedded), rows, vterm_div, ptr(blob), st),
+          "nerf_viewdir_term_bwd")
+    return blob
+
+
+def grad_unpack(blob, grads, accumulate=False):
+    """Gradient blob -> 24 tensors shaped like Model.parameters() (registration order)."""
+    lib = _lib.load()
+    assert len(grads) == 24 and all(g.is_contiguous() and g.dtype == torch.float32 for g in grads)
+    arr = (ctypes.c_void_p * 24)(*[ptr(g) for g in grads])
+    check(lib.nerf_grad_unpack(ptr(blob), arr, int(accumulate), stream_of(blob)), "nerf_grad_unpack")
+    return grads
+
+
+def mse_loss_grad(x, target, want_grad=True, loss=None):
+    """mean((x-target)^2) accumulated into `loss` (1-element tensor) and its gradient."""
+    lib = _lib.load()
+    x, target = f32c(x), f32c(target, x.device)
+    assert x.shape == target.shape
+    if loss is None:
+        loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+    grad = torch.empty_like(x) if want_grad else None
+    check(lib.nerf_mse_loss_grad(ptr(x), ptr(target), x.numel(), ptr(grad), ptr(loss), stream_of(x)),
+          "nerf_mse_loss_grad")
+    return loss, grad

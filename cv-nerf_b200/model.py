@@ -41,13 +41,18 @@ class _FieldFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, spec, *params):
-        raw = model._forward_raw(spec)
-        ctx.model, ctx.spec = model, spec
+        act = torch.empty(K.act_bytes(spec["rows"]), dtype=torch.uint8, device=spec["in0"].device)
+        raw = model._forward_raw(spec, act_save=act)
+        ctx.model, ctx.spec, ctx.act = model, spec, act
+        # the transposed weights must be the ones this forward used (an optimizer step may run
+        # before backward in exotic loops); packing is one small kernel
+        ctx.packed_bwd = model.packed_bwd()
         return raw
 
     @staticmethod
     def backward(ctx, grad_raw):
-        grads = ctx.model._backward_raw(ctx.spec, grad_raw.contiguous())
+        grads = ctx.model._backward_raw(ctx.spec, ctx.act, ctx.packed_bwd, grad_raw.contiguous())
+        ctx.act = None
         return (None, None) + tuple(grads)
 
 
@@ -75,6 +80,8 @@ class Model(nn.Module):
         self.l11 = nn.Linear(128, 3)
         self._packed = None
         self._packed_key = None
+        self._packed_bwd = None
+        self._packed_bwd_key = None
 
     @staticmethod
     def _encoding_dim(num_comp, L):
@@ -101,15 +108,42 @@ class Model(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def packed_bwd(self):
+        """Transposed BF16 weights for the backward dZ chain (same caching rule as packed())."""
+        params = self.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed_bwd is None or key != self._packed_bwd_key:
+            if not params[0].is_cuda:
+                raise NerfB200Error("Model parameters must live on a CUDA device; there is no CPU fallback")
+            self._packed_bwd = K.pack_model_bwd(params)   # fresh buffer: an in-flight backward may hold the old one
+            self._packed_bwd_key = key
+        return self._packed_bwd
+
     # ------------------------------------------------------------------ kernels
-    def _forward_raw(self, spec):
+    def _forward_raw(self, spec, act_save=None):
         packed = self.packed()
         vterm = K.viewdir_term(packed, spec["dirs"], embedded=spec.get("dirs_embedded", False))
         return K.mlp_fwd(packed, spec["mode"], spec["in0"], spec.get("in1"), spec["rows"],
-                         spec.get("samples", 1), vterm, spec["vterm_div"], spec.get("in_stride", 0))
+                         spec.get("samples", 1), vterm, spec["vterm_div"], spec.get("in_stride", 0),
+                         act_save=act_save)
 
-    def _backward_raw(self, spec, grad_raw):
-        raise NotImplementedError("field-network backward kernel is not built yet")
+    def _backward_blob(self, spec, act, packed_bwd, grad_raw, blob):
+        """grad_raw [rows,4] -> parameter gradients accumulated into the fp32 blob (see
+        csrc/mlp_bwd_layout.h): dZ chain, then dW/db contractions."""
+        rows = spec["rows"]
+        dz = K.mlp_bwd_dz(packed_bwd, grad_raw.reshape(rows, 4), act, rows)
+        K.mlp_bwd_params(act, dz, grad_raw.reshape(rows, 4), rows, spec["dirs"], spec["vterm_div"],
+                         spec.get("dirs_embedded", False), blob)
+        return blob
+
+    def _backward_raw(self, spec, act, packed_bwd, grad_raw):
+        dev = grad_raw.device
+        blob = torch.zeros(K.grad_blob_floats(), dtype=torch.float32, device=dev)
+        self._backward_blob(spec, act, packed_bwd, grad_raw, blob)
+        grads = [torch.empty_like(p) for p in self.ordered_params()]
+        K.grad_unpack(blob, grads)
+        # autograd wants them in the order the parameters were passed: ordered_params()
+        return grads
 
     def field(self, spec):
         """Evaluate the network for an input spec; differentiable w.r.t. the parameters."""

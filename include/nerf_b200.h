@@ -126,6 +126,34 @@ int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, const float*
 
 size_t nerf_mlp_act_bytes(long M);
 
+/* ---------------------------------------------------------------- training: backward of the field
+ * Replaces autograd through Model.forward for loss.backward(), main.py:385.  Three stages:
+ *   nerf_mlp_bwd_dz     grad_raw [M,4] + saved activations -> dZ of every layer (BF16 tile images,
+ *                       nerf_mlp_dz_bytes(M) bytes), tensor cores against the transposed weights
+ *   nerf_mlp_bwd_dw     dW/db of l1..l10 = dZ^T . X over the sample axis, tensor cores
+ *   nerf_mlp_bwd_heads  dW/db of l_alpha and l11; nerf_viewdir_term_bwd: l10's view columns + bias
+ * All of them ACCUMULATE (+=) into a padded fp32 gradient blob of nerf_grad_blob_bytes() bytes
+ * that the caller zeroes; nerf_grad_unpack scatters it into the 24 .grad tensors (registration
+ * order, like nerf_pack_model), adding to them when accumulate != 0. */
+size_t nerf_packed_model_bwd_bytes(void);
+int nerf_pack_model_bwd(const float* const* host_params, void* packed_bwd_out, void* stream);
+size_t nerf_mlp_dz_bytes(long M);
+int nerf_mlp_bwd_dz(const void* packed_bwd, const float* grad_raw, const void* act_save, long M,
+                    void* dz_out, void* stream);
+size_t nerf_grad_blob_bytes(void);
+int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, float* grad_blob, void* stream);
+int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, long M, float* grad_blob,
+                       void* stream);
+/* dirs / dir_stride / embedded / vterm_div exactly as passed to nerf_viewdir_term + nerf_mlp_fwd */
+int nerf_viewdir_term_bwd(const void* dz, const float* dirs, int dir_stride, int embedded, long M,
+                          int vterm_div, float* grad_blob, void* stream);
+int nerf_grad_unpack(const float* grad_blob, float* const* host_grads, int accumulate, void* stream);
+
+/* mean((x - target)^2) over n elements, main.py:380-383: *loss_accum += the mean (may be NULL),
+ * grad_out[i] = 2 (x[i] - target[i]) / n (may be NULL). */
+int nerf_mse_loss_grad(const float* x, const float* target, long n, float* grad_out,
+                       float* loss_accum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

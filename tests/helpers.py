@@ -79,3 +79,26 @@ def flip_aware_stats(got, want, sigma_last_got=None, sigma_last_want=None):
 def psnr(a, b):
     mse = torch.mean((a - b) ** 2).item()
     return float("inf") if mse == 0 else -10. * np.log10(mse)
+
+
+# ------------------------------------------------------------------ training-kernel helpers
+def decode_tile_image(buf, n_tiles, tile_bytes, offset, n_blocks):
+    """uint8 record buffer -> [n_tiles*128, n_blocks*64] fp32: undo the 128-byte-swizzled BF16 tile
+    image layout of csrc/mlp_bwd_layout.h (block = [128 rows][64 cols], 16-byte chunks XOR row&7)."""
+    rec = buf.cpu().view(n_tiles, tile_bytes)[:, offset:offset + n_blocks * 16384]
+    blocks = rec.reshape(n_tiles, n_blocks, 128, 8, 16)                 # tile, block, row, chunk slot, bytes
+    rows = torch.arange(128)
+    chunk = torch.arange(8)
+    slot = chunk[None, :] ^ (rows[:, None] & 7)                         # [row, logical chunk] -> physical slot
+    idx = slot[None, None, :, :, None].expand(n_tiles, n_blocks, 128, 8, 16)
+    logical = torch.gather(blocks, 3, idx)                              # logical chunk order
+    vals = logical.reshape(n_tiles, n_blocks, 128, 128).contiguous().view(torch.bfloat16)   # 64 bf16 per row
+    return vals.permute(0, 2, 1, 3).reshape(n_tiles * 128, n_blocks * 64).float()
+
+
+def grad_stats(got, want):
+    got, want = got.double().reshape(-1), want.double().reshape(-1)
+    denom = want.norm().item()
+    rel = (got - want).norm().item() / max(denom, 1e-30)
+    cos = float(torch.dot(got, want) / max(got.norm().item() * denom, 1e-30))
+    return {"rel_l2": rel, "cos": cos, "max_abs": (got - want).abs().max().item(), "ref_norm": denom}

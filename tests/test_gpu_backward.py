@@ -1,0 +1,239 @@
+"""GPU parity of the training path: saved activations, dZ chain, dW/db contractions, and the whole
+loss.backward() of a render against the reference's autograd (oracle + fixtures recorded from the
+real reference: gradient norms and the first 96 elements of every parameter gradient).
+
+Tolerance: the contractions run in BF16 (operands) with FP32 accumulation, so gradients are compared
+by relative L2 error and cosine per tensor (SURVEY.md App. C measured rel-L2 1.2e-2 for a
+BF16-emulated reference); the bounds below are written per test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from tests.helpers import (bf16, decode_tile_image, focal_of, golden, grad_stats, load_model_params)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ACT_TILE, DZ_TILE = 638976, 622592
+
+
+def _K():
+    import cv_nerf_b200
+    return cv_nerf_b200.kernels
+
+
+def _model(p):
+    from cv_nerf_b200.model import Model
+    return load_model_params(Model(), p).to(DEV)
+
+
+def _reference_chain(p, pts, dirs_per_row, grad_raw):
+    """fp32 autograd reference of the field with every layer's pre-activation kept:
+    returns (raw, acts dict, dz dict, param grads dict)."""
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    x = torch.cat([O.freq_encode(pts, 10), O.freq_encode(dirs_per_row, 4)], -1)
+    lin = lambda n, v: torch.nn.functional.linear(v, q[n + ".weight"], q[n + ".bias"])
+    pe, ped = x[:, :63], x[:, 63:]
+    z, acts = {}, {}
+    h = pe
+    for i, n in enumerate(("l1", "l2", "l3", "l4", "l5"), 1):
+        z[i] = lin(n, h); h = torch.relu(z[i]); acts[i] = h
+    h = torch.cat([pe, h], -1)
+    for i, n in ((6, "l6"), (7, "l7"), (8, "l8")):
+        z[i] = lin(n, h); h = torch.relu(z[i]); acts[i] = h
+    sigma = lin("l_alpha", h)
+    z[9] = lin("l9", h); acts[9] = z[9]
+    z[10] = lin("l10", torch.cat([z[9], ped], -1)); acts[10] = torch.relu(z[10])
+    rgb = lin("l11", acts[10])
+    raw = torch.cat([rgb, sigma], -1)
+    for v in z.values():
+        v.retain_grad()
+    raw.backward(grad_raw)
+    return raw.detach(), {k: v.detach() for k, v in acts.items()}, {k: v.grad for k, v in z.items()}, \
+        {k: v.grad for k, v in q.items()}
+
+
+def _emulated_chain(p, pe, acts, pe_dir, grad_raw):
+    """The kernels' arithmetic restated in fp64: BF16 operands (saved activations, BF16-rounded dZ,
+    BF16 weights), exact accumulation, ReLU masks taken from the SAVED activations.
+    Returns (dz dict, param grads dict)."""
+    W = lambda n: bf16(p[n + ".weight"]).double()
+    g = grad_raw.double()
+    a = {k: v.double() for k, v in acts.items()}
+    dz, r = {}, {}
+    r16 = lambda t: bf16(t.float()).double()
+    dz[10] = r16((g[:, :3] @ p["l11.weight"].double()) * (a[10] > 0))
+    dz[9] = r16(dz[10] @ W("l10")[:, :256])
+    dz[8] = r16((dz[9] @ W("l9") + g[:, 3:4] * p["l_alpha.weight"].double()) * (a[8] > 0))
+    dz[7] = r16((dz[8] @ W("l8")) * (a[7] > 0))
+    dz[6] = r16((dz[7] @ W("l7")) * (a[6] > 0))
+    dz[5] = r16((dz[6] @ W("l6")[:, 63:]) * (a[5] > 0))
+    for i in (4, 3, 2, 1):
+        dz[i] = r16((dz[i + 1] @ W(f"l{i + 1}")) * (a[i] > 0))
+    x_in = {1: pe.double()[:, :63], 6: torch.cat([pe.double()[:, :63], a[5]], -1), 10: a[9]}
+    for i in range(1, 10):
+        x = x_in.get(i, a.get(i - 1))
+        r[f"l{i}.weight"] = dz[i].T @ x
+        r[f"l{i}.bias"] = dz[i].sum(0)
+    dv = dz[10]
+    r["l10.weight"] = torch.cat([dv.T @ a[9], dv.T @ pe_dir.double()], -1)
+    r["l10.bias"] = dv.sum(0)
+    r["l_alpha.weight"] = (g[:, 3:4] * a[8]).sum(0, keepdim=True)
+    r["l_alpha.bias"] = g[:, 3].sum().reshape(1)
+    r["l11.weight"] = g[:, :3].T @ a[10]
+    r["l11.bias"] = g[:, :3].sum(0)
+    return dz, r
+
+
+@pytest.mark.parametrize("rows,S", [(96, 8), (1000, 8), (3 * 128 * 4, 64)])
+def test_field_backward_stages(rows, S):
+    """saved activations, dZ of every layer and all 24 parameter gradients, stage by stage."""
+    K = _K()
+    torch.manual_seed(rows)
+    p, _ = O.init_field_params(3, 0.5, 5.0)
+    model = _model(p)
+    n_rays = rows // S
+    pts = (torch.rand(rows, 3) * 2 - 1) * 1.5
+    dirs = torch.nn.functional.normalize(torch.randn(n_rays, 3), dim=-1)
+    grad_raw = torch.randn(rows, 4) * torch.tensor([1., 1., 1., .3])
+    raw_ref, acts, dz_ref, g_ref = _reference_chain(p, pts, dirs.repeat_interleave(S, 0), grad_raw)
+
+    packed = model.packed()
+    vterm = K.viewdir_term(packed, dirs.to(DEV))
+    act = torch.zeros(K.act_bytes(rows), dtype=torch.uint8, device=DEV)
+    raw = K.mlp_fwd(packed, K.IN_POINTS, pts.to(DEV), None, rows, S, vterm, S, act_save=act)
+    raw_plain = K.mlp_fwd(packed, K.IN_POINTS, pts.to(DEV), None, rows, S, vterm, S)
+    torch.cuda.synchronize()
+    assert torch.equal(raw, raw_plain), "saving activations changed the forward result"
+    n_tiles = (rows + 127) // 128
+    assert act.numel() == n_tiles * ACT_TILE
+
+    # 1. activation records
+    pe = decode_tile_image(act, n_tiles, ACT_TILE, 0, 1)[:rows]
+    want_pe = torch.cat([O.freq_encode(pts, 10), torch.zeros(rows, 1)], -1)
+    assert (pe - bf16(want_pe)).abs().max() <= 2e-2          # bf16 ulp at |x|<=2 is 1.6e-2 (sin/cos anchors)
+    saved = {}
+    for i in range(1, 10):
+        saved[i] = decode_tile_image(act, n_tiles, ACT_TILE, 16384 + (i - 1) * 65536, 4)[:rows]
+        err = (saved[i] - acts[i]).abs().max().item()
+        assert err <= 2e-2 * max(1.0, acts[i].abs().max().item()), (i, err)
+    saved[10] = decode_tile_image(act, n_tiles, ACT_TILE, 16384 + 9 * 65536, 2)[:rows]
+    assert (saved[10] - acts[10]).abs().max() <= 2e-2 * max(1.0, acts[10].abs().max().item())
+    pe_dir = O.freq_encode(dirs.repeat_interleave(S, 0), 4)
+    dz_emu, g_emu = _emulated_chain(p, pe, saved, pe_dir, grad_raw)
+
+    # 2. dZ chain
+    dz = K.mlp_bwd_dz(model.packed_bwd(), grad_raw.to(DEV), act, rows)
+    torch.cuda.synchronize()
+    assert dz.numel() == n_tiles * DZ_TILE
+    full = decode_tile_image(dz, n_tiles, DZ_TILE, 9 * 65536, 2)
+    assert full[rows:].abs().max().item() == 0 if full.shape[0] > rows else True, "padding rows must carry zero gradient"
+    for i in range(10, 0, -1):
+        off, nb = (9 * 65536, 2) if i == 10 else ((i - 1) * 65536, 4)
+        got = decode_tile_image(dz, n_tiles, DZ_TILE, off, nb)[:rows]
+        # (a) the kernel's own arithmetic (BF16 operands, masks from the saved activations): tight
+        se = grad_stats(got, dz_emu[i])
+        # (b) the fp32 reference: ReLU masks of near-zero activations differ between a BF16 and an
+        #     fp32 forward, which moves single elements by O(|dh|); judged by norm and direction
+        st = grad_stats(got, dz_ref[i])
+        print(f"dZ{i} vs emulation", se, "vs fp32 reference", st)
+        assert se["rel_l2"] <= 1e-2 and se["cos"] >= 0.9999, (i, se)
+        assert st["rel_l2"] <= 0.15 and st["cos"] >= 0.99, (i, st)
+
+    # 3. parameter gradients
+    blob = torch.zeros(K.grad_blob_floats(), device=DEV)
+    K.mlp_bwd_params(act, dz, grad_raw.to(DEV), rows, dirs.to(DEV), S, False, blob)
+    grads = [torch.empty_like(q) for q in model.ordered_params()]
+    K.grad_unpack(blob, grads)
+    torch.cuda.synchronize()
+    names = [f"{n}.{k}" for n in O.LAYER_NAMES for k in ("weight", "bias")]
+    for name, got in zip(names, grads):
+        se = grad_stats(got.cpu(), g_emu[name])
+        st = grad_stats(got.cpu(), g_ref[name])
+        print(name, "vs emulation", se, "vs fp32 reference", st)
+        assert se["rel_l2"] <= 1e-2 and se["cos"] >= 0.9999, (name, se)
+        assert st["rel_l2"] <= 0.15 and st["cos"] >= 0.99, (name, st)
+    # accumulate mode adds
+    K.grad_unpack(blob, grads, accumulate=True)
+    torch.cuda.synchronize()
+    st = grad_stats(grads[2].cpu(), 2 * g_emu["l2.weight"])
+    assert st["rel_l2"] <= 1e-2
+
+
+def test_model_forward_backward_through_autograd():
+    """Model.forward(x[...,90]) is differentiable w.r.t. the parameters (embedded-input mode)."""
+    K = _K()
+    torch.manual_seed(5)
+    p, _ = O.init_field_params(4, 0.5, 5.0)
+    model = _model(p)
+    rows = 300
+    pts = torch.rand(rows, 3) * 2 - 1
+    dirs = torch.nn.functional.normalize(torch.randn(rows, 3), dim=-1)
+    x = torch.cat([O.freq_encode(pts, 10), O.freq_encode(dirs, 4)], -1)
+    g = torch.randn(rows, 4)
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    O.field_mlp(q, x).backward(g)
+    out = model(x.to(DEV))
+    out.backward(g.to(DEV))
+    for name, prm in model.named_parameters():
+        st = grad_stats(prm.grad.cpu(), q[name].grad)
+        assert st["rel_l2"] <= 0.15 and st["cos"] >= 0.99, (name, st)
+
+
+def test_mse_loss_grad():
+    K = _K()
+    torch.manual_seed(0)
+    x, t = torch.rand(1000, 3), torch.rand(1000, 3)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.mean((xr - t) ** 2)
+    ref.backward()
+    loss, grad = K.mse_loss_grad(x.to(DEV), t.to(DEV))
+    assert abs(loss.item() - ref.item()) <= 1e-6
+    assert (grad.cpu() - xr.grad).abs().max() <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["lego_train", "fern_train"])
+def test_train_step_gradients_match_reference_fixture(name):
+    """render -> loss -> backward through the drop-in surface vs gradients recorded from the real
+    reference (main.py:376-385) on the same rays, weights, target and random draws."""
+    from cv_nerf_b200 import main as M
+    from cv_nerf_b200.model import Model
+    g = golden(f"render_{name}.npz")
+    h, w = int(g["hwf"][0]), int(g["hwf"][1])
+    f = focal_of(g)
+    coarse_p, fine_p = O.init_field_params(int(g["seed"]), float(g["sigma_bias"]), float(g["sigma_gain"]))
+    coarse, fine = _model(coarse_p), _model(fine_p)
+    noise = float(g["noise"])
+    draws = M.RenderDraws(u=torch.from_numpy(g["u"]), t_rand=torch.from_numpy(g["t_rand"]))
+    if noise > 0:
+        draws.noise_c, draws.noise_f = torch.from_numpy(g["noise_c"]), torch.from_numpy(g["noise_f"])
+    rays = torch.stack([torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])], 0).to(DEV)
+    target = torch.from_numpy(g["target"]).to(DEV)
+    rgb, extras = M.render(h, w, f, rays=rays, draws=draws, coarse_model=coarse, fine_model=fine, q_fn=None,
+                           n_coarse_samples=64, n_fine_samples=128, perturb=1., noise=noise,
+                           white_bkg=bool(g["white_bkg"]), ndc=bool(g["ndc"]), near=float(g["near"]),
+                           far=float(g["far"]))
+    loss = torch.mean((rgb - target) ** 2) + torch.mean((extras["rgb_c"] - target) ** 2)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 2e-3, (loss.item(), float(g["loss"]))
+    worst_norm, worst_cos, bad = 0., 1., []
+    for tag, net in (("coarse", coarse), ("fine", fine)):
+        for k, prm in net.named_parameters():
+            gn = float(g[f"gnorm/{tag}.{k}"])
+            got = prm.grad.detach().cpu().reshape(-1)
+            head = torch.from_numpy(g[f"ghead/{tag}.{k}"])
+            rel_norm = abs(got.norm().item() - gn) / max(gn, 1e-12)
+            st = grad_stats(got[:head.numel()], head)
+            print(tag, k, "norm rel err", rel_norm, st)
+            worst_norm = max(worst_norm, rel_norm)
+            # BF16 contractions + ReLU masks of a BF16 forward: norm within 5 %, direction of the
+            # recorded 96-element head within cos >= 0.98 (fp32-vs-BF16 mask flips, see
+            # test_field_backward_stages for the tight check against the kernel's own arithmetic)
+            if rel_norm > 5e-2:
+                bad.append((tag, k, "norm", rel_norm))
+            if st["ref_norm"] > 1e-3 * gn:      # the head is informative only when not ~0
+                worst_cos = min(worst_cos, st["cos"])
+                if st["cos"] < 0.98:
+                    bad.append((tag, k, "cos", st))
+    print("worst gradient-norm error", worst_norm, "worst head cosine", worst_cos)
+    assert not bad, bad

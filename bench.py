@@ -184,7 +184,7 @@ def run_ours(args):
     def step_device(i):
         rgb, _ = M.render(H, W, FOCAL, c2w=pose_dev[i % 40], rows=(r0, r1), **kw_test)
         if world > 1:
-            dist.all_gather_into_tensor(frame.view(world, -1), rgb.reshape(-1))
+            dist.all_gather_into_tensor(frame.view(-1), rgb.reshape(-1))
         return rgb
 
     def step_e2e(i):

@@ -61,6 +61,17 @@ _SIGNATURES = {
     "nerf_grad_unpack": (ctypes.c_int, [c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]),
     "nerf_mse_loss_grad": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_long, c_float_p, c_float_p,
                                           ctypes.c_void_p]),
+    "nerf_adam_step": (ctypes.c_int, [ctypes.c_int] + [ctypes.POINTER(ctypes.c_void_p)] * 4 +
+                       [ctypes.POINTER(ctypes.c_long), ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                        ctypes.c_long, ctypes.c_float, ctypes.c_void_p]),
+    "nerf_adam_step_blob": (ctypes.c_int, [c_float_p] + [ctypes.POINTER(ctypes.c_void_p)] * 3 +
+                            [ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_long,
+                             ctypes.c_float, ctypes.c_void_p]),
+    "nerf_train_rays": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                       c_float_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_float,
+                                       ctypes.c_float, c_float_p, c_float_p, c_float_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
 }
 
 # debug / test-only symbols that are exported but not part of the public header

@@ -313,3 +313,55 @@ def mse_loss_grad(x, target, want_grad=True, loss=None):
     check(lib.nerf_mse_loss_grad(ptr(x), ptr(target), x.numel(), ptr(grad), ptr(loss), stream_of(x)),
           "nerf_mse_loss_grad")
     return loss, grad
+
+
+# ---------------------------------------------------------------------- optimizer / train-loop batch
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[ptr(t) for t in tensors])
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, step, grad_scale=1.0):
+    """torch.optim.Adam semantics for a list of tensors, one launch (in place)."""
+    lib = _lib.load()
+    n = len(params)
+    if n == 0:
+        return
+    sizes = (ctypes.c_long * n)(*[p.numel() for p in params])
+    check(lib.nerf_adam_step(n, _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avg), _ptr_array(exp_avg_sq),
+                             sizes, float(lr), float(betas[0]), float(betas[1]), float(eps), int(step),
+                             float(grad_scale), stream_of(params[0])), "nerf_adam_step", launches=(n + 47) // 48)
+
+
+def adam_step_blob(blob, params, exp_avg, exp_avg_sq, lr, betas, eps, step, grad_scale=1.0):
+    """Adam for the 24 tensors of one Model with the gradient read from the padded blob."""
+    lib = _lib.load()
+    assert len(params) == 24
+    check(lib.nerf_adam_step_blob(ptr(blob), _ptr_array(params), _ptr_array(exp_avg), _ptr_array(exp_avg_sq),
+                                  float(lr), float(betas[0]), float(betas[1]), float(eps), int(step),
+                                  float(grad_scale), stream_of(blob)), "nerf_adam_step_blob")
+
+
+def train_rays(height, width, focal, pose, n, *, pix=None, seed=0, crop=None, image=None, ndc=True, near=0.,
+               far=1., want_pix=False):
+    """One train iteration's batch (main.py:351-374): packed rays [n,11], target [n,3] (when an
+    image [H,W,3] is given) and optionally the chosen linear pixel indices."""
+    lib = _lib.load()
+    pose = f32c(pose[:3, :4])
+    dev = pose.device
+    cw, ch = _ndc_consts(height, width, focal)
+    r0, c0, hh, ww = (0, 0, height, width) if crop is None else crop
+    if pix is not None:
+        pix = pix.to(device=dev, dtype=torch.int32).contiguous()
+        n = pix.numel()
+    rays = torch.empty((n, RAY_STRIDE), dtype=torch.float32, device=dev)
+    target = None
+    if image is not None:
+        image = f32c(image, dev)
+        assert image.shape == (height, width, 3)
+        target = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    pix_out = torch.empty(n, dtype=torch.int32, device=dev) if want_pix else None
+    check(lib.nerf_train_rays(height, width, _f32(focal), cw, ch, ptr(pose), None if pix is None else pix.data_ptr(),
+                              int(seed) & 0xFFFFFFFFFFFFFFFF, r0, c0, hh, ww, n, int(bool(ndc)), _f32(near), _f32(far),
+                              ptr(image), ptr(rays), ptr(target), None if pix_out is None else pix_out.data_ptr(),
+                              torch.cuda.current_stream(dev).cuda_stream), "nerf_train_rays")
+    return rays, target, pix_out

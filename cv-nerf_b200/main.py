@@ -200,7 +200,9 @@ def create_model(args):
                                                         embed_fn=xyz_embedder.embed,
                                                         embeddirs_fn=ang_embedder.embed,
                                                         netchunk=args.netchunk)
-    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lr, betas=(0.9, 0.999))
+    # torch.optim.Adam's update rule as one multi-tensor launch (train.FusedAdam)
+    from .train import FusedAdam
+    optimizer = FusedAdam(params=grad_vars, lr=args.lr, betas=(0.9, 0.999))
     start = 0
     render_kwargs_train = {
         'q_fn': q_fn,

@@ -13,6 +13,15 @@ from . import kernels as K
 from ._lib import NerfB200Error, f32c
 
 STD_CHUNK_SIZE = 65536
+_PARAM_EPOCH = 0
+
+
+def bump_param_epoch():
+    """Called by in-place parameter updates that bypass torch's version counters (the fused Adam
+    kernels): invalidates every Model's packed-weight cache."""
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1
+
 PARAM_ORDER = ("l1", "l2", "l3", "l4", "l5", "l6", "l7", "l8", "l9", "l_alpha", "l10", "l11")
 
 
@@ -99,7 +108,7 @@ class Model(nn.Module):
         """BF16 UMMA-layout blob of the current parameters; re-packed (one small kernel) when any
         parameter was modified in place (optimizer step, load_state_dict) or moved."""
         params = self.ordered_params()
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (_PARAM_EPOCH,) + tuple((p.data_ptr(), p._version) for p in params)
         if self._packed is None or key != self._packed_key:
             if not params[0].is_cuda:
                 raise NerfB200Error("Model parameters must live on a CUDA device; there is no CPU fallback")
@@ -111,7 +120,7 @@ class Model(nn.Module):
     def packed_bwd(self):
         """Transposed BF16 weights for the backward dZ chain (same caching rule as packed())."""
         params = self.ordered_params()
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (_PARAM_EPOCH,) + tuple((p.data_ptr(), p._version) for p in params)
         if self._packed_bwd is None or key != self._packed_bwd_key:
             if not params[0].is_cuda:
                 raise NerfB200Error("Model parameters must live on a CUDA device; there is no CPU fallback")

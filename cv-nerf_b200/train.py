@@ -1,0 +1,171 @@
+"""The train iteration of the reference (/root/reference/main.py:344-394) on the device.
+
+Two entry levels:
+
+* ``FusedAdam`` -- a ``torch.optim.Optimizer`` with the hyper-parameters and update rule of the
+  ``torch.optim.Adam`` that ``create_model`` builds (main.py:144), stepping every tensor in one
+  launch.  With it the reference's loop body (render -> loss -> backward -> optimizer.step ->
+  ``param_group['lr'] = ...``) runs unchanged on the drop-in surface.
+
+* ``TrainStep`` -- the same iteration without autograd bookkeeping: pixel batch and rays generated
+  on the device (main.py:351-374), forward with saved activations, loss, compositing backward,
+  field backward into two flat gradient blobs, one all-reduce of those blobs across data-parallel
+  ranks (NCCL; rays are sharded, every rank draws its own batch), Adam straight from the blobs,
+  re-pack of the BF16 weights, learning-rate decay (main.py:276-277, 392-394).
+"""
+import math
+
+import torch
+
+from . import kernels as K
+from . import model as _model
+from ._lib import NerfB200Error
+from .model import Model
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr, betas) semantics (no weight decay / amsgrad, like main.py:144)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            ps, gs, ms, vs = [], [], [], []
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise NerfB200Error("FusedAdam needs CUDA parameters; there is no CPU fallback")
+                st = self.state[p]
+                if not st:
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                ps.append(p.data); gs.append(p.grad.contiguous()); ms.append(st['exp_avg']); vs.append(st['exp_avg_sq'])
+            if not ps:
+                continue
+            group['step'] = group.get('step', 0) + 1
+            K.adam_step(ps, gs, ms, vs, group['lr'], group['betas'], group['eps'], group['step'])
+        _model.bump_param_epoch()
+        return loss
+
+
+def decayed_learning_rate(step, decay_steps, initial_lr, decay_rate=0.1):
+    return initial_lr * (decay_rate ** (step / decay_steps))
+
+
+class TrainStep:
+    """One object per process (= per GPU).  ``step(image, pose)`` runs one iteration and returns
+    the loss as a 1-element device tensor (no host synchronisation)."""
+
+    def __init__(self, coarse_model, fine_model, *, height, width, focal, n_rays=4096, n_coarse_samples=64,
+                 n_fine_samples=128, perturb=1., noise=0., white_bkg=False, ndc=True, near=0., far=1.,
+                 lr=5e-4, lr_decay=250, betas=(0.9, 0.999), eps=1e-8, seed=0, process_group=None):
+        if not isinstance(coarse_model, Model) or not isinstance(fine_model, Model):
+            raise NerfB200Error("TrainStep needs cv_nerf_b200.model.Model networks")
+        self.coarse, self.fine = coarse_model, fine_model
+        self.h, self.w, self.f = int(height), int(width), focal
+        self.n_rays, self.s_c, self.n_fine = int(n_rays), int(n_coarse_samples), int(n_fine_samples)
+        self.s_f = self.s_c + self.n_fine
+        self.perturb, self.noise, self.white_bkg, self.ndc = perturb, noise, bool(white_bkg), bool(ndc)
+        self.near, self.far = near, far
+        self.lr0, self.lr, self.lr_decay, self.betas, self.eps = lr, lr, lr_decay, betas, eps
+        self.seed, self.it = int(seed), 0
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        dev = next(coarse_model.parameters()).device
+        if dev.type != "cuda":
+            raise NerfB200Error("TrainStep needs the models on a CUDA device; there is no CPU fallback")
+        self.dev = dev
+        g = K.grad_blob_floats()
+        self.blob = torch.zeros((2, g), dtype=torch.float32, device=dev)          # [coarse, fine]
+        rows_c, rows_f = self.n_rays * self.s_c, self.n_rays * self.s_f
+        self.act_c = torch.empty(K.act_bytes(rows_c), dtype=torch.uint8, device=dev)
+        self.act_f = torch.empty(K.act_bytes(rows_f), dtype=torch.uint8, device=dev)
+        self.dz = torch.empty(K.dz_bytes(max(rows_c, rows_f)), dtype=torch.uint8, device=dev)
+        self.params = [coarse_model.ordered_params(), fine_model.ordered_params()]
+        self.m = [[torch.zeros_like(p) for p in ps] for ps in self.params]
+        self.v = [[torch.zeros_like(p) for p in ps] for ps in self.params]
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def crop_window(self, precrop_frac=None):
+        """Pre-crop window of main.py:354-361 as (row0, col0, rows, cols)."""
+        if precrop_frac is None:
+            return None
+        dh, dw = int(self.h // 2 * precrop_frac), int(self.w // 2 * precrop_frac)
+        return (self.h // 2 - dh, self.w // 2 - dw, 2 * dh, 2 * dw)
+
+    @torch.no_grad()
+    def forward_backward(self, rays, target, draws=None):
+        """rays [n,11], target [n,3] -> loss tensor; gradients of both networks accumulated into
+        self.blob (zeroed first).  ``draws``: main.RenderDraws with injected random numbers."""
+        n = rays.shape[0]
+        dev = self.dev
+        pick = lambda t, shape, fn: (t.to(dev).float().contiguous() if t is not None else fn(shape, device=dev))
+        t_rand = None
+        if self.perturb > 0.:
+            t_rand = pick(draws.t_rand if draws else None, (n, self.s_c), torch.rand)
+        z_c = K.sample_coarse(rays, self.s_c, t_rand)
+        noise_c = noise_f = None
+        if self.noise > 0.:
+            noise_c = pick(draws.noise_c if draws else None, (n, self.s_c), torch.randn) * self.noise
+            noise_f = pick(draws.noise_f if draws else None, (n, self.s_f), torch.randn) * self.noise
+        u = pick(draws.u if draws else None, (n, self.n_fine), torch.rand)
+
+        pk_c, pk_f = self.coarse.packed(), self.fine.packed()
+        rows_c, rows_f = n * self.s_c, n * self.s_f
+        vt_c = K.viewdir_term(pk_c, rays)
+        raw_c = K.mlp_fwd(pk_c, K.IN_RAYS, rays, z_c, rows_c, self.s_c, vt_c, self.s_c, act_save=self.act_c)
+        rgb_c, w_c = K.composite_fwd(raw_c.view(n, self.s_c, 4), z_c, rays, noise_c, self.white_bkg)
+        z_f = K.resample_merge(z_c, w_c, u)
+        vt_f = K.viewdir_term(pk_f, rays)
+        raw_f = K.mlp_fwd(pk_f, K.IN_RAYS, rays, z_f, rows_f, self.s_f, vt_f, self.s_f, act_save=self.act_f)
+        rgb_f, _ = K.composite_fwd(raw_f.view(n, self.s_f, 4), z_f, rays, noise_f, self.white_bkg, want_weights=False)
+
+        self.loss.zero_()
+        _, g_f = K.mse_loss_grad(rgb_f, target, loss=self.loss)
+        _, g_c = K.mse_loss_grad(rgb_c, target, loss=self.loss)
+        graw_f = K.composite_bwd(raw_f.view(n, self.s_f, 4), z_f, rays, noise_f, self.white_bkg, g_f)
+        graw_c = K.composite_bwd(raw_c.view(n, self.s_c, 4), z_c, rays, noise_c, self.white_bkg, g_c)
+
+        self.blob.zero_()
+        for idx, (net, graw, act, rows, s) in enumerate(((self.coarse, graw_c, self.act_c, rows_c, self.s_c),
+                                                        (self.fine, graw_f, self.act_f, rows_f, self.s_f))):
+            graw = graw.view(rows, 4)
+            K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=self.dz)
+            K.mlp_bwd_params(act, self.dz, graw, rows, rays, s, False, self.blob[idx])
+        return self.loss
+
+    @torch.no_grad()
+    def apply_gradients(self):
+        """all-reduce (data parallel), Adam from the blobs, weight re-pack, learning-rate decay."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.blob, group=self.pg)
+        self.it += 1
+        for idx in range(2):
+            K.adam_step_blob(self.blob[idx], [p.data for p in self.params[idx]], self.m[idx], self.v[idx], self.lr,
+                             self.betas, self.eps, self.it, grad_scale=1. / self.world)
+        _model.bump_param_epoch()
+        # main.py:392-394: the decayed rate takes effect from the next iteration on
+        self.lr = decayed_learning_rate(self.it, self.lr_decay * 1000, self.lr0)
+
+    @torch.no_grad()
+    def step(self, image, pose, *, precrop_frac=None, pix=None, draws=None):
+        rays, target, _ = K.train_rays(self.h, self.w, self.f, pose, self.n_rays, pix=pix,
+                                       seed=self.seed * 0x9E3779B97F4A7C15 + self.it, crop=self.crop_window(precrop_frac),
+                                       image=image, ndc=self.ndc, near=self.near, far=self.far)
+        loss = self.forward_backward(rays, target, draws)
+        self.apply_gradients()
+        return loss
+
+    def gradients(self, idx):
+        """The current blob of network idx (0 coarse, 1 fine) unpacked into 24 tensors."""
+        grads = [torch.empty_like(p) for p in self.params[idx]]
+        return K.grad_unpack(self.blob[idx], grads)

@@ -154,6 +154,29 @@ int nerf_grad_unpack(const float* grad_blob, float* const* host_grads, int accum
 int nerf_mse_loss_grad(const float* x, const float* target, long n, float* grad_out,
                        float* loss_accum, void* stream);
 
+/* ---------------------------------------------------------------- training: optimizer, ray batch */
+
+/* torch.optim.Adam(lr, betas=(beta1,beta2), eps) of main.py:144,386 for n_tensors tensors in one
+ * launch.  All pointer arrays are HOST arrays of DEVICE pointers; sizes in elements; step is the
+ * 1-based step count after this update (bias correction); grads are multiplied by grad_scale. */
+int nerf_adam_step(int n_tensors, float* const* params, const float* const* grads,
+                   float* const* exp_avg, float* const* exp_avg_sq, const long* sizes, float lr,
+                   float beta1, float beta2, float eps, long step, float grad_scale, void* stream);
+/* Same for the 24 tensors of one Model, gradient read from the padded gradient blob. */
+int nerf_adam_step_blob(const float* grad_blob, float* const* params, float* const* exp_avg,
+                        float* const* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                        long step, float grad_scale, void* stream);
+
+/* One train iteration's batch, main.py:351-374: n rays (packed [n,11] like nerf_pack_rays) and
+ * their target pixels [n,3] from image [H,W,3].  pix != NULL: the caller's linear pixel indices
+ * (i*W + j).  pix == NULL: n DISTINCT pixels of the crop window drawn by a keyed permutation
+ * (np.random.choice(replace=False) of main.py:368; pre-crop window of main.py:354-361).
+ * target_out / image / pix_out may be NULL. */
+int nerf_train_rays(int H, int W, float focal, float cw, float ch, const float* pose, const int* pix,
+                    unsigned long long seed, int crop_r0, int crop_c0, int crop_h, int crop_w, long n,
+                    int ndc, float near, float far, const float* image, float* rays_out,
+                    float* target_out, int* pix_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

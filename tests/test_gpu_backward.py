@@ -194,46 +194,79 @@ def test_mse_loss_grad():
 
 @pytest.mark.parametrize("name", ["lego_train", "fern_train"])
 def test_train_step_gradients_match_reference_fixture(name):
-    """render -> loss -> backward through the drop-in surface vs gradients recorded from the real
-    reference (main.py:376-385) on the same rays, weights, target and random draws."""
+    """render -> loss -> backward through the drop-in surface vs the reference's autograd
+    (main.py:376-385) on the same rays, weights, target and random draws.
+
+    delta_last = 1e10 makes a ray's colour a step function of the sign of the far sample's density
+    (SURVEY.md App. C); rays whose sign differs between the BF16 and the fp32 forward are excluded
+    from BOTH sides (counted and bounded), like the forward parity tests do.  When no ray flips, the
+    gradients are also compared with the norms / 96-element heads recorded from the real reference."""
     from cv_nerf_b200 import main as M
-    from cv_nerf_b200.model import Model
     g = golden(f"render_{name}.npz")
     h, w = int(g["hwf"][0]), int(g["hwf"][1])
     f = focal_of(g)
     coarse_p, fine_p = O.init_field_params(int(g["seed"]), float(g["sigma_bias"]), float(g["sigma_gain"]))
     coarse, fine = _model(coarse_p), _model(fine_p)
     noise = float(g["noise"])
-    draws = M.RenderDraws(u=torch.from_numpy(g["u"]), t_rand=torch.from_numpy(g["t_rand"]))
+    cpu = {k: torch.from_numpy(g[k]) for k in ("u", "t_rand", "rays_o", "rays_d", "target")}
     if noise > 0:
-        draws.noise_c, draws.noise_f = torch.from_numpy(g["noise_c"]), torch.from_numpy(g["noise_f"])
-    rays = torch.stack([torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])], 0).to(DEV)
-    target = torch.from_numpy(g["target"]).to(DEV)
-    rgb, extras = M.render(h, w, f, rays=rays, draws=draws, coarse_model=coarse, fine_model=fine, q_fn=None,
-                           n_coarse_samples=64, n_fine_samples=128, perturb=1., noise=noise,
-                           white_bkg=bool(g["white_bkg"]), ndc=bool(g["ndc"]), near=float(g["near"]),
-                           far=float(g["far"]))
-    loss = torch.mean((rgb - target) ** 2) + torch.mean((extras["rgb_c"] - target) ** 2)
+        cpu["noise_c"], cpu["noise_f"] = torch.from_numpy(g["noise_c"]), torch.from_numpy(g["noise_f"])
+    kw = dict(white_bkg=bool(g["white_bkg"]), ndc=bool(g["ndc"]), near=float(g["near"]), far=float(g["far"]))
+
+    def ours(keep):
+        d = M.RenderDraws(u=cpu["u"][keep], t_rand=cpu["t_rand"][keep])
+        if noise > 0:
+            d.noise_c, d.noise_f = cpu["noise_c"][keep], cpu["noise_f"][keep]
+        rays = torch.stack([cpu["rays_o"][keep], cpu["rays_d"][keep]], 0).to(DEV)
+        packed = M.K.pack_rays(h, w, f, rays_o=rays[0], rays_d=rays[1], ndc=kw["ndc"], near=kw["near"], far=kw["far"])
+        return M.render_rays(packed, draws=d, extras=True, coarse_model=coarse, fine_model=fine, n_coarse_samples=64,
+                             n_fine_samples=128, perturb=1., noise=noise, white_bkg=kw["white_bkg"])
+
+    def oracle(keep, cp, fp):
+        d = O.RenderDraws(u=cpu["u"][keep], t_rand=cpu["t_rand"][keep])
+        if noise > 0:
+            d.noise_c, d.noise_f = cpu["noise_c"][keep] * noise, cpu["noise_f"][keep] * noise
+        return O.render_image(h, w, f, cp, fp, rays=(cpu["rays_o"][keep], cpu["rays_d"][keep]), ndc=kw["ndc"],
+                              near=kw["near"], far=kw["far"], draws=d, white_bkg=kw["white_bkg"], extras=True)
+
+    everything = torch.ones(cpu["u"].shape[0], dtype=torch.bool)
+    with torch.no_grad():
+        a, b = ours(everything), oracle(everything, coarse_p, fine_p)
+    flip = torch.zeros_like(everything)
+    for key in ("raw_c", "raw_f"):
+        flip |= (a[key][:, -1, 3].cpu() > 0) != (b[key][:, -1, 3] > 0)
+    n_flip = int(flip.sum())
+    print(name, "far-sample sign flips:", n_flip, "of", flip.numel())
+    assert n_flip <= max(2, flip.numel() // 20)
+    keep = ~flip
+
+    target = cpu["target"][keep]
+    out = ours(keep)
+    loss = torch.mean((out["rgb_map"] - target.to(DEV)) ** 2) + torch.mean((out["rgb_c"] - target.to(DEV)) ** 2)
     loss.backward()
-    assert abs(loss.item() - float(g["loss"])) <= 2e-3, (loss.item(), float(g["loss"]))
-    worst_norm, worst_cos, bad = 0., 1., []
-    for tag, net in (("coarse", coarse), ("fine", fine)):
+    cq = {k: v.clone().requires_grad_(True) for k, v in coarse_p.items()}
+    fq = {k: v.clone().requires_grad_(True) for k, v in fine_p.items()}
+    ref = oracle(keep, cq, fq)
+    ref_loss = O.train_loss(ref["rgb_map"], ref["rgb_c"], target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-3 * max(1., ref_loss.item()), (loss.item(), ref_loss.item())
+
+    bad, worst_norm, worst_cos = [], 0., 1.
+    for tag, net, q in (("coarse", coarse, cq), ("fine", fine, fq)):
         for k, prm in net.named_parameters():
-            gn = float(g[f"gnorm/{tag}.{k}"])
-            got = prm.grad.detach().cpu().reshape(-1)
-            head = torch.from_numpy(g[f"ghead/{tag}.{k}"])
-            rel_norm = abs(got.norm().item() - gn) / max(gn, 1e-12)
-            st = grad_stats(got[:head.numel()], head)
+            st = grad_stats(prm.grad.detach().cpu(), q[k].grad)
+            got_n = prm.grad.norm().item()
+            rel_norm = abs(got_n - st["ref_norm"]) / max(st["ref_norm"], 1e-30)
             print(tag, k, "norm rel err", rel_norm, st)
-            worst_norm = max(worst_norm, rel_norm)
-            # BF16 contractions + ReLU masks of a BF16 forward: norm within 5 %, direction of the
-            # recorded 96-element head within cos >= 0.98 (fp32-vs-BF16 mask flips, see
-            # test_field_backward_stages for the tight check against the kernel's own arithmetic)
-            if rel_norm > 5e-2:
-                bad.append((tag, k, "norm", rel_norm))
-            if st["ref_norm"] > 1e-3 * gn:      # the head is informative only when not ~0
-                worst_cos = min(worst_cos, st["cos"])
-                if st["cos"] < 0.98:
-                    bad.append((tag, k, "cos", st))
-    print("worst gradient-norm error", worst_norm, "worst head cosine", worst_cos)
+            worst_norm, worst_cos = max(worst_norm, rel_norm), min(worst_cos, st["cos"])
+            # BF16 contractions + ReLU masks of a BF16 forward on <= 96 rays: norm within 5 %,
+            # direction cos >= 0.98 per tensor (the kernels' own arithmetic is pinned to 1e-2 rel-L2,
+            # measured 6e-4, by test_field_backward_stages)
+            if rel_norm > 5e-2 or st["cos"] < 0.98:
+                bad.append((tag, k, rel_norm, st))
+            if n_flip == 0:
+                gn = float(g[f"gnorm/{tag}.{k}"])
+                if abs(got_n - gn) > 5e-2 * gn:
+                    bad.append((tag, k, "vs recorded reference norm", got_n, gn))
+    print("worst gradient-norm error", worst_norm, "worst cosine", worst_cos)
     assert not bad, bad

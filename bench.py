@@ -226,6 +226,10 @@ def run_ours(args):
     K.STATS.reset()
     e2e_ms = timed(step_e2e, args.steps, max(args.warmup, 1), timed_kernels=False)
 
+    train = None
+    if not args.no_train:
+        train = bench_train_step(args, dev, world, rank)
+
     peaks, peak_kind = measured_peaks()
     n_rays = H * W
     rays_per_s = n_rays * args.steps / (total_ms * 1e-3)
@@ -262,9 +266,118 @@ def run_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if train is not None:
+        line["train"] = train
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+TRAIN_FLOP_PER_RAY = (N_COARSE + N_COARSE + N_FINE) * 2 * (593408 + 593408 + 557696)
+
+
+def bench_train_step(args, dev, world, rank):
+    """BASELINE.json configs[3]: lego training, 4096 rays per GPU, data parallel: device-side batch,
+    forward with saved activations, loss, backward, all-reduce of the gradient blobs, Adam, re-pack.
+    Returns the `train` object of the JSON line (ms per step = max over ranks)."""
+    import torch.distributed as dist
+    from cv_nerf_b200 import kernels as K
+    from cv_nerf_b200.data_helpers import pose_spherical
+    from cv_nerf_b200.model import Model
+    from cv_nerf_b200.train import TrainStep
+    torch.manual_seed(0)
+    coarse, fine = Model().to(dev), Model().to(dev)        # same init on every rank (seeded)
+    h = w = 400
+    focal = FOCAL / 2.
+    n_rays = args.train_rays
+    ts = TrainStep(coarse, fine, height=h, width=w, focal=focal, n_rays=n_rays, perturb=1., noise=0., white_bkg=True,
+                   ndc=False, near=NEAR, far=FAR, lr=5e-4, lr_decay=500, seed=1234 + rank)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    images = torch.rand((4, h, w, 3), device=dev, generator=g)            # synthetic targets, per rank
+    pose_dev = torch.stack(poses(4, pose_spherical)).to(dev)
+    steps, warmup = args.train_steps, max(args.warmup, 3)
+
+    def one(i):
+        return ts.step(images[i % 4], pose_dev[i % 4])
+
+    for i in range(warmup):
+        one(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    K.STATS.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = one(warmup + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = K.STATS.launches
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / steps
+    # per-kernel split of one more step (events around each stage; not part of the timed region)
+    stages = {}
+    if rank == 0:
+        stages = time_train_stages(ts, images[0], pose_dev[0])
+    peaks, _ = measured_peaks()
+    tflops = n_rays * TRAIN_FLOP_PER_RAY / (ms_step * 1e-3) / 1e12
+    return {"metric": "train step ms (4096 rays per GPU, fwd+bwd+allreduce+Adam)", "ms_per_step": ms_step,
+            "rays_per_step_per_gpu": n_rays, "rays_per_s_all_gpus": n_rays * world / (ms_step * 1e-3),
+            "steps": steps, "warmup": warmup, "tflops_per_gpu": tflops,
+            "frac_of_sustained_bf16_peak": tflops / float(peaks["bf16_tflops_sustained"]),
+            "gpu_launches_per_step": launches / steps, "loss_last": float(loss.item()),
+            "grad_allreduce_bytes": int(ts.blob.numel() * 4) if world > 1 else 0, "stages_ms": stages}
+
+
+def time_train_stages(ts, image, pose):
+    """CUDA-event time of each stage of one train step (diagnostic split, same kernels)."""
+    from cv_nerf_b200 import kernels as K
+    ev = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        ev.append((name, e))
+    n, dev = ts.n_rays, ts.dev
+    mark("start")
+    rays, target, _ = K.train_rays(ts.h, ts.w, ts.f, pose, n, seed=1, image=image, ndc=ts.ndc, near=ts.near, far=ts.far)
+    z_c = K.sample_coarse(rays, ts.s_c, torch.rand((n, ts.s_c), device=dev))
+    u = torch.rand((n, ts.n_fine), device=dev)
+    pk_c, pk_f = ts.coarse.packed(), ts.fine.packed()
+    vt_c, vt_f = K.viewdir_term(pk_c, rays), K.viewdir_term(pk_f, rays)
+    mark("batch+sampling")
+    raw_c = K.mlp_fwd(pk_c, K.IN_RAYS, rays, z_c, n * ts.s_c, ts.s_c, vt_c, ts.s_c, act_save=ts.act_c)
+    mark("fwd_coarse(save)")
+    rgb_c, w_c = K.composite_fwd(raw_c.view(n, ts.s_c, 4), z_c, rays, None, ts.white_bkg)
+    z_f = K.resample_merge(z_c, w_c, u)
+    mark("composite+resample")
+    raw_f = K.mlp_fwd(pk_f, K.IN_RAYS, rays, z_f, n * ts.s_f, ts.s_f, vt_f, ts.s_f, act_save=ts.act_f)
+    mark("fwd_fine(save)")
+    rgb_f, _ = K.composite_fwd(raw_f.view(n, ts.s_f, 4), z_f, rays, None, ts.white_bkg, want_weights=False)
+    ts.loss.zero_()
+    _, g_f = K.mse_loss_grad(rgb_f, target, loss=ts.loss)
+    _, g_c = K.mse_loss_grad(rgb_c, target, loss=ts.loss)
+    graw_f = K.composite_bwd(raw_f.view(n, ts.s_f, 4), z_f, rays, None, ts.white_bkg, g_f).view(-1, 4)
+    graw_c = K.composite_bwd(raw_c.view(n, ts.s_c, 4), z_c, rays, None, ts.white_bkg, g_c).view(-1, 4)
+    ts.blob.zero_()
+    mark("composite+loss+bwd")
+    K.mlp_bwd_dz(ts.fine.packed_bwd(), graw_f, ts.act_f, n * ts.s_f, dz=ts.dz)
+    mark("dz_fine")
+    K.mlp_bwd_params(ts.act_f, ts.dz, graw_f, n * ts.s_f, rays, ts.s_f, False, ts.blob[1])
+    mark("dw_fine(+heads,view)")
+    K.mlp_bwd_dz(ts.coarse.packed_bwd(), graw_c, ts.act_c, n * ts.s_c, dz=ts.dz)
+    mark("dz_coarse")
+    K.mlp_bwd_params(ts.act_c, ts.dz, graw_c, n * ts.s_c, rays, ts.s_c, False, ts.blob[0])
+    mark("dw_coarse(+heads,view)")
+    ts.apply_gradients()
+    ts.coarse.packed(); ts.fine.packed(); ts.coarse.packed_bwd(); ts.fine.packed_bwd()
+    mark("allreduce+adam+repack")
+    torch.cuda.synchronize()
+    return {name: ev[i - 1][1].elapsed_time(e) for i, (name, e) in enumerate(ev) if i > 0}
 
 
 def main():
@@ -276,6 +389,9 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays of the CPU-baseline sample (ours arm)")
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step measurement")
+    ap.add_argument("--train-rays", type=int, default=4096, help="rays per GPU and train step (BASELINE configs[3])")
+    ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--size", type=int, default=800, help="frame height=width (profiling runs only; 800 is the benchmark)")
     args = ap.parse_args()
     global H, W, FOCAL, WORKLOAD

@@ -61,6 +61,13 @@ __device__ __forceinline__ uint32_t relu_mask_mul(uint32_t x, uint32_t h) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// one 32-byte sector = a swizzled pair of 16-byte chunks (LDG.256)
+__device__ __forceinline__ void ldg_nc_v8(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -106,30 +113,36 @@ __device__ __forceinline__ void head_stage(float4 g, const uint8_t* h10_row, uin
 // One layer's epilogue for this thread's 128 columns [c0, c0+128): accumulator (+ grad_sigma *
 // w_alpha when ADD_SIGMA) -> BF16 -> * [h > 0] (when MASK) -> A tile in place.
 // h_row: this row's line in block 0 of the saved activation (global), or NULL for zero rows.
+constexpr int kAhead = 2;                          // activation sectors in flight per thread
+
+// load the 32-byte sector holding logical chunks c16, c16+1 (c16 even) of this row; the swizzle
+// swaps them inside the sector for odd rows -- undone when the words are used
+__device__ __forceinline__ void load_mask_sector(const uint8_t* h_row, int c0, int it, uint32_t swz, uint4 (&dst)[2]) {
+    const int c = c0 + it * 16;
+    const int blk = c >> 6, c16 = (c & 63) >> 3;
+    if (h_row) {
+        ldg_nc_v8(h_row + blk * 16384 + ((((uint32_t)c16 << 4) ^ swz) & ~16u), dst[0], dst[1]);
+    } else {
+        dst[0] = dst[1] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// issued BEFORE waiting for the accumulator: the first mask loads overlap the tensor-core work
+__device__ __forceinline__ void mask_preload(const uint8_t* h_row, int c0, uint32_t swz, uint4 (&hm)[kAhead + 1][2]) {
+#pragma unroll
+    for (int a = 0; a < kAhead; ++a) load_mask_sector(h_row, c0, a, swz, hm[a]);
+}
+
 template <bool MASK, bool ADD_SIGMA>
 __device__ __forceinline__ void epilogue_dz(uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
-                                            const uint8_t* h_row, float dsig, uint32_t walpha_addr) {
-    constexpr int kAhead = 2;                      // activation loads in flight (x 2 chunks)
+                                            const uint8_t* h_row, float dsig, uint32_t walpha_addr,
+                                            uint4 (&hm)[kAhead + 1][2]) {
     uint32_t v[2][16];
-    uint4 hm[kAhead + 1][2];
-    auto load_h = [&](int it, uint4 (&dst)[2]) {
-        if (!MASK) return;
-        const int c = c0 + it * 16;
-        const int blk = c >> 6, c16 = (c & 63) >> 3;
-        if (h_row) {
-            dst[0] = ldg_nc_v4(h_row + blk * 16384 + (((uint32_t)c16 << 4) ^ swz));
-            dst[1] = ldg_nc_v4(h_row + blk * 16384 + (((uint32_t)(c16 + 1) << 4) ^ swz));
-        } else {
-            dst[0] = dst[1] = make_uint4(0, 0, 0, 0);
-        }
-    };
-#pragma unroll
-    for (int a = 0; a < kAhead; ++a) load_h(a, hm[a]);
     umma::tmem_ld16(tacc + c0, v[0]);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int c = c0 + it * 16;
-        if (it + kAhead < 8) load_h(it + kAhead, hm[(it + kAhead) % (kAhead + 1)]);
+        if (MASK && it + kAhead < 8) load_mask_sector(h_row, c0, it + kAhead, swz, hm[(it + kAhead) % (kAhead + 1)]);
         umma::tmem_wait_ld();
         if (it + 1 < 8) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
         const uint32_t(&cur)[16] = v[it & 1];
@@ -145,7 +158,13 @@ __device__ __forceinline__ void epilogue_dz(uint32_t tacc, int c0, uint32_t row_
                 d[2 * q + 1] = __ffma2_rn(s2, make_float2(w.z, w.w), d[2 * q + 1]);
             }
         }
-        const uint4(&hc)[2] = hm[it % (kAhead + 1)];
+        uint4 hc[2];
+        {
+            const uint4(&hs)[2] = hm[it % (kAhead + 1)];
+            const bool odd = (swz & 16u) != 0;
+            hc[0] = odd ? hs[1] : hs[0];
+            hc[1] = odd ? hs[0] : hs[1];
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             uint32_t o0 = pack_bf16x2(d[q * 4 + 0].x, d[q * 4 + 0].y), o1 = pack_bf16x2(d[q * 4 + 1].x, d[q * 4 + 1].y);
@@ -205,10 +224,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams 
         // ===================== producer: transposed weight slots, L2 -> smem =====================
         if (lane == 0) {
             uint32_t it = 0;
+            // The epilogues read the saved activations (ReLU masks) straight from global memory;
+            // pull every tile into L2 one layer ahead with bulk prefetches so those loads see L2
+            // latency and DRAM is read in whole lines.
+            auto prefetch_h10 = [&](long pair) {
+                for (int g = 0; g < 2; ++g) {
+                    const long tile = pair * 2 + g;
+                    if (tile < n_tiles) umma::bulk_prefetch_l2(P.act + (size_t)tile * kActTileBytes + kActH10, 32768);
+                }
+            };
+            if ((long)blockIdx.x < n_pairs) prefetch_h10(blockIdx.x);
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 for (int j = 0; j < kBwdLayers; ++j) {
                     const int first = bwd_first_stage(j), chunks = bwd_chunks(j);
                     for (int g = 0; g < 2; ++g) {
+                        const long tile = pair * 2 + g;
+                        if (j + 1 < kBwdLayers) {
+                            if (tile < n_tiles)
+                                umma::bulk_prefetch_l2(P.act + (size_t)tile * kActTileBytes + act_hidden(8 - j), 65536);
+                        } else if (g == 0 && pair + gridDim.x < n_pairs) {
+                            prefetch_h10(pair + gridDim.x);
+                        }
                         for (int c = 0; c < chunks; ++c, ++it) {
                             const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
                             umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
@@ -296,18 +332,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams 
             umma::named_bar_sync(group_bar, kGroupThreads);
 #pragma unroll 1
             for (int j = 0; j < kBwdLayers; ++j) {
-                umma::mbar_wait(bar_acc_full + 8 * g, n_full & 1);
-                ++n_full;
-                umma::tc_fence_after();
                 const int i = 9 - j;               // this epilogue produces dZ_i
                 const uint8_t* h_row = tile_ok ? act_tile + act_hidden(i) + row * 128 : nullptr;
                 const int c0 = half * 128;
+                uint4 hm[kAhead + 1][2];
+                if (j > 0) mask_preload(h_row, c0, swz, hm);
+                umma::mbar_wait(bar_acc_full + 8 * g, n_full & 1);
+                ++n_full;
+                umma::tc_fence_after();
                 if (j == 0) {
-                    epilogue_dz<false, false>(tacc, c0, a_row_addr, swz, nullptr, 0.f, walpha_addr);
+                    epilogue_dz<false, false>(tacc, c0, a_row_addr, swz, nullptr, 0.f, walpha_addr, hm);
                 } else if (j == 1) {
-                    epilogue_dz<true, true>(tacc, c0, a_row_addr, swz, h_row, graw.w, walpha_addr);
+                    epilogue_dz<true, true>(tacc, c0, a_row_addr, swz, h_row, graw.w, walpha_addr, hm);
                 } else {
-                    epilogue_dz<true, false>(tacc, c0, a_row_addr, swz, h_row, 0.f, walpha_addr);
+                    epilogue_dz<true, false>(tacc, c0, a_row_addr, swz, h_row, 0.f, walpha_addr, hm);
                 }
                 umma::fence_proxy_async_smem();
                 umma::tc_fence_before();

@@ -20,55 +20,101 @@ __device__ __forceinline__ float bf16_at(const uint8_t* block0, int f, int r) {
     return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(p)) << 16);
 }
 
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+    f[0] = __uint_as_float(q.x << 16); f[1] = __uint_as_float(q.x & 0xffff0000u);
+    f[2] = __uint_as_float(q.y << 16); f[3] = __uint_as_float(q.y & 0xffff0000u);
+    f[4] = __uint_as_float(q.z << 16); f[5] = __uint_as_float(q.z & 0xffff0000u);
+    f[6] = __uint_as_float(q.w << 16); f[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+
 // ------------------------------------------------------------------ l_alpha / l11
+// 8 warps; warp w owns rows w, w+8, ... of a tile, lane l owns the 16-byte chunk l of the row's
+// h8 line (features 8l..8l+7) and, for l < 16, of its h10 line: whole 128-byte lines per request,
+// 16 independent requests per lane and tile.  HBM-bound: 96 KB per tile.
 __global__ void __launch_bounds__(256) heads_bwd_kernel(const uint8_t* __restrict__ act,
                                                         const float* __restrict__ grad_raw, long M,
                                                         long n_tiles, float* __restrict__ grad) {
-    __shared__ float4 g[kTileRows];
-    const int f = threadIdx.x;
-    float acc_a = 0.f, acc_r0 = 0.f, acc_r1 = 0.f, acc_r2 = 0.f, acc_b = 0.f;
+    __shared__ float red[8][256 + 3 * 128 + 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float a8[8], r0[8], r1[8], r2[8], gb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a8[e] = r0[e] = r1[e] = r2[e] = 0.f;
+    const uint32_t blk_off = (uint32_t)(lane >> 3) * (uint32_t)kBlockBytes;
+    const uint32_t c16 = lane & 7;
     for (long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        __syncthreads();
-        if (f < kTileRows) {
-            const long row = t * kTileRows + f;
-            g[f] = row < M ? __ldg(reinterpret_cast<const float4*>(grad_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
         const uint8_t* tile = act + (size_t)t * kActTileBytes;
-        const uint8_t* h8 = tile + act_hidden(8);
-        const uint8_t* h10 = tile + kActH10;
+        const uint8_t* h8 = tile + act_hidden(8) + blk_off;
+        const uint8_t* h10 = tile + kActH10 + blk_off;
 #pragma unroll 4
-        for (int r = 0; r < kTileRows; ++r) {
-            const float4 gr = g[r];
-            acc_a = fmaf(gr.w, bf16_at(h8, f, r), acc_a);
-            if (f < kL10Out) {
-                const float h = bf16_at(h10, f, r);
-                acc_r0 = fmaf(gr.x, h, acc_r0);
-                acc_r1 = fmaf(gr.y, h, acc_r1);
-                acc_r2 = fmaf(gr.z, h, acc_r2);
+        for (int i = 0; i < kTileRows / 8; ++i) {
+            const int r = i * 8 + warp;
+            const long row = t * kTileRows + r;
+            const float4 g = row < M ? __ldg(reinterpret_cast<const float4*>(grad_raw) + row)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t off = (uint32_t)r * 128 + ((c16 ^ (uint32_t)(r & 7)) << 4);
+            float h[8];
+            unpack8(ldg_nc_v4(h8 + off), h);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a8[e] = fmaf(g.w, h[e], a8[e]);
+            if (lane < 16) {
+                unpack8(ldg_nc_v4(h10 + off), h);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    r0[e] = fmaf(g.x, h[e], r0[e]);
+                    r1[e] = fmaf(g.y, h[e], r1[e]);
+                    r2[e] = fmaf(g.z, h[e], r2[e]);
+                }
             }
-        }
-        if (f < 4) {
-            for (int r = 0; r < kTileRows; ++r) acc_b += reinterpret_cast<const float*>(&g[r])[f];
+            if (lane == 0) { gb[0] += g.x; gb[1] += g.y; gb[2] += g.z; gb[3] += g.w; }
         }
     }
-    atomicAdd(grad + kG_WAlpha + f, acc_a);
-    if (f < kL10Out) {
-        atomicAdd(grad + kG_W11 + 0 * kL10Out + f, acc_r0);
-        atomicAdd(grad + kG_W11 + 1 * kL10Out + f, acc_r1);
-        atomicAdd(grad + kG_W11 + 2 * kL10Out + f, acc_r2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        red[warp][lane * 8 + e] = a8[e];
+        if (lane < 16) {
+            red[warp][256 + 0 * 128 + lane * 8 + e] = r0[e];
+            red[warp][256 + 1 * 128 + lane * 8 + e] = r1[e];
+            red[warp][256 + 2 * 128 + lane * 8 + e] = r2[e];
+        }
     }
-    if (f < 3) atomicAdd(grad + kG_B11 + f, acc_b);
-    if (f == 3) atomicAdd(grad + kG_BAlpha, acc_b);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) red[warp][256 + 384 + k] = gb[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 + 384 + 4; i += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][i];
+        float* dst = i < 256 ? grad + kG_WAlpha + i
+                   : i < 256 + 384 ? grad + kG_W11 + (i - 256)
+                   : (i - 640 < 3 ? grad + kG_B11 + (i - 640) : grad + kG_BAlpha);
+        atomicAdd(dst, s);
+    }
 }
 
 // ------------------------------------------------------------------ l10 view columns / bias
+// One block walks over rays; its 8 warps split a ray's rows, 16 lanes cover one row's 128 dZ10
+// values with 16-byte loads (two rows per warp and request).
 __global__ void __launch_bounds__(128) viewdir_term_bwd_kernel(const uint8_t* __restrict__ dz,
                                                                const float* __restrict__ dirs, int dir_stride,
                                                                int embedded, long M, int div, long count,
                                                                float* __restrict__ grad) {
     __shared__ float pe[28];
+    __shared__ float part[8][128];
     const int j = threadIdx.x;
+    const int sub = j >> 4;                 // 8 row groups
+    const int l16 = j & 15;                 // chunk of the row: features 8*l16 .. 8*l16+7
+    const uint32_t blk_off = (uint32_t)(l16 >> 3) * (uint32_t)kBlockBytes;
+    const uint32_t c16 = l16 & 7;
     float acc[kViewPeDim];
 #pragma unroll
     for (int e = 0; e < kViewPeDim; ++e) acc[e] = 0.f;
@@ -88,13 +134,26 @@ __global__ void __launch_bounds__(128) viewdir_term_bwd_kernel(const uint8_t* __
                 pe[3 + 6 * k + 3 + a] = c;
             }
         }
+        float s8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s8[e] = 0.f;
+        const long r0 = ray * div, r1 = (r0 + div < M) ? r0 + div : M;
+#pragma unroll 4
+        for (long row = r0 + sub; row < r1; row += 8) {
+            const int r = (int)(row & 127);
+            const uint8_t* p = dz + (size_t)(row >> 7) * kDzTileBytes + kDz10 + blk_off + (uint32_t)r * 128 +
+                               ((c16 ^ (uint32_t)(r & 7)) << 4);
+            float h[8];
+            unpack8(ldg_nc_v4(p), h);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s8[e] += h[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part[sub][l16 * 8 + e] = s8[e];
         __syncthreads();
         float dv = 0.f;
-        const long r0 = ray * div, r1 = (r0 + div < M) ? r0 + div : M;
-        for (long row = r0; row < r1; ++row) {
-            const uint8_t* tile = dz + (size_t)(row >> 7) * kDzTileBytes + kDz10;
-            dv += bf16_at(tile, j, (int)(row & 127));
-        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) dv += part[g][j];
 #pragma unroll
         for (int e = 0; e < kViewPeDim; ++e) acc[e] = fmaf(dv, pe[e], acc[e]);
         accb += dv;

@@ -89,6 +89,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
         : "memory");
 }
 
+// pull a contiguous global range into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // shared -> global bulk copy (bulk async-group completion)
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem),

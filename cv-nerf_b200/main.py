@@ -130,6 +130,7 @@ def batch_rays(rays_flat, chunk=32768, *, draws=None, **kwargs):
 
 
 batchify_rays = batch_rays  # the name render() calls in the reference (main.py:79)
+to8b = to_byte              # the name main() calls in the reference (main.py:404)
 
 
 def render(height, width, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1.,

@@ -163,7 +163,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short watchdog: a rank that misses a collective must fail the run, not hang the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
 
     torch.manual_seed(0)                      # same weights on every rank (create_model order)
     cfg = M.load_config(None, dtype="blender", white_bkg=True, n_coarse_samples=N_COARSE, n_fine_samples=N_FINE)
@@ -373,9 +375,9 @@ def time_train_stages(ts, image, pose):
     mark("dz_coarse")
     K.mlp_bwd_params(ts.act_c, ts.dz, graw_c, n * ts.s_c, rays, ts.s_c, False, ts.blob[0])
     mark("dw_coarse(+heads,view)")
-    ts.apply_gradients()
+    ts.apply_gradients(allreduce=False)     # this split runs on rank 0 only: no collectives here
     ts.coarse.packed(); ts.fine.packed(); ts.coarse.packed_bwd(); ts.fine.packed_bwd()
-    mark("allreduce+adam+repack")
+    mark("adam+repack")
     torch.cuda.synchronize()
     return {name: ev[i - 1][1].elapsed_time(e) for i, (name, e) in enumerate(ev) if i > 0}
 

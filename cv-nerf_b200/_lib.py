@@ -34,6 +34,9 @@ _SIGNATURES = {
     "nerf_composite_bwd": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_long,
                                           ctypes.c_int, ctypes.c_int, c_float_p, c_float_p, c_float_p,
                                           ctypes.c_void_p]),
+    "nerf_composite_maps": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_long, ctypes.c_int, c_float_p,
+                                           ctypes.c_void_p]),
+    "nerf_to_byte": (ctypes.c_int, [c_float_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p]),
     "nerf_sample_pdf": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                        c_float_p, ctypes.c_void_p]),
     "nerf_resample_merge": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_long, ctypes.c_int,

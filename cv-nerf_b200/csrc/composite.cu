@@ -194,6 +194,30 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
     }
 }
 
+// Optional extra maps from the compositing weights (the reference computes only sum(w) internally,
+// main.py:199, and returns none of them; these are nerf-pytorch raw2outputs' definitions, which the
+// reference's README lists as the model it follows): depth = sum w z, acc = sum w,
+// disp = 1 / max(1e-10, depth / acc).  One warp per ray.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+composite_maps_kernel(const float* __restrict__ w, const float* __restrict__ z, long n, int S,
+                      float* __restrict__ maps) {
+    const int lane = threadIdx.x & 31;
+    const long ray = (long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (ray >= n) return;
+    float depth = 0.f, acc = 0.f;
+    for (int i = lane; i < S; i += 32) {
+        const float wi = __ldg(w + ray * S + i);
+        depth = fmaf(wi, __ldg(z + ray * S + i), depth);
+        acc += wi;
+    }
+    depth = warp_sum(depth); acc = warp_sum(acc);
+    if (lane == 0) {
+        maps[3 * ray + 0] = depth;
+        maps[3 * ray + 1] = acc;
+        maps[3 * ray + 2] = 1.f / fmaxf(1e-10f, depth / acc);
+    }
+}
+
 // ---------------------------------------------------------------------------------- resampling
 
 // Monotone map float -> uint32 (NaNs sort last, like torch.sort).
@@ -365,4 +389,13 @@ extern "C" int nerf_resample_merge(const float* z_c, const float* w_c, const flo
     resample_merge_kernel<<<nerf::blocks_for(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
         z_c, w_c, u, n, S, m, z_f);
     return nerf::check_launch("nerf_resample_merge");
+}
+
+extern "C" int nerf_composite_maps(const float* weights, const float* z, long n, int S, float* maps_out,
+                                   void* stream) {
+    if (n < 0 || S < 1 || (n > 0 && (!weights || !z || !maps_out))) return nerf::arg_error("nerf_composite_maps");
+    if (n == 0) return 0;
+    composite_maps_kernel<<<nerf::blocks_for(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+        weights, z, n, S, maps_out);
+    return nerf::check_launch("nerf_composite_maps");
 }

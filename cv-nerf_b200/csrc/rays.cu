@@ -145,7 +145,32 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, long n, int
     z_out[idx] = z;
 }
 
+// to_byte / cont_to_byte8_im (model.py:134, utils.py:57): (255 * clip(x, 0, 1)).astype(uint8);
+// numpy multiplies in fp32 and astype truncates toward zero.  4 values per thread.
+__global__ void to_byte_kernel(const float* __restrict__ x, long n, uint8_t* __restrict__ out) {
+    long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    if (i + 4 <= n && ((uintptr_t)(x + i) & 15) == 0 && ((uintptr_t)(out + i) & 3) == 0) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i);
+        uchar4 o;
+        o.x = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(v.x, 0.f), 1.f));
+        o.y = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(v.y, 0.f), 1.f));
+        o.z = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(v.z, 0.f), 1.f));
+        o.w = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(v.w, 0.f), 1.f));
+        *reinterpret_cast<uchar4*>(out + i) = o;
+    } else {
+        for (long k = i; k < n && k < i + 4; ++k) out[k] = (uint8_t)__fmul_rn(255.f, fminf(fmaxf(x[k], 0.f), 1.f));
+    }
+}
+
 }  // namespace
+
+extern "C" int nerf_to_byte(const float* x, long n, unsigned char* out, void* stream) {
+    if (n < 0 || (n > 0 && (!x || !out))) return nerf::arg_error("nerf_to_byte");
+    if (n == 0) return 0;
+    to_byte_kernel<<<nerf::blocks_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    return nerf::check_launch("nerf_to_byte");
+}
 
 extern "C" int nerf_compute_rays(int H, int W, float focal, const float* pose, int row0, int row1,
                                  float* origins_out, float* dirs_out, void* stream) {

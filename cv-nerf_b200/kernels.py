@@ -142,6 +142,25 @@ def composite_bwd(raw, z, dirs, noise, white_bkg, grad_rgb, grad_w=None):
     return grad_raw
 
 
+def composite_maps(weights, z):
+    """weights [n,S], z [n,S] -> [n,3] = (depth, acc, disp)."""
+    lib = _lib.load()
+    weights, z = f32c(weights), f32c(z)
+    n, s = z.shape
+    out = torch.empty((n, 3), dtype=torch.float32, device=z.device)
+    check(lib.nerf_composite_maps(ptr(weights), ptr(z), n, s, ptr(out), stream_of(z)), "nerf_composite_maps")
+    return out
+
+
+def to_byte(x):
+    """uint8(255 * clip(x, 0, 1)) on the device (model.py:134)."""
+    lib = _lib.load()
+    x = f32c(x)
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(lib.nerf_to_byte(ptr(x), x.numel(), out.data_ptr(), stream_of(x)), "nerf_to_byte")
+    return out
+
+
 def sample_pdf(bins, weights, u):
     lib = _lib.load()
     bins, weights, u = f32c(bins), f32c(weights), f32c(u)

@@ -72,7 +72,7 @@ def _field(model, rays, z):
 
 
 def render_rays(ray_batch, coarse_model, q_fn=None, n_coarse_samples=64, perturb=0.0, n_fine_samples=0,
-                fine_model=None, white_bkg=False, noise=0.0, *, draws=None, extras=False):
+                fine_model=None, white_bkg=False, noise=0.0, *, draws=None, extras=False, maps=False):
     """[n,11] rays -> {'rgb_map': [n,3], 'rgb_c': [n,3]} (main.py:207-261).
 
     ``q_fn`` is accepted and ignored: when the models are cv_nerf_b200 ``Model`` instances the
@@ -110,6 +110,10 @@ def render_rays(ray_batch, coarse_model, q_fn=None, n_coarse_samples=64, perturb
     rgb_f, w_f = _composite(raw_f, z_f, rays, noise_for(z_f.shape, draws.noise_f), bool(white_bkg))
 
     out = {'rgb_map': rgb_f, 'rgb_c': rgb_c}
+    if maps:
+        # not returned by the reference (main.py:259-261); depth/acc/disp of the fine pass
+        m = K.composite_maps(w_f.detach(), z_f)
+        out.update(depth_map=m[:, 0], acc_map=m[:, 1], disp_map=m[:, 2])
     if extras:
         out.update(z_c=z_c, raw_c=raw_c, w_c=w_c, z_f=z_f, raw_f=raw_f, w_f=w_f)
     return out
@@ -161,27 +165,49 @@ def render(height, width, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True,
     return ret_list + [ret_dict]
 
 
-def render_full(render_poses, hwf, chunk, render_kwargs, save_dir=None, factor=0):
-    """Render every pose (main.py:102-124) -> np.ndarray [n_poses,H,W,3].  Frames are copied to
-    pinned host memory asynchronously so frame i+1 renders while frame i drains."""
+def render_full(render_poses, hwf, chunk, render_kwargs, save_dir=None, factor=0, *, as_bytes=False,
+                process_group=None, verbose=True):
+    """Render every pose (main.py:102-124) -> np.ndarray [n_poses,H,W,3] (float32, or uint8 with
+    ``as_bytes`` -- the to_byte quantisation of main.py:118 done on the device, 4x less to copy).
+
+    Frames are copied to pinned host memory asynchronously, so frame i+1 renders while frame i
+    drains (the reference synchronises on ``.cpu().numpy()`` per frame, main.py:116).  When
+    torch.distributed is initialised the frames are rendered round-robin across the ranks
+    (frame-parallel: no communication until the final gather) and every rank returns the full stack."""
+    from . import parallel as P
     height, width, focal = hwf
     if factor != 0:
         height, width, focal = height // factor, width // factor, focal / factor
     height, width = int(height), int(width)
     n = len(render_poses)
-    host = torch.empty((n, height, width, 3), dtype=torch.float32).pin_memory()
+    rank, world = P.world_info(process_group)
+    mine = P.frame_indices(n, world, rank)
+    dtype = torch.uint8 if as_bytes else torch.float32
     t = time.time()
-    with torch.no_grad():
-        for i, c2w in enumerate(render_poses):
-            rgb, _ = render(height, width, focal, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
-            host[i].copy_(rgb, non_blocking=True)
-    torch.cuda.synchronize()
-    rgbs = host.numpy()
-    if save_dir is not None:
+    if world == 1:
+        host = torch.empty((n, height, width, 3), dtype=dtype).pin_memory()
+        with torch.no_grad():
+            for i, c2w in enumerate(render_poses):
+                rgb, _ = render(height, width, focal, chunk=chunk, c2w=torch.as_tensor(c2w)[:3, :4], **render_kwargs)
+                host[i].copy_(K.to_byte(rgb) if as_bytes else rgb, non_blocking=True)
+        torch.cuda.synchronize()
+        rgbs = host.numpy()
+    else:
+        with torch.no_grad():
+            frames = []
+            for i in mine:
+                rgb, _ = render(height, width, focal, chunk=chunk, c2w=torch.as_tensor(render_poses[i])[:3, :4],
+                                **render_kwargs)
+                frames.append(K.to_byte(rgb) if as_bytes else rgb)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            local = torch.stack(frames, 0) if frames else torch.empty((0, height, width, 3), dtype=dtype, device=dev)
+            rgbs = P.gather_frames(local, n, process_group).cpu().numpy()
+    if save_dir is not None and rank == 0:
         os.makedirs(save_dir, exist_ok=True)
         for i in range(n):
-            np.save(os.path.join(save_dir, '{:03d}.npy'.format(i)), to_byte(rgbs[i]))
-    print(f"rendered {n} frames in {time.time() - t:.3f}s")
+            np.save(os.path.join(save_dir, '{:03d}.npy'.format(i)), rgbs[i] if as_bytes else to_byte(rgbs[i]))
+    if verbose and rank == 0:
+        print(f"rendered {n} frames in {time.time() - t:.3f}s")
     return rgbs
 
 

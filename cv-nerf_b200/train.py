@@ -144,9 +144,9 @@ class TrainStep:
         return self.loss
 
     @torch.no_grad()
-    def apply_gradients(self):
+    def apply_gradients(self, allreduce=True):
         """all-reduce (data parallel), Adam from the blobs, weight re-pack, learning-rate decay."""
-        if self.world > 1:
+        if self.world > 1 and allreduce:
             torch.distributed.all_reduce(self.blob, group=self.pg)
         self.it += 1
         for idx in range(2):
@@ -169,3 +169,35 @@ class TrainStep:
         """The current blob of network idx (0 coarse, 1 fine) unpacked into 24 tensors."""
         grads = [torch.empty_like(p) for p in self.params[idx]]
         return K.grad_unpack(self.blob[idx], grads)
+
+
+# ------------------------------------------------------------------ checkpoints
+def save_checkpoint(path, step, coarse_model, fine_model, optimizer=None, train_step=None):
+    """{step}.pt in the layout NeRF trainers of this family write (the reference's own
+    ``results/lego/{N}.pt`` files are listed in its .MISSING_LARGE_BLOBS but the saving code is
+    gone): state_dicts with the reference's parameter names (model.py:57-71)."""
+    blob = {"global_step": int(step), "coarse_state_dict": coarse_model.state_dict(),
+            "fine_state_dict": fine_model.state_dict()}
+    if optimizer is not None:
+        blob["optimizer_state_dict"] = optimizer.state_dict()
+    if train_step is not None:
+        blob["train_step"] = {"it": train_step.it, "lr": train_step.lr,
+                              "m": [[t.cpu() for t in ms] for ms in train_step.m],
+                              "v": [[t.cpu() for t in vs] for vs in train_step.v]}
+    torch.save(blob, path)
+
+
+def load_checkpoint(path, coarse_model, fine_model, optimizer=None, train_step=None, map_location=None):
+    blob = torch.load(path, map_location=map_location, weights_only=False)
+    coarse_model.load_state_dict(blob["coarse_state_dict"])
+    fine_model.load_state_dict(blob["fine_state_dict"])
+    _model.bump_param_epoch()
+    if optimizer is not None and "optimizer_state_dict" in blob:
+        optimizer.load_state_dict(blob["optimizer_state_dict"])
+    if train_step is not None and "train_step" in blob:
+        st = blob["train_step"]
+        train_step.it, train_step.lr = st["it"], st["lr"]
+        for dst, src in zip(train_step.m + train_step.v, st["m"] + st["v"]):
+            for d, s_ in zip(dst, src):
+                d.copy_(s_)
+    return blob["global_step"]

@@ -80,6 +80,15 @@ int nerf_composite_bwd(const float* raw, const float* z, const float* dirs, int 
                        const float* noise, long n, int S, int white_bkg, const float* grad_rgb,
                        const float* grad_weights, float* grad_raw, void* stream);
 
+/* Extra maps from the compositing weights: maps_out [n,3] = (depth = sum w z, acc = sum w,
+ * disp = 1 / max(1e-10, depth / acc)).  The reference forms only sum(w) (main.py:199) and returns
+ * none of them; definitions follow nerf-pytorch's raw2outputs. */
+int nerf_composite_maps(const float* weights, const float* z, long n, int S, float* maps_out,
+                        void* stream);
+
+/* to_byte / cont_to_byte8_im, model.py:134, utils.py:57: out[i] = uint8(255 * clip(x[i], 0, 1)). */
+int nerf_to_byte(const float* x, long n, unsigned char* out, void* stream);
+
 /* inv_transform_sampling, utils.py:4-53, with the uniform draws supplied by the caller.
  * bins [n,B], weights [n,B-1], u [n,m] -> samples_out [n,m] (unsorted). B <= 256. */
 int nerf_sample_pdf(const float* bins, const float* weights, const float* u, long n, int B, int m,

@@ -105,3 +105,24 @@ def test_ndc_constant_folding():
         want_w = torch.tensor(-1. / (504 / (2. * focal))).float().item()
         want_h = torch.tensor(-1. / (378 / (2. * focal))).float().item()
         assert cw == want_w and ch == want_h
+
+
+def test_checkpoint_round_trip_keeps_reference_keys(tmp_path):
+    """state_dict keys/shapes are the reference's (model.py:57-71), so its checkpoints load; the
+    save/load helpers round-trip both networks and the step counter (host-only, no kernels)."""
+    import cv_nerf_b200
+    from cv_nerf_b200.model import Model
+    from cv_nerf_b200.train import load_checkpoint, save_checkpoint
+    from oracle import nerf_oracle as O
+    torch.manual_seed(0)
+    a, b = Model(), Model()
+    sd = a.state_dict()
+    assert set(sd) == {f"{n}.{k}" for n in O.LAYER_NAMES for k in ("weight", "bias")}
+    for n in O.LAYER_NAMES:
+        assert tuple(sd[n + ".weight"].shape) == O.LAYER_SHAPES[n]
+    path = tmp_path / "000123.pt"
+    save_checkpoint(str(path), 123, a, b)
+    c, d = Model(), Model()
+    assert load_checkpoint(str(path), c, d) == 123
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), c.state_dict().values()))
+    assert all(torch.equal(x, y) for x, y in zip(b.state_dict().values(), d.state_dict().values()))

@@ -139,3 +139,45 @@ def test_drop_in_surface_small_calls():
         got2 = net(x).reshape(5, 64, 4)
     assert (got.cpu() - want).abs().max().item() <= 3e-2
     assert (got2.cpu() - want).abs().max().item() <= 3e-2
+
+
+def test_depth_acc_disp_maps_and_to_byte():
+    """Extra maps (depth, acc, disp: nerf-pytorch raw2outputs definitions over the reference's
+    weights) and the device-side to_byte against numpy."""
+    from cv_nerf_b200 import kernels as K
+    torch.manual_seed(1)
+    n, s = 300, 192
+    w = torch.rand(n, s) / s
+    z = torch.sort(torch.rand(n, s) * 4 + 2, -1).values
+    m = K.composite_maps(w.to(DEV), z.to(DEV)).cpu()
+    depth, acc = (w * z).sum(-1), w.sum(-1)
+    disp = 1. / torch.max(1e-10 * torch.ones_like(depth), depth / acc)
+    assert (m[:, 0] - depth).abs().max() <= 1e-5 and (m[:, 1] - acc).abs().max() <= 1e-6
+    assert ((m[:, 2] - disp).abs() / disp).max() <= 1e-5
+    x = torch.cat([torch.rand(1001, 3) * 1.4 - 0.2, torch.tensor([[0., 1., 0.5]])])
+    got = K.to_byte(x.to(DEV)).cpu().numpy()
+    want = (255 * np.clip(x.numpy(), 0, 1)).astype(np.uint8)
+    assert np.array_equal(got, want)
+
+
+def test_render_full_video_pipeline():
+    """render_full (main.py:102-124): float and uint8 stacks agree with per-frame render()."""
+    from cv_nerf_b200 import main as M
+    from cv_nerf_b200.model import Model
+    coarse_p, fine_p = O.init_field_params(0, 1.0, 5.0)
+    coarse, fine = load_model_params(Model(), coarse_p).to(DEV), load_model_params(Model(), fine_p).to(DEV)
+    kw = dict(coarse_model=coarse, fine_model=fine, n_coarse_samples=64, n_fine_samples=128, white_bkg=True,
+              ndc=False, near=2., far=6., perturb=False, noise=0.)
+    poses = [O.lego_pose(a, -30., 4.).to(DEV) for a in (-180., -90., 0.)]
+    torch.manual_seed(5)
+    vid = M.render_full(poses, [20, 24, 30.], 32768, kw, verbose=False)
+    torch.manual_seed(5)
+    vid8 = M.render_full(poses, [20, 24, 30.], 32768, kw, as_bytes=True, verbose=False)
+    assert vid.shape == (3, 20, 24, 3) and vid8.dtype == np.uint8
+    assert np.array_equal(vid8, (255 * np.clip(vid, 0, 1)).astype(np.uint8))
+    torch.manual_seed(5)
+    with torch.no_grad():
+        first, _ = M.render(20, 24, 30., c2w=poses[0][:3, :4], **kw)
+    assert np.array_equal(first.cpu().numpy(), vid[0])
+    half = M.render_full(poses[:1], [20, 24, 30.], 32768, kw, factor=2, verbose=False)
+    assert half.shape == (1, 10, 12, 3)

@@ -51,6 +51,12 @@ _SIGNATURES = {
                                     ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p,
                                     ctypes.c_void_p, ctypes.c_void_p]),
     "nerf_mlp_act_bytes": (ctypes.c_size_t, [ctypes.c_long]),
+    "nerf_model_host_tail_bytes": (ctypes.c_size_t, []),
+    "nerf_model_host_tail": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nerf_mlp_fwd_host_tail": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p,
+                                              ctypes.c_int, ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int,
+                                              c_float_p, ctypes.c_void_p]),
+    "nerf_mlp_fwd_use_pairs": (ctypes.c_int, [ctypes.c_int]),
     "nerf_packed_model_bwd_bytes": (ctypes.c_size_t, []),
     "nerf_pack_model_bwd": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p]),
     "nerf_mlp_dz_bytes": (ctypes.c_size_t, [ctypes.c_long]),

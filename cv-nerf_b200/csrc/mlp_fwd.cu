@@ -23,6 +23,7 @@
 // The two sub-tiles ping-pong: while the tensor core runs layer l of Y, group X runs the epilogue
 // of layer l of X, so MMA and epilogue overlap.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "mlp_bwd_layout.h"
@@ -63,7 +64,21 @@ struct Cfg {
     static_assert(off_w + RING * kSlotBytes <= kOffBar, "ring does not fit");
 };
 
+// Host copy of the head of the fp32 tail, passed BY VALUE inside the kernel parameters: the
+// epilogues then read biases / l_alpha / l11 through the constant bank with uniform loads
+// (LDCU + FADD2 R, R, UR), which costs nothing on the L1 data pipe the tensor core needs for its
+// operands (a warp-uniform LDS.128 costs 2 wavefronts there, an LDG.128 four).
+struct ConstTail {
+    float bias[9 * kHidden];
+    float walpha[kHidden];
+    float balpha[4];
+    float w11[3 * kL10Out];
+    float b11[4];
+};
+static_assert(sizeof(ConstTail) == (size_t)kTailW10View * 4, "ConstTail mirrors the head of the device tail");
+
 struct FwdParams {
+    ConstTail ct;            // valid for the CT kernel variants only
     const uint8_t* blob;     // packed model
     int in_mode;
     const float* in0;
@@ -193,36 +208,45 @@ __device__ __forceinline__ void lds_bias16(uint32_t addr, float4 (&dst)[4]) {
 // folded into the BF16 conversion (F2FP.RELU), so a column costs about one issue slot.
 // row_addr: shared-space address of this row's 128-byte line in block 0 of the A tile;
 // swz = (row & 7) << 4.
-template <int MODE, bool PROBE, int EXP>
+// CT: bias and l_alpha come from the kernel parameters (ct, layer l) instead of shared / global memory.
+// L >= 0: the layer index is a compile-time constant, so with CT every bias is an immediate
+// constant-bank operand of its FADD2 (no load instruction at all); L = -1: runtime index l.
+template <int MODE, bool PROBE, int EXP, bool CT, int NIT = 8, int L = -1>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
                                                 uint32_t bias_addr,
                                                 const float* __restrict__ walpha, float& sigma,
-                                                float* probe_row) {
+                                                float* probe_row, const ConstTail& ct, int l) {
     uint32_t v[2][16] = {};
     float4 b[2][4] = {};
     float2 sig2 = make_float2(0.f, 0.f);
     if (!(EXP & 4)) umma::tmem_ld16(tacc + c0, v[0]);
-    if (!(EXP & 2)) lds_bias16(bias_addr + c0 * 4, b[0]);
+    if (!CT && !(EXP & 2)) lds_bias16(bias_addr + c0 * 4, b[0]);
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < NIT; ++it) {
         const int c = c0 + it * 16;
-        if (it + 1 < 8 && !(EXP & 2)) lds_bias16(bias_addr + (c + 16) * 4, b[(it + 1) & 1]);
+        if (!CT && it + 1 < NIT && !(EXP & 2)) lds_bias16(bias_addr + (c + 16) * 4, b[(it + 1) & 1]);
         if (!(EXP & 4)) umma::tmem_wait_ld();
-        if (it + 1 < 8 && !(EXP & 4)) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
+        if (it + 1 < NIT && !(EXP & 4)) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
         const uint32_t(&cur)[16] = v[it & 1];
         const float4(&bc)[4] = b[it & 1];
         float2 h[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            h[2 * q] = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 0]), __uint_as_float(cur[q * 4 + 1])),
-                                  make_float2(bc[q].x, bc[q].y));
-            h[2 * q + 1] = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 2]), __uint_as_float(cur[q * 4 + 3])),
-                                      make_float2(bc[q].z, bc[q].w));
+            float2 b0 = make_float2(bc[q].x, bc[q].y), b1 = make_float2(bc[q].z, bc[q].w);
+            if (CT) {
+                const float* bl = ct.bias + (L >= 0 ? L : l) * kHidden + c + q * 4;
+                b0 = make_float2(bl[0], bl[1]);
+                b1 = make_float2(bl[2], bl[3]);
+            }
+            h[2 * q] = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 0]), __uint_as_float(cur[q * 4 + 1])), b0);
+            h[2 * q + 1] = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 2]), __uint_as_float(cur[q * 4 + 3])), b1);
         }
         if (MODE == 1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(walpha + c) + q);
+                float4 w;
+                if (CT) w = make_float4(ct.walpha[c + q * 4], ct.walpha[c + q * 4 + 1], ct.walpha[c + q * 4 + 2], ct.walpha[c + q * 4 + 3]);
+                else w = __ldg(reinterpret_cast<const float4*>(walpha + c) + q);
                 h[2 * q].x = fmaxf(h[2 * q].x, 0.f); h[2 * q].y = fmaxf(h[2 * q].y, 0.f);
                 h[2 * q + 1].x = fmaxf(h[2 * q + 1].x, 0.f); h[2 * q + 1].y = fmaxf(h[2 * q + 1].y, 0.f);
                 sig2 = __ffma2_rn(make_float2(w.x, w.y), h[2 * q], sig2);
@@ -255,24 +279,38 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t 
     if (MODE == 1) sigma += sig2.x + sig2.y;
 }
 
+// CT epilogue of hidden layer l (0..8) with the layer index turned into a template constant.
+template <int NIT>
+__device__ __forceinline__ void epilogue_hidden_ct(int l, uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
+                                                   float& sigma, const ConstTail& ct) {
+    switch (l) {
+#define NERF_CT_LAYER(LL, MODE) \
+        case LL: epilogue_hidden<MODE, false, 0, true, NIT, LL>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, LL); break;
+        NERF_CT_LAYER(0, 0) NERF_CT_LAYER(1, 0) NERF_CT_LAYER(2, 0) NERF_CT_LAYER(3, 0) NERF_CT_LAYER(4, 0)
+        NERF_CT_LAYER(5, 0) NERF_CT_LAYER(6, 0) NERF_CT_LAYER(7, 1)
+        default: epilogue_hidden<2, false, 0, true, NIT, 8>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 8); break;
+#undef NERF_CT_LAYER
+    }
+}
+
 // l10 (+ hoisted view term, ReLU) and l11 in FP32 over this thread's 64 columns [c0, c0+64):
 // partial rgb_raw.
 // SAVE: h10 (post-ReLU, BF16) is written to blocks 0..1 of the A tile for the activation record.
-template <bool PROBE, bool SAVE>
+template <bool PROBE, bool SAVE, bool CT, int NIT = 4>
 __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float* __restrict__ vt,
                                              const float* __restrict__ w11, float (&rgb)[3],
-                                             float* probe_row, uint32_t row_addr, uint32_t swz) {
+                                             float* probe_row, uint32_t row_addr, uint32_t swz, const ConstTail& ct) {
     uint32_t v[2][16];
     float4 t[2][4];
     umma::tmem_ld16(tacc + c0, v[0]);
     load_bias16(vt + c0, t[0]);
     float2 acc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < NIT; ++it) {
         const int c = c0 + it * 16;
-        if (it + 1 < 4) load_bias16(vt + c + 16, t[(it + 1) & 1]);
+        if (it + 1 < NIT) load_bias16(vt + c + 16, t[(it + 1) & 1]);
         umma::tmem_wait_ld();
-        if (it + 1 < 4) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
+        if (it + 1 < NIT) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
         const uint32_t(&cur)[16] = v[it & 1];
         const float4(&tc)[4] = t[it & 1];
         uint32_t pk[8];
@@ -290,7 +328,13 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(w11 + k * kL10Out + c) + q);
+                float4 w;
+                if (CT) {
+                    const float* wk = ct.w11 + k * kL10Out + c + q * 4;
+                    w = make_float4(wk[0], wk[1], wk[2], wk[3]);
+                } else {
+                    w = __ldg(reinterpret_cast<const float4*>(w11 + k * kL10Out + c) + q);
+                }
                 acc[k] = __ffma2_rn(make_float2(w.x, w.y), ha, acc[k]);
                 acc[k] = __ffma2_rn(make_float2(w.z, w.w), hb, acc[k]);
             }
@@ -314,8 +358,15 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
 }
 
 // ---------------------------------------------------------------------------- kernel
-template <bool PROBE, class CFG, bool SAVE = false>
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P) {
+// WIDE (inference, CT only): all 16 epilogue warps work on ONE sub-tile at a time (four threads per
+// row, 64 columns each) and alternate between the two sub-tiles, instead of 8 warps per sub-tile.
+// The MMA -> epilogue -> MMA chain of a sub-tile is latency-bound on the epilogue; with twice the
+// warps on it the next layer's operand is ready in about half the time and the tensor core idles less.
+template <bool PROBE, class CFG, bool SAVE = false, bool CT = false, bool WIDE = false>
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
+    static_assert(!WIDE || (CT && !SAVE && !PROBE), "WIDE is an inference-only variant");
+    constexpr bool kStageBias = !CT;          // per-layer bias staged in shared memory
+    constexpr bool kGroupSync = !CT || SAVE;  // group barriers around the staging / the record copies
     constexpr int kRing = CFG::ring;
     constexpr uint32_t kOffPE = CFG::off_pe, kOffW = CFG::off_w;
     // SWIZZLE_128B atoms need 1024-byte aligned tiles (the kernel has no static shared memory, so
@@ -342,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
             umma::mbar_init(bar_w_empty + 8 * s, 1);
         }
         for (int g = 0; g < 2; ++g) {
-            umma::mbar_init(bar_a_ready + 8 * g, kEpiWarpsPerGroup * 32);
+            umma::mbar_init(bar_a_ready + 8 * g, (WIDE ? 2 : 1) * kEpiWarpsPerGroup * 32);
             umma::mbar_init(bar_acc_full + 8 * g, 1);
         }
         umma::fence_barrier_init();
@@ -423,6 +474,73 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
                 }
             }
         }
+    } else if (WIDE) {
+        // ===================== one 16-warp epilogue crew, alternating between the sub-tiles =====================
+        const int cg = (warp - 2) >> 2;          // column group: columns [64 cg, 64 cg + 64) of a hidden layer
+        const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;
+        const uint32_t quad_bar = 1 + quad;      // named barrier of the four warps sharing rows
+        const uint32_t swz = (uint32_t)(row & 7) << 4;
+        float sigma[2] = {0.f, 0.f};
+        uint32_t n_full[2] = {0, 0};
+        // PE of sub-tile g of tile pair `pair` (two of the four threads of a row encode, all arrive)
+        auto in_stage = [&](int g, long pair) {
+            const long grow_raw = (pair * 2 + g) * kTileM + row;
+            const long grow = grow_raw < P.M ? grow_raw : P.M - 1;
+            uint8_t* pe_tile = smem + kOffPE + g * 16384;
+            if (cg == 0) input_stage<0>(P, grow, pe_tile, row);
+            else if (cg == 1) input_stage<1>(P, grow, pe_tile, row);
+            umma::fence_proxy_async_smem();
+            umma::mbar_arrive(bar_a_ready + 8 * g);
+        };
+        if ((long)blockIdx.x < n_pairs) { in_stage(0, blockIdx.x); in_stage(1, blockIdx.x); }
+        for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+#pragma unroll 1
+            for (int l = 0; l < kNumMmaLayers; ++l) {
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
+                    const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
+                    umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full[g] & 1);
+                    ++n_full[g];
+                    umma::tc_fence_after();
+                    if (l < 9) {
+                        const int c0 = cg * 64;
+                        float sg = 0.f;
+                        epilogue_hidden_ct<4>(l, tacc, c0, a_row_addr, swz, sg, P.ct);
+                        if (l == 7) sigma[g] = sg;
+                        umma::fence_proxy_async_smem();
+                        umma::tc_fence_before();
+                        umma::mbar_arrive(bar_a_ready + 8 * g);
+                    } else {
+                        const long grow_raw = (pair * 2 + g) * kTileM + row;
+                        const bool valid = grow_raw < P.M;
+                        const long grow = valid ? grow_raw : P.M - 1;
+                        float rgb[3];
+                        const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
+                        epilogue_rgb<false, false, true, 2>(tacc, cg * 32, vt, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
+                        umma::tc_fence_before();
+                        // FP32 hand-over between the four threads of a row, inside the row's own PE
+                        // line (free between l6's MMA and the next tile's encoding)
+                        float4* xchg = reinterpret_cast<float4*>(smem + kOffPE + g * 16384 + row * 128);
+                        if (cg > 0) xchg[cg - 1] = make_float4(rgb[0], rgb[1], rgb[2], sigma[g]);
+                        umma::named_bar_sync(quad_bar, 128);
+                        if (cg == 0 && valid) {
+                            const float4 p1 = xchg[0], p2 = xchg[1], p3 = xchg[2];
+                            float4 o;
+                            o.x = rgb[0] + p1.x + p2.x + p3.x + P.ct.b11[0];
+                            o.y = rgb[1] + p1.y + p2.y + p3.y + P.ct.b11[1];
+                            o.z = rgb[2] + p1.z + p2.z + p3.z + P.ct.b11[2];
+                            o.w = sigma[g] + p1.w + p2.w + p3.w + P.ct.balpha[0];
+                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
+                        }
+                        // the next tile's encoding overwrites the hand-over slots: wait for the reads
+                        umma::named_bar_sync(quad_bar, 128);
+                        if (pair + gridDim.x < n_pairs) in_stage(g, pair + gridDim.x);
+                    }
+                }
+            }
+        }
     } else {
         // ===================== epilogue groups =====================
         const int ew = warp - 2;
@@ -443,8 +561,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
         const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
         const float* tail = reinterpret_cast<const float*>(P.blob + kWeightBytes);
         uint32_t n_full = 0;
-        umma::st_shared_f32(bias_addr + gtid * 4, __ldg(tail + kTailBias + gtid));
-        umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+        if (kStageBias) {
+            umma::st_shared_f32(bias_addr + gtid * 4, __ldg(tail + kTailBias + gtid));
+            umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+        }
         for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             const long grow_raw = (pair * 2 + g) * kTileM + row;
             const bool valid = grow_raw < P.M;
@@ -472,27 +592,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
 #pragma unroll 1
             for (int l = 0; l < kNumMmaLayers; ++l) {
                 long long t0 = PROBE ? clock64() : 0;
-                umma::mbar_wait(bar_acc_full + 8 * g, n_full & 1);
+                umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
                 if (PROBE) t_wait0 += clock64() - t0;
                 ++n_full;
                 umma::tc_fence_after();
                 if (PROBE) probe_row = (P.probe_out && P.probe_layer == l && valid) ? P.probe_out + grow * 256 : nullptr;
                 if (l < 9) {
                     const int c0 = half * 128;
-                    if (l == 7) {
-                        epilogue_hidden<1, PROBE, CFG::exp>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row);
+                    if (CT && !PROBE) {
+                        epilogue_hidden_ct<8>(l, tacc, c0, a_row_addr, swz, sigma, P.ct);
+                    } else if (l == 7) {
+                        epilogue_hidden<1, PROBE, CFG::exp, CT>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row, P.ct, l);
                     } else if (l == 8) {
-                        epilogue_hidden<2, PROBE, CFG::exp>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row);
+                        epilogue_hidden<2, PROBE, CFG::exp, CT>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row, P.ct, l);
                     } else {
-                        epilogue_hidden<0, PROBE, CFG::exp>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row);
+                        epilogue_hidden<0, PROBE, CFG::exp, CT>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row, P.ct, l);
                     }
                     umma::fence_proxy_async_smem();
                     umma::tc_fence_before();
                     umma::mbar_arrive(bar_a_ready + 8 * g);
                     // stage the next hidden layer's bias (after l9 comes l1 of the next tile); both
                     // barriers fall into the time the group would wait for the tensor core anyway
-                    const float bnext = __ldg(tail + kTailBias + (l == 8 ? 0 : l + 1) * kHidden + gtid);
-                    umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+                    float bnext = 0.f;
+                    if (kStageBias) bnext = __ldg(tail + kTailBias + (l == 8 ? 0 : l + 1) * kHidden + gtid);
+                    if (kGroupSync) umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
                     if (SAVE && gtid == 0) {
                         // activation record: h_{l+1} (l9's output for l == 8) straight from the A tile;
                         // the copy must have read the tile before the next epilogue overwrites it
@@ -502,12 +625,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
                         }
                         umma::bulk_wait_read0();
                     }
-                    umma::st_shared_f32(bias_addr + gtid * 4, bnext);
-                    umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+                    if (kStageBias) umma::st_shared_f32(bias_addr + gtid * 4, bnext);
+                    if (kGroupSync) umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
                 } else {
                     float rgb[3];
                     const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                    epilogue_rgb<PROBE, SAVE>(tacc, half * 64, vt, tail + kTailW11, rgb, probe_row, a_row_addr, swz);
+                    epilogue_rgb<PROBE, SAVE, CT>(tacc, half * 64, vt, tail + kTailW11, rgb, probe_row, a_row_addr, swz, P.ct);
                     umma::tc_fence_before();
                     if (SAVE) {
                         umma::fence_proxy_async_smem();
@@ -524,10 +647,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
                         const float4 o2 = *xchg;
                         if (valid) {
                             float4 o;
-                            o.x = rgb[0] + o2.x + __ldg(tail + kTailB11 + 0);
-                            o.y = rgb[1] + o2.y + __ldg(tail + kTailB11 + 1);
-                            o.z = rgb[2] + o2.z + __ldg(tail + kTailB11 + 2);
-                            o.w = sigma + o2.w + __ldg(tail + kTailBAlpha);
+                            o.x = rgb[0] + o2.x + (CT ? P.ct.b11[0] : __ldg(tail + kTailB11 + 0));
+                            o.y = rgb[1] + o2.y + (CT ? P.ct.b11[1] : __ldg(tail + kTailB11 + 1));
+                            o.z = rgb[2] + o2.z + (CT ? P.ct.b11[2] : __ldg(tail + kTailB11 + 2));
+                            o.w = sigma + o2.w + (CT ? P.ct.balpha[0] : __ldg(tail + kTailBAlpha));
                             reinterpret_cast<float4*>(P.raw_out)[grow] = o;
                         }
                     }
@@ -556,7 +679,215 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const FwdParams P)
     }
 }
 
-using FwdKernel = void (*)(const FwdParams);
+// ---------------------------------------------------------------------------- CTA-pair kernel
+// Inference variant on tcgen05 cta_group::2: the two CTAs of a cluster (one TPC) run ONE
+// M=256 x N=256 MMA per K step over their two 128-row sub-tiles, and each CTA stages only ITS
+// half of every weight chunk (128 of the 256 output rows).  Per SM and tile-layer that halves both
+// the bytes the TMA engine writes into shared memory and the B-operand bytes the tensor core
+// reads from it -- the traffic that saturates the shared-memory pipe of the single-CTA kernel
+// (A 64 KB + B 128 KB + fill 128 KB + epilogue stores 64 KB per 2048 MMA cycles).
+//   tiles        a cluster takes four tiles at a time: CTA r, group g -> tile 4q + 2r + g
+//   warp 0       (both CTAs) producer of the CTA's own 16 KB half-chunks, ring of 4
+//   warp 1       leader: MMA issuer (tcgen05.mma.cta_group::2, commits multicast to both CTAs);
+//                peer: relays "my half-chunk has landed" to the leader's w_peer barriers
+//   warps 2-17   epilogue groups as in the single-CTA kernel; a group signals "A tile written" with
+//                one arrive (local in the leader, remote from the peer) after a group barrier
+constexpr int kPairRing = 4;
+constexpr uint32_t kPairOffBar = kOffW + kPairRing * kStageBytes;
+static_assert(kPairOffBar == kOffBar, "same footprint as the single-CTA kernel");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = umma::smem_u32(smem);
+    if ((sbase & 1023u) != 0) __trap();
+    const uint32_t bar_w_full = sbase + kPairOffBar;              // [4] own half-chunk landed
+    const uint32_t bar_w_empty = bar_w_full + 8 * kPairRing;      // [4] MMAs done with the slot (multicast commit)
+    const uint32_t bar_w_peer = bar_w_empty + 8 * kPairRing;      // [4] leader only: peer's half-chunk landed
+    const uint32_t bar_a_ready = bar_w_peer + 8 * kPairRing;      // [2] leader only: both CTAs' A tiles written
+    const uint32_t bar_acc_full = bar_a_ready + 16;               // [2] accumulators complete (multicast commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kPairOffBar + 8 * (3 * kPairRing + 4));
+    static_assert(8 * (3 * kPairRing + 4) + 4 <= 256, "barrier region");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = umma::cluster_ctarank();
+    const long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const long n_tiles = (P.M + kTileM - 1) / kTileM;
+    const long n_quads = (n_tiles + 3) / 4;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kPairRing; ++s) {
+            umma::mbar_init(bar_w_full + 8 * s, 1);
+            umma::mbar_init(bar_w_empty + 8 * s, 1);
+            umma::mbar_init(bar_w_peer + 8 * s, 1);
+        }
+        for (int g = 0; g < 2; ++g) {
+            umma::mbar_init(bar_a_ready + 8 * g, 2);
+            umma::mbar_init(bar_acc_full + 8 * g, 1);
+        }
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) {
+        umma::tmem_alloc_pair(umma::smem_u32(tmem_slot), 512);
+        umma::tmem_relinquish_pair();
+    }
+    umma::tc_fence_before();
+    umma::cluster_sync_all();          // barriers of BOTH CTAs initialised before any remote arrive
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer: this CTA's half of every weight chunk =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+                for (int l = 0; l < kNumMmaLayers; ++l) {
+                    const int first = layer_first_stage(l), chunks = layer_chunks(l), halves = layer_halves(l);
+                    // N = 256: stage (chunk, half = rank); N = 128 (l10): rows [64 rank, 64 rank + 64) of the stage
+                    const uint32_t bytes = halves == 2 ? kStageBytes : kStageBytes / 2;
+                    for (int g = 0; g < 2; ++g) {
+                        for (int j = 0; j < chunks; ++j, ++it) {
+                            const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
+                            umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                            umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
+                            const uint8_t* src = halves == 2
+                                ? P.blob + (size_t)(first + j * 2 + (int)rank) * kStageBytes
+                                : P.blob + (size_t)(first + j) * kStageBytes + (size_t)rank * (kStageBytes / 2);
+                            umma::bulk_g2s(sbase + kOffW + slot * kStageBytes, src, bytes, bar_w_full + 8 * slot);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 1) {
+            // ===================== peer: relay slot arrivals to the leader =====================
+            uint32_t it = 0;
+            const uint32_t leader_w_peer = umma::map_to_cta(bar_w_peer, 0);
+            for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+                for (int l = 0; l < kNumMmaLayers; ++l) {
+                    const int chunks = layer_chunks(l);
+                    for (int gj = 0; gj < 2 * chunks; ++gj, ++it) {
+                        const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
+                        umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                        umma::mbar_arrive_remote(leader_w_peer + 8 * slot);
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            // ===================== leader: MMA issuer for the pair =====================
+            uint32_t it = 0, n_ready[2] = {0, 0};
+            constexpr uint32_t kIdescPair256 = umma::instr_desc_bf16(256, 256);
+            constexpr uint32_t kIdescPair128 = umma::instr_desc_bf16(256, 128);
+            for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+                for (int l = 0; l < kNumMmaLayers; ++l) {
+                    const int chunks = layer_chunks(l);
+                    const uint32_t idesc = layer_halves(l) == 2 ? kIdescPair256 : kIdescPair128;
+                    for (int g = 0; g < 2; ++g) {
+                        umma::mbar_wait_cluster(bar_a_ready + 8 * g, n_ready[g] & 1);
+                        ++n_ready[g];
+                        umma::tc_fence_after();
+                        const uint32_t d_base = tmem_base + g * 256;
+                        const uint32_t a_tile = sbase + kOffA + g * 65536;
+                        const uint32_t pe_tile = sbase + kOffPE + g * 16384;
+                        for (int j = 0; j < chunks; ++j) {
+                            uint32_t a_addr;
+                            if (l == 0) a_addr = pe_tile;
+                            else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
+                            else a_addr = a_tile + j * 16384;
+                            const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
+                            ++it;
+                            umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                            umma::mbar_wait_cluster(bar_w_peer + 8 * slot, ph);
+                            umma::tc_fence_after();
+                            const uint32_t b_addr = sbase + kOffW + slot * kStageBytes;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                umma::mma_bf16_ss_pair(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
+                                                       umma::smem_desc_sw128(b_addr + kk * 32), idesc,
+                                                       (j > 0 || kk > 0) ? 1u : 0u);
+                            }
+                            umma::mma_commit_pair(bar_w_empty + 8 * slot);
+                        }
+                        umma::mma_commit_pair(bar_acc_full + 8 * g);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue groups =====================
+        const int ew = warp - 2;
+        const int g = ew >> 3;
+        const int half = (ew >> 2) & 1;
+        const int quadrant = warp & 3;
+        const int row = quadrant * 32 + lane;
+        const uint32_t pair_bar = 1 + g * 4 + quadrant;
+        const uint32_t group_bar = 9 + g;
+        const int gtid = (ew & 7) * 32 + lane;
+        const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
+        const uint32_t swz = (uint32_t)(row & 7) << 4;
+        uint8_t* pe_tile = smem + kOffPE + g * 16384;
+        float4* xchg = reinterpret_cast<float4*>(pe_tile + row * 128);
+        const uint32_t tacc = tmem_base + ((uint32_t)(quadrant * 32) << 16) + g * 256;
+        const uint32_t leader_a_ready = umma::map_to_cta(bar_a_ready + 8 * g, 0);
+        // "this group's A tile is written": every writer has fenced its stores towards the async
+        // proxy and its TMEM loads towards the tensor core; one thread tells the leader's MMA warp
+        auto signal_a_ready = [&]() {
+            umma::fence_proxy_async_smem();
+            umma::tc_fence_before();
+            umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+            if (gtid == 0) umma::mbar_arrive_remote(leader_a_ready);
+        };
+        uint32_t n_full = 0;
+        for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+            const long grow_raw = (quad * 4 + rank * 2 + g) * kTileM + row;
+            const bool valid = grow_raw < P.M;
+            const long grow = valid ? grow_raw : P.M - 1;
+            if (half == 0) input_stage<0>(P, grow, pe_tile, row);
+            else input_stage<1>(P, grow, pe_tile, row);
+            signal_a_ready();
+            float sigma = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < kNumMmaLayers; ++l) {
+                umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
+                ++n_full;
+                umma::tc_fence_after();
+                if (l < 9) {
+                    const int c0 = half * 128;
+                    epilogue_hidden_ct<8>(l, tacc, c0, a_row_addr, swz, sigma, P.ct);
+                    signal_a_ready();
+                } else {
+                    float rgb[3];
+                    const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
+                    epilogue_rgb<false, false, true>(tacc, half * 64, vt, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
+                    umma::tc_fence_before();
+                    if (half == 1) *xchg = make_float4(rgb[0], rgb[1], rgb[2], sigma);
+                    umma::named_bar_sync(pair_bar, 64);
+                    if (half == 0) {
+                        const float4 o2 = *xchg;
+                        if (valid) {
+                            float4 o;
+                            o.x = rgb[0] + o2.x + P.ct.b11[0];
+                            o.y = rgb[1] + o2.y + P.ct.b11[1];
+                            o.z = rgb[2] + o2.z + P.ct.b11[2];
+                            o.w = sigma + o2.w + P.ct.balpha[0];
+                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
+                        }
+                    }
+                    umma::named_bar_sync(pair_bar, 64);
+                }
+            }
+        }
+    }
+    umma::tc_fence_before();
+    umma::cluster_sync_all();          // no CTA frees tensor memory while its partner still uses it
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+using FwdKernel = void (*)(const FwdParams);   // (__grid_constant__ does not change the type)
 
 // variant 0 = production; 1 = probe (production config + debug outputs);
 // 2, 3 = pipeline-timing experiments (probe kernels with other ring depths)
@@ -571,13 +902,15 @@ FwdKernel fwd_variant(int v) {
         case 6: return mlp_fwd_kernel<true, Cfg<kRing, false, 4>>;
         case 7: return mlp_fwd_kernel<true, Cfg<kRing, false, 7>>;
         case 8: return mlp_fwd_kernel<false, Cfg<kRing, false>, true>;   // training: saves activations
+        case 9: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;   // inference with the host tail
+        case 10: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true, true>;   // + 16-warp epilogue crew
         default: return nullptr;
     }
 }
 
 int launch_fwd(const FwdParams& P, int variant, void* stream) {
     static int sm_count = 0;
-    static bool configured[9] = {};
+    static bool configured[11] = {};
     FwdKernel k = fwd_variant(variant);
     if (!k) return nerf::arg_error("nerf_mlp_fwd: variant");
     if (sm_count == 0) {
@@ -603,6 +936,35 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
     const unsigned grid = (unsigned)(n_pairs < sm_count ? n_pairs : sm_count);
     k<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
     return nerf::check_launch("nerf_mlp_fwd");
+}
+
+// measured on B200 (profiles/r01_fwd_variants_ncu.txt): 0 is the fastest of the three
+int g_use_pairs = 0;
+
+int launch_fwd_pair(const FwdParams& P, void* stream) {
+    static int sm_count = 0;
+    static bool configured = false;
+    if (sm_count == 0) {
+        sm_count = nerf_b200_sm_count();
+        if (sm_count <= 0) {
+            sm_count = 0;
+            nerf::set_last_error("nerf_mlp_fwd setup: no CUDA device");
+            return (int)cudaErrorNoDevice;
+        }
+    }
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) {
+            nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    const long n_tiles = (P.M + kTileM - 1) / kTileM;
+    const long n_quads = (n_tiles + 3) / 4;
+    const long clusters = n_quads < sm_count / 2 ? n_quads : sm_count / 2;
+    mlp_fwd_pair_kernel<<<(unsigned)(2 * clusters), kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    return nerf::check_launch("nerf_mlp_fwd (CTA pairs)");
 }
 
 int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0, const float* in1,
@@ -634,6 +996,43 @@ extern "C" int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, c
     if (act_save && ((uintptr_t)act_save & 15)) return nerf::arg_error("nerf_mlp_fwd: act_save must be 16-byte aligned");
     P.act_save = (uint8_t*)act_save;
     return launch_fwd(P, act_save ? 8 : 0, stream);
+}
+
+extern "C" size_t nerf_model_host_tail_bytes(void) { return sizeof(ConstTail); }
+
+// Copies the part of the packed blob's fp32 tail that the epilogues consume into HOST memory
+// (asynchronously: synchronise the stream before passing it to nerf_mlp_fwd_host_tail).
+extern "C" int nerf_model_host_tail(const void* packed, void* host_tail_out, void* stream) {
+    if (!packed || !host_tail_out) return nerf::arg_error("nerf_model_host_tail");
+    cudaError_t e = cudaMemcpyAsync(host_tail_out, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail),
+                                    cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        nerf::set_last_error("nerf_model_host_tail: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// nerf_mlp_fwd with biases, l_alpha and l11 travelling in the kernel parameters (inference path).
+extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail, int in_mode, const float* in0,
+                                      const float* in1, int in_stride, long M, int S, const float* vterm,
+                                      int vterm_div, float* raw_out, void* stream) {
+    if (!host_tail) return nerf::arg_error("nerf_mlp_fwd_host_tail: host_tail");
+    FwdParams P;
+    int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out);
+    if (rc) return rc;
+    if (M == 0) return 0;
+    memcpy(&P.ct, host_tail, sizeof(ConstTail));
+    return g_use_pairs == 1 ? launch_fwd_pair(P, stream) : launch_fwd(P, g_use_pairs == 2 ? 10 : 9, stream);
+}
+
+// Kernel behind nerf_mlp_fwd_host_tail: 0 (default) single CTA per SM; 1 CTA pairs (tcgen05
+// cta_group::2, half the weight bytes staged and read per SM); 2 single CTA with one 16-warp epilogue
+// crew.  All give the same results; the switch exists for A/B timing and tests.
+extern "C" int nerf_mlp_fwd_use_pairs(int enable) {
+    const int old = g_use_pairs;
+    if (enable >= 0) g_use_pairs = enable;     // 0 single CTA, 1 CTA pairs, 2 single CTA with the 16-warp crew
+    return old;
 }
 
 // Debug entry (tests only): additionally dumps the FP32 post-activation output of MMA layer

@@ -69,6 +69,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Same wait for a FULLY ACTIVE warp: the loop condition goes through a vote, so the compiler can
+// prove that control flow after the wait is warp-uniform (and keep using the uniform datapath:
+// LDCU constant loads, UR operands) instead of treating the spin loop as a divergence point.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+    long long t0 = clock64();
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (clock64() - t0 > NERF_MBAR_TIMEOUT_CYCLES) {
+            printf("nerf_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
 // ------------------------------------------------------------------ proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -226,10 +226,29 @@ def freq_encode(x, n_freq):
     return out.reshape(*x.shape[:-1], out.shape[-1])
 
 
+def use_pairs(enable=None):
+    """Select the CTA-pair (tcgen05 cta_group::2) field kernel for the inference fast path (default
+    on); returns the previous setting.  ``None`` only queries."""
+    return int(_lib.load().nerf_mlp_fwd_use_pairs(-1 if enable is None else int(enable)))
+
+
+def model_host_tail(packed):
+    """Pinned host copy of the blob's biases / l_alpha / l11 for the inference fast path
+    (synchronises the current stream once)."""
+    lib = _lib.load()
+    host = torch.empty(int(lib.nerf_model_host_tail_bytes()), dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream(packed.device)
+    check(lib.nerf_model_host_tail(packed.data_ptr(), host.data_ptr(), stream.cuda_stream), "nerf_model_host_tail",
+          launches=0)
+    stream.synchronize()
+    return host
+
+
 def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_stride=0,
-            probe_layer=None, act_save=None):
+            probe_layer=None, act_save=None, host_tail=None):
     """-> raw [rows,4] (and the probed layer's FP32 activations when probe_layer is given).
-    act_save: uint8 buffer of act_bytes(rows) that receives the activation records (training)."""
+    act_save: uint8 buffer of act_bytes(rows) that receives the activation records (training).
+    host_tail: model_host_tail(packed) -> the inference fast path (same results)."""
     lib = _lib.load()
     raw = torch.empty((rows, 4), dtype=torch.float32, device=in0.device)
     st = stream_of(in0)
@@ -238,9 +257,14 @@ def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_
         if STATS.timed is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream(in0.device))
-        check(lib.nerf_mlp_fwd(packed.data_ptr(), mode, ptr(in0), ptr(in1), in_stride, rows, samples_per_ray,
-                               ptr(vterm), vterm_div, ptr(raw), None if act_save is None else act_save.data_ptr(),
-                               st), "nerf_mlp_fwd")
+        if host_tail is not None and act_save is None:
+            check(lib.nerf_mlp_fwd_host_tail(packed.data_ptr(), host_tail.data_ptr(), mode, ptr(in0), ptr(in1),
+                                             in_stride, rows, samples_per_ray, ptr(vterm), vterm_div, ptr(raw), st),
+                  "nerf_mlp_fwd_host_tail")
+        else:
+            check(lib.nerf_mlp_fwd(packed.data_ptr(), mode, ptr(in0), ptr(in1), in_stride, rows, samples_per_ray,
+                                   ptr(vterm), vterm_div, ptr(raw),
+                                   None if act_save is None else act_save.data_ptr(), st), "nerf_mlp_fwd")
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(in0.device))
             STATS.timed.append((ev[0], ev[1], rows))

@@ -91,6 +91,8 @@ class Model(nn.Module):
         self._packed_key = None
         self._packed_bwd = None
         self._packed_bwd_key = None
+        self._host_tail = None
+        self._host_tail_key = None
 
     @staticmethod
     def _encoding_dim(num_comp, L):
@@ -117,6 +119,15 @@ class Model(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def host_tail(self):
+        """Host copy of the biases and heads for the inference kernel variant (one stream
+        synchronisation per weight change; the training path never calls this)."""
+        packed = self.packed()
+        if self._host_tail is None or self._host_tail_key != self._packed_key:
+            self._host_tail = K.model_host_tail(packed)
+            self._host_tail_key = self._packed_key
+        return self._host_tail
+
     def packed_bwd(self):
         """Transposed BF16 weights for the backward dZ chain (same caching rule as packed())."""
         params = self.ordered_params()
@@ -134,7 +145,7 @@ class Model(nn.Module):
         vterm = K.viewdir_term(packed, spec["dirs"], embedded=spec.get("dirs_embedded", False))
         return K.mlp_fwd(packed, spec["mode"], spec["in0"], spec.get("in1"), spec["rows"],
                          spec.get("samples", 1), vterm, spec["vterm_div"], spec.get("in_stride", 0),
-                         act_save=act_save)
+                         act_save=act_save, host_tail=None if act_save is not None else self.host_tail())
 
     def _backward_blob(self, spec, act, packed_bwd, grad_raw, blob):
         """grad_raw [rows,4] -> parameter gradients accumulated into the fp32 blob (see

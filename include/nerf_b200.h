@@ -135,6 +135,23 @@ int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, const float*
 
 size_t nerf_mlp_act_bytes(long M);
 
+/* Inference fast path: the biases, l_alpha and l11 (11.8 KB of the blob's fp32 tail) travel in the
+ * kernel parameters, so the epilogues read them through the constant bank instead of the L1 data
+ * pipe the tensor core reads its operands through.  nerf_model_host_tail copies them to a HOST
+ * buffer of nerf_model_host_tail_bytes() bytes (asynchronously on `stream`; synchronise before
+ * use); nerf_mlp_fwd_host_tail is nerf_mlp_fwd (without act_save) taking that host copy.  Results
+ * are identical to nerf_mlp_fwd. */
+size_t nerf_model_host_tail_bytes(void);
+int nerf_model_host_tail(const void* packed, void* host_tail_out, void* stream);
+int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail, int in_mode, const float* in0,
+                           const float* in1, int in_stride, long M, int S, const float* vterm,
+                           int vterm_div, float* raw_out, void* stream);
+/* Kernel variant behind nerf_mlp_fwd_host_tail: 0 (default) one CTA per SM; 1 CTA pairs (tcgen05
+ * cta_group::2, clusters of 2: each CTA stages half of every weight chunk); 2 one CTA per SM with
+ * a single 16-warp epilogue crew; -1 only queries.  Returns the previous setting.  Same results
+ * (0 and 1 bit-identical, 2 up to fp32 reassociation in the sigma/rgb heads). */
+int nerf_mlp_fwd_use_pairs(int enable);
+
 /* ---------------------------------------------------------------- training: backward of the field
  * Replaces autograd through Model.forward for loss.backward(), main.py:385.  Three stages:
  *   nerf_mlp_bwd_dz     grad_raw [M,4] + saved activations -> dZ of every layer (BF16 tile images,

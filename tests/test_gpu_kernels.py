@@ -255,3 +255,35 @@ def test_field_large_coordinates():
     want = emulate_field(p, x, vterm_reference(p, dirs))
     scale = want.abs().max().item()
     assert (raw - want).abs().max().item() <= 2e-2 * max(scale, 1.)
+
+
+@pytest.mark.parametrize("rows,S", [(1, 1), (129, 1), (513, 3), (128 * 4 * 80 + 77, 64)])
+def test_field_kernel_variants_agree(rows, S):
+    """The three inference variants (bias staged in shared memory; biases in the kernel parameters on
+    one CTA; CTA pairs with tcgen05 cta_group::2) compute the same contraction in the same order."""
+    K = _K()
+    torch.manual_seed(rows)
+    p, _ = O.init_field_params(2, 1.0, 5.0)
+    from cv_nerf_b200.model import Model
+    net = load_model_params(Model(), p).to(DEV)
+    packed = net.packed()
+    ht = K.model_host_tail(packed)
+    n_rays = (rows + S - 1) // S
+    pts = (torch.rand(rows, 3) * 2 - 1).to(DEV)
+    dirs = torch.nn.functional.normalize(torch.randn(n_rays, 3), dim=-1).to(DEV)
+    vt = K.viewdir_term(packed, dirs)
+    base = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S)
+    old = K.use_pairs(0)
+    try:
+        single = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+        K.use_pairs(1)
+        pairs = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+        K.use_pairs(2)
+        crew = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+        torch.cuda.synchronize()
+    finally:
+        K.use_pairs(old)
+    assert torch.equal(single, base), (single - base).abs().max().item()
+    assert torch.equal(pairs, base), (pairs - base).abs().max().item()
+    # four partial sums per row instead of two in the fp32 heads: same values up to fp32 reassociation
+    assert (crew - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())

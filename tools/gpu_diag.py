@@ -76,23 +76,32 @@ def timing():
     rays[:, 3:6] = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV), dim=-1)
     rays[:, 6], rays[:, 7] = 2., 6.
     rays[:, 8:11] = rays[:, 3:6]
+    ht = K.model_host_tail(packed)
     for S in (64, 192):
         z = K.sample_coarse(rays, S)
         vt = K.viewdir_term(packed, rays)
-        for _ in range(3):
-            K.mlp_fwd(packed, K.IN_RAYS, rays, z, n_rays * S, S, vt, S)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        reps = 5
-        for _ in range(reps):
-            K.mlp_fwd(packed, K.IN_RAYS, rays, z, n_rays * S, S, vt, S)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        flops = n_rays * S * 1186816
-        print(f"mlp_fwd {n_rays} rays x {S} samples: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s "
-              f"({n_rays * S / ms / 1e3:.2f} M samples/s)")
+        ref = None
+        for tag, tail, mode in (("smem bias", None, 0), ("host tail, single CTA", ht, 0), ("host tail, CTA pairs", ht, 1),
+                                ("host tail, single CTA, 16-warp crew", ht, 2)):
+            K.use_pairs(mode)
+            for _ in range(3):
+                raw = K.mlp_fwd(packed, K.IN_RAYS, rays, z, n_rays * S, S, vt, S, host_tail=tail)
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = raw
+            else:
+                print(f"  max |{tag} - smem bias| =", (raw - ref).abs().max().item())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            reps = 5
+            for _ in range(reps):
+                K.mlp_fwd(packed, K.IN_RAYS, rays, z, n_rays * S, S, vt, S, host_tail=tail)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            flops = n_rays * S * 1186816
+            print(f"mlp_fwd[{tag}] {n_rays} rays x {S} samples: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s "
+                  f"({n_rays * S / ms / 1e3:.2f} M samples/s)")
 
 
 def pipeline_stats(variants=(1, 3, 4, 5, 6, 7)):

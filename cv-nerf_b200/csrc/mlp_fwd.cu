@@ -969,9 +969,10 @@ int launch_fwd_pair(const FwdParams& P, void* stream) {
 
 int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0, const float* in1,
                 int in_stride, long M, int S, const float* vterm, int vterm_div, float* raw_out) {
-    if (!packed || !in0 || !vterm || !raw_out || M < 0 || vterm_div < 1) return nerf::arg_error("nerf_mlp_fwd");
+    if (M < 0 || vterm_div < 1) return nerf::arg_error("nerf_mlp_fwd");
+    if (M > 0 && (!packed || !in0 || !vterm || !raw_out)) return nerf::arg_error("nerf_mlp_fwd: null pointer");
     if (in_mode == NERF_IN_RAYS) {
-        if (!in1 || S < 1) return nerf::arg_error("nerf_mlp_fwd: NERF_IN_RAYS needs z and S");
+        if ((M > 0 && !in1) || S < 1) return nerf::arg_error("nerf_mlp_fwd: NERF_IN_RAYS needs z and S");
     } else if (in_mode == NERF_IN_EMBEDDED) {
         if (in_stride < 63) return nerf::arg_error("nerf_mlp_fwd: in_stride < 63");
     } else if (in_mode != NERF_IN_POINTS) {

@@ -68,7 +68,7 @@ struct Cfg {
 // epilogues then read biases / l_alpha / l11 through the constant bank with uniform loads
 // (LDCU + FADD2 R, R, UR), which costs nothing on the L1 data pipe the tensor core needs for its
 // operands (a warp-uniform LDS.128 costs 2 wavefronts there, an LDG.128 four).
-struct ConstTail {
+struct alignas(16) ConstTail {
     float bias[9 * kHidden];
     float walpha[kHidden];
     float balpha[4];
@@ -234,9 +234,9 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t 
         for (int q = 0; q < 4; ++q) {
             float2 b0 = make_float2(bc[q].x, bc[q].y), b1 = make_float2(bc[q].z, bc[q].w);
             if (CT) {
-                const float* bl = ct.bias + (L >= 0 ? L : l) * kHidden + c + q * 4;
-                b0 = make_float2(bl[0], bl[1]);
-                b1 = make_float2(bl[2], bl[3]);
+                const float4 bl = *reinterpret_cast<const float4*>(ct.bias + (L >= 0 ? L : l) * kHidden + c + q * 4);
+                b0 = make_float2(bl.x, bl.y);
+                b1 = make_float2(bl.z, bl.w);
             }
             h[2 * q] = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 0]), __uint_as_float(cur[q * 4 + 1])), b0);
             h[2 * q + 1] = __fadd2_rn(make_float2(__uint_as_float(cur[q * 4 + 2]), __uint_as_float(cur[q * 4 + 3])), b1);
@@ -245,7 +245,7 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t 
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float4 w;
-                if (CT) w = make_float4(ct.walpha[c + q * 4], ct.walpha[c + q * 4 + 1], ct.walpha[c + q * 4 + 2], ct.walpha[c + q * 4 + 3]);
+                if (CT) w = *reinterpret_cast<const float4*>(ct.walpha + c + q * 4);
                 else w = __ldg(reinterpret_cast<const float4*>(walpha + c) + q);
                 h[2 * q].x = fmaxf(h[2 * q].x, 0.f); h[2 * q].y = fmaxf(h[2 * q].y, 0.f);
                 h[2 * q + 1].x = fmaxf(h[2 * q + 1].x, 0.f); h[2 * q + 1].y = fmaxf(h[2 * q + 1].y, 0.f);
@@ -330,8 +330,7 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
             for (int k = 0; k < 3; ++k) {
                 float4 w;
                 if (CT) {
-                    const float* wk = ct.w11 + k * kL10Out + c + q * 4;
-                    w = make_float4(wk[0], wk[1], wk[2], wk[3]);
+                    w = *reinterpret_cast<const float4*>(ct.w11 + k * kL10Out + c + q * 4);
                 } else {
                     w = __ldg(reinterpret_cast<const float4*>(w11 + k * kL10Out + c) + q);
                 }
@@ -679,6 +678,236 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------- mixed-orientation kernel
+// Inference variant that runs most layers TRANSPOSED: D^T[feature][sample] = W . H^T, i.e. the
+// weight stage is the A operand (M = 128 output features, two M blocks) and the activation tile the
+// B operand (N = 128 samples).  An epilogue thread then owns ONE output feature and 128 samples, so
+// the bias is a single register (no per-column bias traffic at all: the row-per-thread epilogue
+// needs 128 different biases per thread and layer, delivered through LDS or LDC -- the dominant
+// stall of the other variants), and it writes H^T[feature][sample] rows, which tcgen05 reads back
+// as an MN-major operand.  Layers whose epilogue needs a whole sample per thread (l8: FP32 sigma
+// head over the 256 features; l10: view term + FP32 rgb head) stay in the normal orientation; the
+// stored tile of either orientation feeds either kind of MMA just by flipping the operand-major
+// bits of the instruction descriptor.  The weight blob, the producer and the ring are unchanged.
+//   layer         l1 l2 l3 l4 l5 l6 l7 | l8 | l9 | l10
+//   orientation    T  T  T  T  T  T  T |  N |  T |  N
+__host__ __device__ constexpr bool layer_transposed(int l) { return l != 7 && l != 9; }
+
+// Transposed epilogue: this thread's feature row f, 128 samples: acc + bias -> (ReLU) -> BF16 ->
+// H^T tile ([2 blocks of 64 samples][256 feature rows][128 B], swizzled by row like every tile).
+template <bool RELU>
+__device__ __forceinline__ void epilogue_hidden_t(uint32_t tacc, uint32_t tile_addr, int f, float bias) {
+    const uint32_t row_addr = tile_addr + (uint32_t)f * 128;
+    const uint32_t swz = (uint32_t)(f & 7) << 4;
+    const float2 b2 = make_float2(bias, bias);
+    uint32_t v[2][16];
+    umma::tmem_ld16(tacc, v[0]);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int s0 = it * 16;
+        umma::tmem_wait_ld();
+        if (it + 1 < 8) umma::tmem_ld16(tacc + s0 + 16, v[(it + 1) & 1]);
+        const uint32_t(&cur)[16] = v[it & 1];
+        uint32_t o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float2 h = __fadd2_rn(make_float2(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1])), b2);
+            o[e] = RELU ? pack_relu_bf16x2(h.x, h.y) : pack_bf16x2(h.x, h.y);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int s = s0 + q * 8;
+            const int blk = s >> 6, c16 = (s & 63) >> 3;
+            umma::st_shared_v4(row_addr + blk * 32768 + ((uint32_t)(c16 << 4) ^ swz), o[q * 4 + 0], o[q * 4 + 1],
+                               o[q * 4 + 2], o[q * 4 + 3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tr_kernel(const __grid_constant__ FwdParams P) {
+    constexpr int kRingT = kRing;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = umma::smem_u32(smem);
+    if ((sbase & 1023u) != 0) __trap();
+    const uint32_t bar_w_full = sbase + kOffBar;
+    const uint32_t bar_w_empty = bar_w_full + 8 * kMaxRing;
+    const uint32_t bar_a_ready = bar_w_empty + 8 * kMaxRing;
+    const uint32_t bar_acc_full = bar_a_ready + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kMaxRing + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long n_tiles = (P.M + kTileM - 1) / kTileM;
+    const long n_pairs = (n_tiles + 1) / 2;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kRingT; ++s) {
+            umma::mbar_init(bar_w_full + 8 * s, 1);
+            umma::mbar_init(bar_w_empty + 8 * s, 1);
+        }
+        for (int g = 0; g < 2; ++g) {
+            umma::mbar_init(bar_a_ready + 8 * g, kEpiWarpsPerGroup * 32);
+            umma::mbar_init(bar_acc_full + 8 * g, 1);
+        }
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) {
+        umma::tmem_alloc(umma::smem_u32(tmem_slot), 512);
+        umma::tmem_relinquish();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer (same stream of 32 KB slots as mlp_fwd_kernel) =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                for (int l = 0; l < kNumMmaLayers; ++l) {
+                    const int first = layer_first_stage(l), chunks = layer_chunks(l);
+                    const uint32_t bytes = layer_halves(l) * kStageBytes;
+                    for (int g = 0; g < 2; ++g) {
+                        for (int j = 0; j < chunks; ++j, ++it) {
+                            const uint32_t slot = it % kRingT, ph = (it / kRingT) & 1;
+                            umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                            umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
+                            umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
+                                           P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes,
+                                           bar_w_full + 8 * slot);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t it = 0, n_ready[2] = {0, 0};
+            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                for (int l = 0; l < kNumMmaLayers; ++l) {
+                    const int chunks = layer_chunks(l);
+                    const bool out_t = layer_transposed(l);
+                    const bool in_t = l > 0 && layer_transposed(l - 1);   // layout of the hidden input tile
+                    const int n_cols = layer_halves(l) == 2 ? 256 : 128;  // normal orientation: N
+                    for (int g = 0; g < 2; ++g) {
+                        umma::mbar_wait(bar_a_ready + 8 * g, n_ready[g] & 1);
+                        ++n_ready[g];
+                        umma::tc_fence_after();
+                        const uint32_t d_base = tmem_base + g * 256;
+                        const uint32_t a_tile = sbase + kOffA + g * 65536;
+                        const uint32_t pe_tile = sbase + kOffPE + g * 16384;
+                        for (int j = 0; j < chunks; ++j) {
+                            const bool x_is_pe = l == 0 || (l == 5 && j == 0);
+                            const int jj = l == 5 ? j - 1 : j;            // chunk of the hidden tile
+                            const bool x_mn = !x_is_pe && in_t;
+                            const uint32_t slot = it % kRingT, ph = (it / kRingT) & 1;
+                            ++it;
+                            umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                            umma::tc_fence_after();
+                            const uint32_t w_addr = sbase + kOffW + slot * kSlotBytes;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                // activations of K step kk of this chunk: [sample][feature] image (K-major)
+                                // or [feature][sample] image (MN-major), whichever the previous layer wrote
+                                uint64_t x_desc;
+                                if (x_is_pe) x_desc = umma::smem_desc_sw128(pe_tile + kk * 32);
+                                else if (in_t) x_desc = umma::smem_desc_sw128_mn(a_tile + (uint32_t)(jj * 64 + kk * 16) * 128, 32768);
+                                else x_desc = umma::smem_desc_sw128(a_tile + jj * 16384 + kk * 32);
+                                const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
+                                if (out_t) {
+                                    // D^T[mb] (+)= W[mb] . X^T: weights are A (two 128-row halves), N = 128 samples
+                                    const uint32_t idesc = umma::instr_desc_bf16_ex(128, 128, false, x_mn);
+                                    umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(w_addr + kk * 32), x_desc, idesc, acc);
+                                    umma::mma_bf16_ss(d_base + 128, umma::smem_desc_sw128(w_addr + kStageBytes + kk * 32),
+                                                      x_desc, idesc, acc);
+                                } else {
+                                    const uint32_t idesc = umma::instr_desc_bf16_ex(128, n_cols, x_mn, false);
+                                    umma::mma_bf16_ss(d_base, x_desc, umma::smem_desc_sw128(w_addr + kk * 32), idesc, acc);
+                                }
+                            }
+                            umma::mma_commit(bar_w_empty + 8 * slot);
+                        }
+                        umma::mma_commit(bar_acc_full + 8 * g);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue groups =====================
+        const int ew = warp - 2;
+        const int g = ew >> 3;
+        const int half = (ew >> 2) & 1;          // normal layers: column half; transposed layers: M block
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;        // TMEM lane: sample (normal) or feature within the M block (transposed)
+        const uint32_t pair_bar = 1 + g * 4 + quad;
+        const uint32_t a_tile_addr = sbase + kOffA + g * 65536;
+        const uint32_t a_row_addr = a_tile_addr + row * 128;
+        const uint32_t swz = (uint32_t)(row & 7) << 4;
+        uint8_t* pe_tile = smem + kOffPE + g * 16384;
+        float4* xchg = reinterpret_cast<float4*>(pe_tile + row * 128);
+        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
+        const float* tail = reinterpret_cast<const float*>(P.blob + kWeightBytes);
+        const int feat = half * 128 + row;       // transposed layers: this thread's output feature
+        uint32_t n_full = 0;
+        for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            const long grow_raw = (pair * 2 + g) * kTileM + row;
+            const bool valid = grow_raw < P.M;
+            const long grow = valid ? grow_raw : P.M - 1;
+            if (half == 0) input_stage<0>(P, grow, pe_tile, row);
+            else input_stage<1>(P, grow, pe_tile, row);
+            umma::fence_proxy_async_smem();
+            umma::mbar_arrive(bar_a_ready + 8 * g);
+            float sigma = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < kNumMmaLayers; ++l) {
+                // one coalesced load per thread and layer: the bias of this thread's feature
+                const float bias_f = layer_transposed(l) ? __ldg(tail + kTailBias + l * kHidden + feat) : 0.f;
+                umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
+                ++n_full;
+                umma::tc_fence_after();
+                if (l == 9) {
+                    float rgb[3];
+                    const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
+                    epilogue_rgb<false, false, true>(tacc, half * 64, vt, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
+                    umma::tc_fence_before();
+                    if (half == 1) *xchg = make_float4(rgb[0], rgb[1], rgb[2], sigma);
+                    umma::named_bar_sync(pair_bar, 64);
+                    if (half == 0) {
+                        const float4 o2 = *xchg;
+                        if (valid) {
+                            float4 o;
+                            o.x = rgb[0] + o2.x + P.ct.b11[0];
+                            o.y = rgb[1] + o2.y + P.ct.b11[1];
+                            o.z = rgb[2] + o2.z + P.ct.b11[2];
+                            o.w = sigma + o2.w + P.ct.balpha[0];
+                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
+                        }
+                    }
+                    umma::named_bar_sync(pair_bar, 64);
+                    continue;
+                }
+                if (l == 7) {
+                    epilogue_hidden<1, false, 0, true, 8, 7>(tacc, half * 128, a_row_addr, swz, 0, nullptr, sigma, nullptr, P.ct, 7);
+                } else if (l == 8) {
+                    epilogue_hidden_t<false>(tacc + half * 128, a_tile_addr, feat, bias_f);
+                } else {
+                    epilogue_hidden_t<true>(tacc + half * 128, a_tile_addr, feat, bias_f);
+                }
+                umma::fence_proxy_async_smem();
+                umma::tc_fence_before();
+                umma::mbar_arrive(bar_a_ready + 8 * g);
+            }
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ---------------------------------------------------------------------------- CTA-pair kernel
 // Inference variant on tcgen05 cta_group::2: the two CTAs of a cluster (one TPC) run ONE
 // M=256 x N=256 MMA per K step over their two 128-row sub-tiles, and each CTA stages only ITS
@@ -941,6 +1170,31 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
 // measured on B200 (profiles/r01_fwd_variants_ncu.txt): 0 is the fastest of the three
 int g_use_pairs = 0;
 
+int launch_fwd_tr(const FwdParams& P, void* stream) {
+    static int sm_count = 0;
+    static bool configured = false;
+    if (sm_count == 0) {
+        sm_count = nerf_b200_sm_count();
+        if (sm_count <= 0) {
+            sm_count = 0;
+            nerf::set_last_error("nerf_mlp_fwd setup: no CUDA device");
+            return (int)cudaErrorNoDevice;
+        }
+    }
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) {
+            nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    const long n_pairs = ((P.M + kTileM - 1) / kTileM + 1) / 2;
+    const unsigned grid = (unsigned)(n_pairs < sm_count ? n_pairs : sm_count);
+    mlp_fwd_tr_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    return nerf::check_launch("nerf_mlp_fwd (mixed orientation)");
+}
+
 int launch_fwd_pair(const FwdParams& P, void* stream) {
     static int sm_count = 0;
     static bool configured = false;
@@ -1024,6 +1278,7 @@ extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail,
     if (rc) return rc;
     if (M == 0) return 0;
     memcpy(&P.ct, host_tail, sizeof(ConstTail));
+    if (g_use_pairs == 3) return launch_fwd_tr(P, stream);
     return g_use_pairs == 1 ? launch_fwd_pair(P, stream) : launch_fwd(P, g_use_pairs == 2 ? 10 : 9, stream);
 }
 

@@ -220,6 +220,11 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// general form: per-operand major (false = K-major, true = MN-major)
+__host__ __device__ constexpr uint32_t instr_desc_bf16_ex(int M, int N, bool a_mn, bool b_mn) {
+    return instr_desc_bf16(M, N) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
+}
+
 // both operands MN-major (bits 15 / 16)
 __host__ __device__ constexpr uint32_t instr_desc_bf16_mn(int M, int N) {
     return instr_desc_bf16(M, N) | (1u << 15) | (1u << 16);

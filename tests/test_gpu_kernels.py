@@ -280,9 +280,13 @@ def test_field_kernel_variants_agree(rows, S):
         pairs = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
         K.use_pairs(2)
         crew = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+        K.use_pairs(3)
+        mixed = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
         torch.cuda.synchronize()
     finally:
         K.use_pairs(old)
+    print("mixed-orientation vs base max abs diff", (mixed - base).abs().max().item())
+    assert (mixed - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
     assert torch.equal(single, base), (single - base).abs().max().item()
     assert torch.equal(pairs, base), (pairs - base).abs().max().item()
     # four partial sums per row instead of two in the fp32 heads: same values up to fp32 reassociation

@@ -82,7 +82,7 @@ def timing():
         vt = K.viewdir_term(packed, rays)
         ref = None
         for tag, tail, mode in (("smem bias", None, 0), ("host tail, single CTA", ht, 0), ("host tail, CTA pairs", ht, 1),
-                                ("host tail, single CTA, 16-warp crew", ht, 2)):
+                                ("host tail, single CTA, 16-warp crew", ht, 2), ("host tail, mixed orientation", ht, 3)):
             K.use_pairs(mode)
             for _ in range(3):
                 raw = K.mlp_fwd(packed, K.IN_RAYS, rays, z, n_rays * S, S, vt, S, host_tail=tail)

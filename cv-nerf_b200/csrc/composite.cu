@@ -289,9 +289,9 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 resample_merge_kernel(const float* __restrict__ z_c, const float* __restrict__ w_c,
                       const float* __restrict__ u, long n, int S, int m, float* __restrict__ z_f) {
-    __shared__ float s_cdf[WARPS_PER_BLOCK][MAX_SORT];
+    __shared__ __align__(16) float s_cdf[WARPS_PER_BLOCK][MAX_SORT];
     __shared__ float s_bins[WARPS_PER_BLOCK][MAX_SORT];
-    __shared__ uint32_t s_key[WARPS_PER_BLOCK][MAX_SORT];
+    __shared__ __align__(16) uint32_t s_key[WARPS_PER_BLOCK][MAX_SORT];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long ray = (long)blockIdx.x * WARPS_PER_BLOCK + wib;
     if (ray >= n) return;
@@ -307,7 +307,50 @@ resample_merge_kernel(const float* __restrict__ z_c, const float* __restrict__ w
     for (int k = lane; k < m; k += 32)
         s_key[wib][S + k] = order_key(invert_cdf(s_cdf[wib], s_bins[wib], B, __ldg(u + ray * m + k)));
     __syncwarp();
-    // rank sort (values only): rank = #{j : key_j < key_i or (key_j == key_i and j < i)}
+    // Values-only sort of [coarse depths | new samples] (main.py:251).  The coarse depths are already
+    // ascending in every configuration of the reference (linspace, stratified jitter keeps the
+    // order): then only the m new samples need ranking among themselves (m^2/32 compares per lane,
+    // four keys per shared-memory load) and the two sorted lists are merged by binary search.
+    // Ties: coarse first (strict / non-strict counts), which is a permutation and gives the same
+    // VALUES as any other tie order.  Unsorted coarse depths take the general rank sort.
+    bool sorted = true;
+    for (int i = lane; i + 1 < S; i += 32) sorted &= s_key[wib][i] <= s_key[wib][i + 1];
+    sorted = __all_sync(0xffffffffu, sorted);
+    float* out = z_f + ray * total;
+    auto decode = [](uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); };
+    if (sorted && (m & 3) == 0 && (S & 3) == 0) {
+        uint32_t* samp = s_key[wib] + S;                     // m keys, 16-byte aligned (S % 4 == 0)
+        uint32_t* ranked = reinterpret_cast<uint32_t*>(s_cdf[wib]);   // cdf no longer needed
+        for (int i = lane; i < m; i += 32) {
+            const uint32_t ki = samp[i];
+            int rank = 0;
+            for (int j = 0; j < m; j += 4) {
+                const uint4 q = *reinterpret_cast<const uint4*>(samp + j);
+                rank += (q.x < ki) || (q.x == ki && j + 0 < i);
+                rank += (q.y < ki) || (q.y == ki && j + 1 < i);
+                rank += (q.z < ki) || (q.z == ki && j + 2 < i);
+                rank += (q.w < ki) || (q.w == ki && j + 3 < i);
+            }
+            ranked[rank] = ki;
+        }
+        __syncwarp();
+        for (int i = lane; i < total; i += 32) {
+            if (i < S) {                                     // coarse i: + #samples strictly below
+                const uint32_t k = s_key[wib][i];
+                int lo = 0, hi = m;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (ranked[mid] < k) lo = mid + 1; else hi = mid; }
+                out[i + lo] = decode(k);
+            } else {                                         // sample of rank r: + #coarse at or below
+                const int r = i - S;
+                const uint32_t k = ranked[r];
+                int lo = 0, hi = S;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (s_key[wib][mid] <= k) lo = mid + 1; else hi = mid; }
+                out[r + lo] = decode(k);
+            }
+        }
+        return;
+    }
+    // general rank sort: rank = #{j : key_j < key_i or (key_j == key_i and j < i)}
     for (int i = lane; i < total; i += 32) {
         uint32_t ki = s_key[wib][i];
         int rank = 0;
@@ -315,8 +358,7 @@ resample_merge_kernel(const float* __restrict__ z_c, const float* __restrict__ w
             uint32_t kj = s_key[wib][j];
             rank += (kj < ki) || (kj == ki && j < i);
         }
-        uint32_t b = (ki & 0x80000000u) ? (ki & 0x7fffffffu) : ~ki;
-        z_f[ray * total + rank] = __uint_as_float(b);
+        out[rank] = decode(ki);
     }
 }
 

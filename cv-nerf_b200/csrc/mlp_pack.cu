@@ -133,33 +133,53 @@ __global__ void pack_tail_kernel(ParamPtrs p, float* __restrict__ tail) {
     tail[i] = v;
 }
 
-// block = 128 threads = one row (ray); thread n produces out[row][n]
+// block = 128 threads walks over kViewRows rows (rays) at a time; thread n produces out[row][n]
+// with its 27 weights of W10[n, 256:283] held in registers for the whole block.
+constexpr int kViewRows = 16;
 __global__ void __launch_bounds__(128)
 viewdir_term_kernel(const float* __restrict__ tail, const float* __restrict__ dirs, int dir_stride,
                     int embedded, long count, float* __restrict__ out) {
-    __shared__ float pe[28];
-    const long row = blockIdx.x;
+    __shared__ float pe[kViewRows][28];
     const int t = threadIdx.x;
-    const float* d = dirs + row * dir_stride;
-    if (embedded) {
-        if (t < kViewPeDim) pe[t] = __ldg(d + t);
-    } else {
-        // [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^3), cos(x 2^3)], model.py:15-31
-        if (t < 3) pe[t] = __ldg(d + t);
-        if (t >= 32 && t < 32 + 12) {
-            int k = (t - 32) / 3, a = (t - 32) % 3;
-            float s, c;
-            sincosf(__ldg(d + a) * (float)(1 << k), &s, &c);
-            pe[3 + 6 * k + a] = s;
-            pe[3 + 6 * k + 3 + a] = c;
+    float w[kViewPeDim];
+#pragma unroll
+    for (int c = 0; c < kViewPeDim; ++c) w[c] = __ldg(tail + kTailW10View + t * 28 + c);
+    const float b = __ldg(tail + kTailB10 + t);
+    for (long row0 = (long)blockIdx.x * kViewRows; row0 < count; row0 += (long)gridDim.x * kViewRows) {
+        __syncthreads();
+        if (embedded) {
+            for (int i = t; i < kViewRows * kViewPeDim; i += 128) {
+                const int r = i / kViewPeDim, c = i % kViewPeDim;
+                if (row0 + r < count) pe[r][c] = __ldg(dirs + (row0 + r) * dir_stride + c);
+            }
+        } else {
+            // [x, sin(x 2^0), cos(x 2^0), ..., sin(x 2^3), cos(x 2^3)], model.py:15-31:
+            // 16 rows x (3 raw + 12 sincos) work items over 128 threads
+            for (int i = t; i < kViewRows * 15; i += 128) {
+                const int r = i / 15, q = i % 15;
+                if (row0 + r >= count) continue;
+                const float* d = dirs + (row0 + r) * dir_stride;
+                if (q < 3) {
+                    pe[r][q] = __ldg(d + q);
+                } else {
+                    const int k = (q - 3) / 3, a = (q - 3) % 3;
+                    float sn, cs;
+                    sincosf(__ldg(d + a) * (float)(1 << k), &sn, &cs);
+                    pe[r][3 + 6 * k + a] = sn;
+                    pe[r][3 + 6 * k + 3 + a] = cs;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < kViewRows; ++r) {
+            if (row0 + r >= count) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < kViewPeDim; ++c) acc = fmaf(w[c], pe[r][c], acc);
+            out[(row0 + r) * kL10Out + t] = acc + b;
         }
     }
-    __syncthreads();
-    const float* w = tail + kTailW10View + t * 28;
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < kViewPeDim; ++c) acc = fmaf(__ldg(w + c), pe[c], acc);
-    out[row * kL10Out + t] = acc + __ldg(tail + kTailB10 + t);
 }
 
 // FreqEmbedding.embed as a standalone op: one thread per (row, input component).
@@ -230,7 +250,9 @@ extern "C" int nerf_viewdir_term(const void* packed, const float* dirs, int dir_
     if (count < 0 || (count > 0 && (!packed || !dirs || !out))) return nerf::arg_error("nerf_viewdir_term");
     if (count == 0) return 0;
     const float* tail = (const float*)((const uint8_t*)packed + kWeightBytes);
-    viewdir_term_kernel<<<(unsigned)count, 128, 0, (cudaStream_t)stream>>>(tail, dirs, dir_stride, embedded,
-                                                                          count, out);
+    long blocks = (count + kViewRows - 1) / kViewRows;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    viewdir_term_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(tail, dirs, dir_stride, embedded,
+                                                                           count, out);
     return nerf::check_launch("nerf_viewdir_term");
 }

@@ -319,20 +319,31 @@ def mlp_bwd_dz(packed_bwd, grad_raw, act, rows, dz=None):
     return dz
 
 
-def mlp_bwd_params(act, dz, grad_raw, rows, dirs, vterm_div, embedded, blob):
-    """dW/db of every layer accumulated into the fp32 gradient blob (3 launches)."""
+def mlp_bwd_params(act, dz, grad_raw, rows, dirs, vterm_div, embedded, blob, side_stream=None):
+    """dW/db of every layer accumulated into the fp32 gradient blob (3 launches).
+
+    With ``side_stream`` the two small CUDA-core kernels (l_alpha/l11 heads, l10 view columns) run on
+    that stream next to the HBM-bound tensor-core dW kernel instead of after it (they fit beside its
+    one CTA per SM); the caller's stream waits for them before returning."""
     lib = _lib.load()
     grad_raw = f32c(grad_raw)
-    st = stream_of(grad_raw)
+    main = torch.cuda.current_stream(grad_raw.device)
+    st = main.cuda_stream
+    small = st
+    if side_stream is not None:
+        side_stream.wait_stream(main)
+        small = side_stream.cuda_stream
     check(lib.nerf_mlp_bwd_dw(act.data_ptr(), dz.data_ptr(), rows, ptr(blob), st), "nerf_mlp_bwd_dw")
-    check(lib.nerf_mlp_bwd_heads(act.data_ptr(), ptr(grad_raw), rows, ptr(blob), st), "nerf_mlp_bwd_heads")
+    check(lib.nerf_mlp_bwd_heads(act.data_ptr(), ptr(grad_raw), rows, ptr(blob), small), "nerf_mlp_bwd_heads")
     if not embedded and dirs.shape[-1] == RAY_STRIDE:
         dptr, stride = dirs.data_ptr() + 32, RAY_STRIDE
     else:
         dirs = f32c(dirs)
         dptr, stride = dirs.data_ptr(), dirs.shape[-1]
-    check(lib.nerf_viewdir_term_bwd(dz.data_ptr(), dptr, stride, int(embedded), rows, vterm_div, ptr(blob), st),
+    check(lib.nerf_viewdir_term_bwd(dz.data_ptr(), dptr, stride, int(embedded), rows, vterm_div, ptr(blob), small),
           "nerf_viewdir_term_bwd")
+    if side_stream is not None:
+        main.wait_stream(side_stream)
     return blob
 
 

@@ -94,6 +94,7 @@ class TrainStep:
         self.m = [[torch.zeros_like(p) for p in ps] for ps in self.params]
         self.v = [[torch.zeros_like(p) for p in ps] for ps in self.params]
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.side = torch.cuda.Stream(device=dev)      # small gradient kernels next to the dW kernel
 
     def crop_window(self, precrop_frac=None):
         """Pre-crop window of main.py:354-361 as (row0, col0, rows, cols)."""
@@ -140,7 +141,7 @@ class TrainStep:
                                                         (self.fine, graw_f, self.act_f, rows_f, self.s_f))):
             graw = graw.view(rows, 4)
             K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=self.dz)
-            K.mlp_bwd_params(act, self.dz, graw, rows, rays, s, False, self.blob[idx])
+            K.mlp_bwd_params(act, self.dz, graw, rows, rays, s, False, self.blob[idx], side_stream=self.side)
         return self.loss
 
     @torch.no_grad()

@@ -158,6 +158,23 @@ def test_resample_merge_matches_oracle():
     # m = 0: the fine pass re-evaluates the coarse depths (reference behaviour for n_fine_samples=0)
     got0 = K.resample_merge(z.to(DEV), w.to(DEV), torch.zeros(n, 0, device=DEV)).cpu()
     assert torch.equal(_bits(got0), _bits(z))
+    # the merge fast path assumes ascending coarse depths; descending ones (and duplicates) take the
+    # general rank sort and must give the same multiset, sorted
+    zr = torch.flip(z, dims=[-1]).contiguous()
+    zr[:, 5] = zr[:, 6]
+    got_r = K.resample_merge(zr.to(DEV), w.to(DEV), u.to(DEV)).cpu()
+    assert bool((got_r[:, 1:] >= got_r[:, :-1]).all())
+    for r in (0, n - 1):
+        assert set(_bits(zr[r]).tolist()) <= set(_bits(got_r[r]).tolist())
+    # duplicates inside an ascending list (ties between coarse depths and samples) on the fast path
+    zd = z.clone()
+    zd[:, 10] = zd[:, 11]
+    got_d = K.resample_merge(zd.to(DEV), w.to(DEV), u.to(DEV)).cpu()
+    mids_d = .5 * (zd[:, 1:] + zd[:, :-1])
+    want_d, _ = torch.sort(torch.cat([zd, O.inverse_cdf_sample(mids_d, w[:, 1:-1], u)], -1), -1)
+    assert bool((got_d[:, 1:] >= got_d[:, :-1]).all())
+    dd = (got_d - want_d).abs()
+    assert (dd > 3e-5).float().mean().item() <= 1e-3 and dd.max().item() <= 2e-3
 
 
 def test_freq_encode_matches_golden():

@@ -332,7 +332,11 @@ def bench_train_step(args, dev, world, rank):
             "steps": steps, "warmup": warmup, "tflops_per_gpu": tflops,
             "frac_of_sustained_bf16_peak": tflops / float(peaks["bf16_tflops_sustained"]),
             "gpu_launches_per_step": launches / steps, "loss_last": float(loss.item()),
-            "grad_allreduce_bytes": int(ts.blob.numel() * 4) if world > 1 else 0, "stages_ms": stages}
+            "grad_exchange_bytes_per_rank": int(ts.blob.numel() * 4) if world > 1 else 0,
+            "grad_exchange": ("none" if world == 1 else
+                              "fused into Adam: peer loads over NVLink from symmetric memory" if ts.symm is not None
+                              else "nccl all_reduce"),
+            "stages_ms": stages}
 
 
 def time_train_stages(ts, image, pose):

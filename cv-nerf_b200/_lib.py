@@ -76,6 +76,10 @@ _SIGNATURES = {
     "nerf_adam_step_blob": (ctypes.c_int, [c_float_p] + [ctypes.POINTER(ctypes.c_void_p)] * 3 +
                             [ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_long,
                              ctypes.c_float, ctypes.c_void_p]),
+    "nerf_adam_step_blob_peers": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int] +
+                                  [ctypes.POINTER(ctypes.c_void_p)] * 3 +
+                                  [ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_long,
+                                   ctypes.c_float, ctypes.c_void_p]),
     "nerf_train_rays": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                        c_float_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_float,

@@ -102,6 +102,38 @@ __global__ void __launch_bounds__(256) adam_blob_kernel(const float* __restrict_
     }
 }
 
+// Data-parallel variant fused with the gradient exchange: every rank's gradient blob lives in
+// peer-mapped (symmetric) memory; each rank reads all `world` blobs straight over NVLink (plain
+// ld.global on the mapped peer pointers), sums them in rank order -- the same order on every rank,
+// so the replicas stay bit-identical -- and applies Adam to its own copy of the parameters.  One
+// launch replaces ncclAllReduce + Adam; 4.8 MB x world cross NVLink per rank and step.
+constexpr int kMaxPeers = 16;
+struct PeerBlobs {
+    const float* blob[kMaxPeers];
+    int world;
+};
+
+__global__ void __launch_bounds__(256) adam_blob_peers_kernel(const __grid_constant__ PeerBlobs B,
+                                                              const __grid_constant__ BlobTensors T,
+                                                              const AdamScalars s) {
+    const int t = blockIdx.y;
+    const Slot sl = grad_slot(t);
+    const int n = sl.rows * sl.cols;
+    float* __restrict__ p = T.p[t];
+    float* __restrict__ m = T.m[t];
+    float* __restrict__ v = T.v[t];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = i / sl.cols, c = i % sl.cols;
+        const int off = sl.off + r * sl.pitch + (c >= sl.gap ? c + 1 : c);
+        float g = 0.f;
+        for (int k = 0; k < B.world; ++k) g += __ldcv(B.blob[k] + off);   // peer memory: never cached stale
+        g *= s.grad_scale;
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_update(pi, g, mi, vi, s);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+    }
+}
+
 // ------------------------------------------------------------------ train-loop ray batch
 // Pseudo-random permutation of [0, 4^b) (4-round Feistel on b+b bits); cycle-walking restricts it
 // to [0, domain): distinct inputs give distinct outputs, i.e. sampling WITHOUT replacement
@@ -238,6 +270,29 @@ extern "C" int nerf_adam_step_blob(const float* grad_blob, float* const* params,
     }
     adam_blob_kernel<<<dim3(16, NERF_N_PARAM_TENSORS), 256, 0, (cudaStream_t)stream>>>(grad_blob, T, s);
     return nerf::check_launch("nerf_adam_step_blob");
+}
+
+extern "C" int nerf_adam_step_blob_peers(const float* const* peer_blobs, int world, float* const* params,
+                                         float* const* exp_avg, float* const* exp_avg_sq, float lr, float beta1,
+                                         float beta2, float eps, long step, float grad_scale, void* stream) {
+    if (!peer_blobs || world < 1 || world > kMaxPeers || !params || !exp_avg || !exp_avg_sq)
+        return nerf::arg_error("nerf_adam_step_blob_peers");
+    AdamScalars s;
+    int rc = fill_scalars(s, lr, beta1, beta2, eps, step, grad_scale);
+    if (rc) return rc;
+    PeerBlobs B;
+    B.world = world;
+    for (int k = 0; k < world; ++k) {
+        B.blob[k] = peer_blobs[k];
+        if (!B.blob[k]) return nerf::arg_error("nerf_adam_step_blob_peers: null peer pointer");
+    }
+    BlobTensors T;
+    for (int i = 0; i < NERF_N_PARAM_TENSORS; ++i) {
+        T.p[i] = params[i]; T.m[i] = exp_avg[i]; T.v[i] = exp_avg_sq[i];
+        if (!T.p[i] || !T.m[i] || !T.v[i]) return nerf::arg_error("nerf_adam_step_blob_peers: null tensor");
+    }
+    adam_blob_peers_kernel<<<dim3(16, NERF_N_PARAM_TENSORS), 256, 0, (cudaStream_t)stream>>>(B, T, s);
+    return nerf::check_launch("nerf_adam_step_blob_peers");
 }
 
 extern "C" int nerf_train_rays(int H, int W, float focal, float cw, float ch, const float* pose, const int* pix,

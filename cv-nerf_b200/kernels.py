@@ -395,6 +395,16 @@ def adam_step_blob(blob, params, exp_avg, exp_avg_sq, lr, betas, eps, step, grad
                                   float(grad_scale), stream_of(blob)), "nerf_adam_step_blob")
 
 
+def adam_step_blob_peers(peer_ptrs, params, exp_avg, exp_avg_sq, lr, betas, eps, step, grad_scale, stream):
+    """Adam with the gradient summed over the ranks' peer-mapped blobs (device pointers, rank order)."""
+    lib = _lib.load()
+    assert len(params) == 24
+    arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    check(lib.nerf_adam_step_blob_peers(arr, len(peer_ptrs), _ptr_array(params), _ptr_array(exp_avg),
+                                        _ptr_array(exp_avg_sq), float(lr), float(betas[0]), float(betas[1]),
+                                        float(eps), int(step), float(grad_scale), stream), "nerf_adam_step_blob_peers")
+
+
 def train_rays(height, width, focal, pose, n, *, pix=None, seed=0, crop=None, image=None, ndc=True, near=0.,
                far=1., want_pix=False):
     """One train iteration's batch (main.py:351-374): packed rays [n,11], target [n,3] (when an

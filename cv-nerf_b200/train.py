@@ -14,6 +14,7 @@ Two entry levels:
   re-pack of the BF16 weights, learning-rate decay (main.py:276-277, 392-394).
 """
 import math
+import os
 
 import torch
 
@@ -86,6 +87,21 @@ class TrainStep:
         self.dev = dev
         g = K.grad_blob_floats()
         self.blob = torch.zeros((2, g), dtype=torch.float32, device=dev)          # [coarse, fine]
+        # Data parallel: put the blobs into symmetric (peer-mapped) memory so that the fused
+        # exchange+Adam kernel can read every rank's gradients over NVLink; NCCL all-reduce otherwise.
+        self.symm = None
+        if self.world > 1 and os.environ.get("NERF_B200_PEER_ADAM", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                group = process_group if process_group is not None else torch.distributed.group.WORLD
+                blob = symm_mem.empty((2, g), dtype=torch.float32, device=dev)
+                self.symm = symm_mem.rendezvous(blob, group)
+                blob.zero_()
+                self.blob = blob
+                self.rank = torch.distributed.get_rank(process_group)
+            except Exception as exc:                      # no peer access / unsupported backend
+                self.symm = None
+                self.symm_error = repr(exc)
         rows_c, rows_f = self.n_rays * self.s_c, self.n_rays * self.s_f
         self.act_c = torch.empty(K.act_bytes(rows_c), dtype=torch.uint8, device=dev)
         self.act_f = torch.empty(K.act_bytes(rows_f), dtype=torch.uint8, device=dev)
@@ -147,12 +163,24 @@ class TrainStep:
     @torch.no_grad()
     def apply_gradients(self, allreduce=True):
         """all-reduce (data parallel), Adam from the blobs, weight re-pack, learning-rate decay."""
-        if self.world > 1 and allreduce:
-            torch.distributed.all_reduce(self.blob, group=self.pg)
         self.it += 1
-        for idx in range(2):
-            K.adam_step_blob(self.blob[idx], [p.data for p in self.params[idx]], self.m[idx], self.v[idx], self.lr,
-                             self.betas, self.eps, self.it, grad_scale=1. / self.world)
+        if self.world > 1 and allreduce and self.symm is not None:
+            # fused exchange + Adam over peer memory: barrier (all blobs written), one launch per
+            # network reading every rank's blob, barrier (blobs may be zeroed for the next step)
+            stream = torch.cuda.current_stream(self.dev).cuda_stream
+            g_bytes = self.blob.shape[1] * 4
+            self.symm.barrier(channel=0)
+            for idx in range(2):
+                peers = [int(ptr) + idx * g_bytes for ptr in self.symm.buffer_ptrs]
+                K.adam_step_blob_peers(peers, [p.data for p in self.params[idx]], self.m[idx], self.v[idx], self.lr,
+                                       self.betas, self.eps, self.it, 1. / self.world, stream)
+            self.symm.barrier(channel=1)
+        else:
+            if self.world > 1 and allreduce:
+                torch.distributed.all_reduce(self.blob, group=self.pg)
+            for idx in range(2):
+                K.adam_step_blob(self.blob[idx], [p.data for p in self.params[idx]], self.m[idx], self.v[idx],
+                                 self.lr, self.betas, self.eps, self.it, grad_scale=1. / self.world)
         _model.bump_param_epoch()
         # main.py:392-394: the decayed rate takes effect from the next iteration on
         self.lr = decayed_learning_rate(self.it, self.lr_decay * 1000, self.lr0)

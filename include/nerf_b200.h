@@ -193,6 +193,16 @@ int nerf_adam_step_blob(const float* grad_blob, float* const* params, float* con
                         float* const* exp_avg_sq, float lr, float beta1, float beta2, float eps,
                         long step, float grad_scale, void* stream);
 
+/* Data-parallel Adam fused with the gradient exchange: peer_blobs is a HOST array of `world`
+ * DEVICE pointers, entry k being rank k's gradient blob of this Model mapped into this process
+ * (symmetric / peer memory; entry `rank` is the local blob).  The kernel sums the blobs in rank
+ * order over NVLink and applies nerf_adam_step_blob's update with grad_scale (1/world for a mean).
+ * The caller provides the cross-rank barriers before (all blobs complete) and after (blobs may be
+ * reused) the launch. */
+int nerf_adam_step_blob_peers(const float* const* peer_blobs, int world, float* const* params,
+                              float* const* exp_avg, float* const* exp_avg_sq, float lr, float beta1,
+                              float beta2, float eps, long step, float grad_scale, void* stream);
+
 /* One train iteration's batch, main.py:351-374: n rays (packed [n,11] like nerf_pack_rays) and
  * their target pixels [n,3] from image [H,W,3].  pix != NULL: the caller's linear pixel indices
  * (i*W + j).  pix == NULL: n DISTINCT pixels of the crop window drawn by a keyed permutation

@@ -259,7 +259,13 @@ def run_ours(args):
                 "d2h_bytes_per_step": n_rays * 12, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": "mlp_fwd_kernel",
+                     "frac": achieved / peak,
+                     # DRAM bytes per launch: ncu --set full measured 135.3 MB read + 255.7 MB written for a
+                     # 19.2 M-row launch of this kernel (profiles/r01_fwd_variants_ncu.txt) = 20.4 B/row, against
+                     # ~23 B/row algorithmic (depth in, raw out, rays/view term per ray): no re-reads
+                     "traffic": NCU_DRAM_BYTES_PER_ROW * kern_rows / max(len(kern), 1),
+                     "traffic_unit": "bytes per launch (ncu dram__bytes_read+write per row x rows per launch)",
+                     "kernel": "mlp_fwd_kernel",
                      "peak_kind": f"{peak_kind} bf16_tflops_sustained",
                      "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
                      "kernel_share_of_step": kern_ms / total_ms,
@@ -275,6 +281,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+NCU_DRAM_BYTES_PER_ROW = (135.264e6 + 255.746e6) / 19.2e6     # profiles/r01_fwd_variants_ncu.txt
 TRAIN_FLOP_PER_RAY = (N_COARSE + N_COARSE + N_FINE) * 2 * (593408 + 593408 + 557696)
 
 

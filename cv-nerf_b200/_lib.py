@@ -59,6 +59,9 @@ _SIGNATURES = {
     "nerf_mlp_fwd_use_pairs": (ctypes.c_int, [ctypes.c_int]),
     "nerf_packed_model_bwd_bytes": (ctypes.c_size_t, []),
     "nerf_pack_model_bwd": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p]),
+    "nerf_pack_models_train": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                              ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                              ctypes.c_void_p]),
     "nerf_mlp_dz_bytes": (ctypes.c_size_t, [ctypes.c_long]),
     "nerf_mlp_bwd_dz": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
                                        ctypes.c_void_p]),

@@ -78,18 +78,17 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 
 // Head stage: dZ10 for this thread's 64 columns [half*64, half*64+64) of its row -> A tile block
 // `half` (K-major operand of the first contraction).
-__device__ __forceinline__ void head_stage(float4 g, const uint8_t* h10_row, uint32_t row_addr, uint32_t swz,
+// expand the two mask bits of BF16 pair j (iteration parity b) to all-ones / all-zeros halves
+__device__ __forceinline__ uint32_t pair_keep_mask(uint32_t m, int b, int j) {
+    return ((m >> (2 * j + b)) & 0x00010001u) * 0xffffu;
+}
+
+__device__ __forceinline__ void head_stage(float4 g, uint2 mask, uint32_t row_addr, uint32_t swz,
                                            int half, uint32_t w11_addr) {
-    uint4 hv[8];
-    if (h10_row) {
-#pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) hv[c16] = ldg_nc_v4(h10_row + (((uint32_t)c16 << 4) ^ swz));
-    } else {
-#pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) hv[c16] = make_uint4(0, 0, 0, 0);
-    }
 #pragma unroll
     for (int c16 = 0; c16 < 8; ++c16) {
+        const uint32_t mword = (c16 >> 2) ? mask.y : mask.x;      // 16-column iterations 2p, 2p+1 -> word p
+        const int b = (c16 >> 1) & 1, j0 = (c16 & 1) * 4;
         const int c = half * 64 + c16 * 8;
         float dh[8];
 #pragma unroll
@@ -102,10 +101,10 @@ __device__ __forceinline__ void head_stage(float4 g, const uint8_t* h10_row, uin
             dh[q * 4 + 2] = fmaf(g.z, w2.z, fmaf(g.y, w1.z, g.x * w0.z));
             dh[q * 4 + 3] = fmaf(g.z, w2.w, fmaf(g.y, w1.w, g.x * w0.w));
         }
-        const uint32_t o0 = relu_mask_mul(pack_bf16x2(dh[0], dh[1]), hv[c16].x);
-        const uint32_t o1 = relu_mask_mul(pack_bf16x2(dh[2], dh[3]), hv[c16].y);
-        const uint32_t o2 = relu_mask_mul(pack_bf16x2(dh[4], dh[5]), hv[c16].z);
-        const uint32_t o3 = relu_mask_mul(pack_bf16x2(dh[6], dh[7]), hv[c16].w);
+        const uint32_t o0 = pack_bf16x2(dh[0], dh[1]) & pair_keep_mask(mword, b, j0 + 0);
+        const uint32_t o1 = pack_bf16x2(dh[2], dh[3]) & pair_keep_mask(mword, b, j0 + 1);
+        const uint32_t o2 = pack_bf16x2(dh[4], dh[5]) & pair_keep_mask(mword, b, j0 + 2);
+        const uint32_t o3 = pack_bf16x2(dh[6], dh[7]) & pair_keep_mask(mword, b, j0 + 3);
         umma::st_shared_v4(row_addr + half * 16384 + (((uint32_t)c16 << 4) ^ swz), o0, o1, o2, o3);
     }
 }
@@ -113,36 +112,14 @@ __device__ __forceinline__ void head_stage(float4 g, const uint8_t* h10_row, uin
 // One layer's epilogue for this thread's 128 columns [c0, c0+128): accumulator (+ grad_sigma *
 // w_alpha when ADD_SIGMA) -> BF16 -> * [h > 0] (when MASK) -> A tile in place.
 // h_row: this row's line in block 0 of the saved activation (global), or NULL for zero rows.
-constexpr int kAhead = 2;                          // activation sectors in flight per thread
-
-// load the 32-byte sector holding logical chunks c16, c16+1 (c16 even) of this row; the swizzle
-// swaps them inside the sector for odd rows -- undone when the words are used
-__device__ __forceinline__ void load_mask_sector(const uint8_t* h_row, int c0, int it, uint32_t swz, uint4 (&dst)[2]) {
-    const int c = c0 + it * 16;
-    const int blk = c >> 6, c16 = (c & 63) >> 3;
-    if (h_row) {
-        ldg_nc_v8(h_row + blk * 16384 + ((((uint32_t)c16 << 4) ^ swz) & ~16u), dst[0], dst[1]);
-    } else {
-        dst[0] = dst[1] = make_uint4(0, 0, 0, 0);
-    }
-}
-
-// issued BEFORE waiting for the accumulator: the first mask loads overlap the tensor-core work
-__device__ __forceinline__ void mask_preload(const uint8_t* h_row, int c0, uint32_t swz, uint4 (&hm)[kAhead + 1][2]) {
-#pragma unroll
-    for (int a = 0; a < kAhead; ++a) load_mask_sector(h_row, c0, a, swz, hm[a]);
-}
-
 template <bool MASK, bool ADD_SIGMA>
 __device__ __forceinline__ void epilogue_dz(uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
-                                            const uint8_t* h_row, float dsig, uint32_t walpha_addr,
-                                            uint4 (&hm)[kAhead + 1][2]) {
+                                            uint4 mask, float dsig, uint32_t walpha_addr) {
     uint32_t v[2][16];
     umma::tmem_ld16(tacc + c0, v[0]);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int c = c0 + it * 16;
-        if (MASK && it + kAhead < 8) load_mask_sector(h_row, c0, it + kAhead, swz, hm[(it + kAhead) % (kAhead + 1)]);
         umma::tmem_wait_ld();
         if (it + 1 < 8) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
         const uint32_t(&cur)[16] = v[it & 1];
@@ -158,20 +135,14 @@ __device__ __forceinline__ void epilogue_dz(uint32_t tacc, int c0, uint32_t row_
                 d[2 * q + 1] = __ffma2_rn(s2, make_float2(w.z, w.w), d[2 * q + 1]);
             }
         }
-        uint4 hc[2];
-        {
-            const uint4(&hs)[2] = hm[it % (kAhead + 1)];
-            const bool odd = (swz & 16u) != 0;
-            hc[0] = odd ? hs[1] : hs[0];
-            hc[1] = odd ? hs[0] : hs[1];
-        }
+        const uint32_t mword = (it >> 1) == 0 ? mask.x : (it >> 1) == 1 ? mask.y : (it >> 1) == 2 ? mask.z : mask.w;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             uint32_t o0 = pack_bf16x2(d[q * 4 + 0].x, d[q * 4 + 0].y), o1 = pack_bf16x2(d[q * 4 + 1].x, d[q * 4 + 1].y);
             uint32_t o2 = pack_bf16x2(d[q * 4 + 2].x, d[q * 4 + 2].y), o3 = pack_bf16x2(d[q * 4 + 3].x, d[q * 4 + 3].y);
             if (MASK) {
-                o0 = relu_mask_mul(o0, hc[q].x); o1 = relu_mask_mul(o1, hc[q].y);
-                o2 = relu_mask_mul(o2, hc[q].z); o3 = relu_mask_mul(o3, hc[q].w);
+                o0 &= pair_keep_mask(mword, it & 1, q * 4 + 0); o1 &= pair_keep_mask(mword, it & 1, q * 4 + 1);
+                o2 &= pair_keep_mask(mword, it & 1, q * 4 + 2); o3 &= pair_keep_mask(mword, it & 1, q * 4 + 3);
             }
             const int cc = c + q * 8;
             const int blk = cc >> 6, c16 = (cc & 63) >> 3;
@@ -224,27 +195,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams 
         // ===================== producer: transposed weight slots, L2 -> smem =====================
         if (lane == 0) {
             uint32_t it = 0;
-            // The epilogues read the saved activations (ReLU masks) straight from global memory;
-            // pull every tile into L2 one layer ahead with bulk prefetches so those loads see L2
-            // latency and DRAM is read in whole lines.
-            auto prefetch_h10 = [&](long pair) {
-                for (int g = 0; g < 2; ++g) {
-                    const long tile = pair * 2 + g;
-                    if (tile < n_tiles) umma::bulk_prefetch_l2(P.act + (size_t)tile * kActTileBytes + kActH10, 32768);
-                }
-            };
-            if ((long)blockIdx.x < n_pairs) prefetch_h10(blockIdx.x);
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 for (int j = 0; j < kBwdLayers; ++j) {
                     const int first = bwd_first_stage(j), chunks = bwd_chunks(j);
                     for (int g = 0; g < 2; ++g) {
-                        const long tile = pair * 2 + g;
-                        if (j + 1 < kBwdLayers) {
-                            if (tile < n_tiles)
-                                umma::bulk_prefetch_l2(P.act + (size_t)tile * kActTileBytes + act_hidden(8 - j), 65536);
-                        } else if (g == 0 && pair + gridDim.x < n_pairs) {
-                            prefetch_h10(pair + gridDim.x);
-                        }
                         for (int c = 0; c < chunks; ++c, ++it) {
                             const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
                             umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
@@ -317,8 +271,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams 
             // rows past M carry a zero gradient, so their (duplicated) activations never reach dW
             const float4 graw = valid ? __ldg(reinterpret_cast<const float4*>(P.grad_raw) + grow)
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-            head_stage(graw, tile_ok ? act_tile + kActH10 + half * 16384 + row * 128 : nullptr, a_row_addr, swz, half,
-                       w11_addr);
+            // ReLU masks are bits written by the forward epilogue thread that owned the same (row, half)
+            const uint2 m10 = tile_ok ? __ldg(reinterpret_cast<const uint2*>(act_tile + act_mask_slot(8, row, half)))
+                                      : make_uint2(0, 0);
+            head_stage(graw, m10, a_row_addr, swz, half, w11_addr);
             umma::fence_proxy_async_smem();
             umma::mbar_arrive(bar_a_ready + 8 * g);
             umma::named_bar_sync(group_bar, kGroupThreads);
@@ -333,19 +289,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams 
 #pragma unroll 1
             for (int j = 0; j < kBwdLayers; ++j) {
                 const int i = 9 - j;               // this epilogue produces dZ_i
-                const uint8_t* h_row = tile_ok ? act_tile + act_hidden(i) + row * 128 : nullptr;
                 const int c0 = half * 128;
-                uint4 hm[kAhead + 1][2];
-                if (j > 0) mask_preload(h_row, c0, swz, hm);
+                // one 16-byte load per thread and layer, issued before the accumulator wait
+                uint4 mk = make_uint4(0, 0, 0, 0);
+                if (j > 0 && tile_ok) mk = __ldg(reinterpret_cast<const uint4*>(act_tile + act_mask_slot(i - 1, row, half)));
                 umma::mbar_wait(bar_acc_full + 8 * g, n_full & 1);
                 ++n_full;
                 umma::tc_fence_after();
                 if (j == 0) {
-                    epilogue_dz<false, false>(tacc, c0, a_row_addr, swz, nullptr, 0.f, walpha_addr, hm);
+                    epilogue_dz<false, false>(tacc, c0, a_row_addr, swz, mk, 0.f, walpha_addr);
                 } else if (j == 1) {
-                    epilogue_dz<true, true>(tacc, c0, a_row_addr, swz, h_row, graw.w, walpha_addr, hm);
+                    epilogue_dz<true, true>(tacc, c0, a_row_addr, swz, mk, graw.w, walpha_addr);
                 } else {
-                    epilogue_dz<true, false>(tacc, c0, a_row_addr, swz, h_row, 0.f, walpha_addr, hm);
+                    epilogue_dz<true, false>(tacc, c0, a_row_addr, swz, mk, 0.f, walpha_addr);
                 }
                 umma::fence_proxy_async_smem();
                 umma::tc_fence_before();

@@ -24,7 +24,22 @@ __host__ __device__ constexpr size_t act_hidden(int i) {      // i = 1..8: h_i (
     return kBlockBytes + (size_t)(i - 1) * 4 * kBlockBytes;
 }
 constexpr size_t kActH10 = kBlockBytes + 9 * 4 * kBlockBytes; // h10 (post-ReLU), 2 blocks
-constexpr size_t kActTileBytes = kActH10 + 2 * kBlockBytes;   // 638976
+// ReLU masks of h1..h8 and h10 as bits, for the dZ chain (which then never re-reads the BF16
+// activations): [9 layers][128 rows][2 column halves] x 16 bytes.  The thread that owns (row, half)
+// in the forward epilogue writes one uint4 per layer: word p covers its 16-column iterations 2p and
+// 2p+1; the BF16 pair j (columns 2j, 2j+1 of iteration with parity b) puts its low element at bit
+// 2j+b and its high element at bit 16+2j+b (relu_mask_bits below).  h10 (64 columns per thread)
+// uses words 0 and 1 of its slot.
+constexpr size_t kActMasks = kActH10 + 2 * kBlockBytes;
+constexpr int kMaskLayers = 9;                                // index 0..7: h1..h8, 8: h10
+constexpr size_t kActMaskBytes = (size_t)kMaskLayers * kTileRows * 2 * 16;   // 36864
+constexpr size_t kActTileBytes = kActMasks + kActMaskBytes;   // 675840
+__host__ __device__ constexpr size_t act_mask_slot(int layer, int row, int half) {
+    return kActMasks + ((size_t)(layer * kTileRows + row) * 2 + half) * 16;
+}
+__host__ __device__ constexpr uint32_t relu_mask_bits(int parity, int j) {
+    return (1u << (2 * j + parity)) | (1u << (16 + 2 * j + parity));
+}
 
 // ---- dZ record of one tile (written by nerf_mlp_bwd_dz) ---------------------------------------
 // dZ_i = dL/d(pre-activation of layer i): i = 1..8 trunk, 9 = l9 (no activation), 10 = l10.

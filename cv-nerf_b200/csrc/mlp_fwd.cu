@@ -211,11 +211,20 @@ __device__ __forceinline__ void lds_bias16(uint32_t addr, float4 (&dst)[4]) {
 // CT: bias and l_alpha come from the kernel parameters (ct, layer l) instead of shared / global memory.
 // L >= 0: the layer index is a compile-time constant, so with CT every bias is an immediate
 // constant-bank operand of its FADD2 (no load instruction at all); L = -1: runtime index l.
-template <int MODE, bool PROBE, int EXP, bool CT, int NIT = 8, int L = -1>
+// [x > 0] of a post-ReLU BF16 pair as an all-ones/all-zeros mask per 16-bit half (HSET2.BM)
+__device__ __forceinline__ uint32_t bf16x2_positive_mask(uint32_t w) {
+    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+    return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w), zero);
+}
+
+// MASKS (training): additionally returns the ReLU mask bits of this thread's columns in mw[0..3]
+// (layout in mlp_bwd_layout.h).
+template <int MODE, bool PROBE, int EXP, bool CT, int NIT = 8, int L = -1, bool MASKS = false>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
                                                 uint32_t bias_addr,
                                                 const float* __restrict__ walpha, float& sigma,
-                                                float* probe_row, const ConstTail& ct, int l) {
+                                                float* probe_row, const ConstTail& ct, int l,
+                                                uint32_t* mw = nullptr) {
     uint32_t v[2][16] = {};
     float4 b[2][4] = {};
     float2 sig2 = make_float2(0.f, 0.f);
@@ -270,6 +279,14 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t 
                 o0 = pack_bf16x2(h[q * 4 + 0].x, h[q * 4 + 0].y); o1 = pack_bf16x2(h[q * 4 + 1].x, h[q * 4 + 1].y);
                 o2 = pack_bf16x2(h[q * 4 + 2].x, h[q * 4 + 2].y); o3 = pack_bf16x2(h[q * 4 + 3].x, h[q * 4 + 3].y);
             }
+            if (MASKS && MODE != 2) {
+                uint32_t& m = mw[it >> 1];
+                if ((it & 1) == 0 && q == 0) m = 0;
+                m |= bf16x2_positive_mask(o0) & relu_mask_bits(it & 1, q * 4 + 0);
+                m |= bf16x2_positive_mask(o1) & relu_mask_bits(it & 1, q * 4 + 1);
+                m |= bf16x2_positive_mask(o2) & relu_mask_bits(it & 1, q * 4 + 2);
+                m |= bf16x2_positive_mask(o3) & relu_mask_bits(it & 1, q * 4 + 3);
+            }
             const int cc = c + q * 8;
             const int blk = cc >> 6, c16 = (cc & 63) >> 3;
             if (!(EXP & 1) || o0 == 0x12345678u)
@@ -299,7 +316,8 @@ __device__ __forceinline__ void epilogue_hidden_ct(int l, uint32_t tacc, int c0,
 template <bool PROBE, bool SAVE, bool CT, int NIT = 4>
 __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float* __restrict__ vt,
                                              const float* __restrict__ w11, float (&rgb)[3],
-                                             float* probe_row, uint32_t row_addr, uint32_t swz, const ConstTail& ct) {
+                                             float* probe_row, uint32_t row_addr, uint32_t swz, const ConstTail& ct,
+                                             uint32_t* mw = nullptr) {
     uint32_t v[2][16];
     float4 t[2][4];
     umma::tmem_ld16(tacc + c0, v[0]);
@@ -343,6 +361,10 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
             }
         }
         if (SAVE) {
+            uint32_t& m = mw[it >> 1];
+            if ((it & 1) == 0) m = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m |= bf16x2_positive_mask(pk[j]) & relu_mask_bits(it & 1, j);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int cc = c + q * 8;
@@ -573,10 +595,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
             umma::fence_proxy_async_smem();
             umma::mbar_arrive(bar_a_ready + 8 * g);
             uint8_t* act_tile = nullptr;
+            uint8_t* mask_tile = nullptr;          // every thread stores its own mask words
             if (SAVE) {
                 const long tile = pair * 2 + g;
                 const bool saver = gtid == 0 && tile < n_tiles;
                 act_tile = saver ? P.act_save + (size_t)tile * kActTileBytes : nullptr;
+                mask_tile = tile < n_tiles ? P.act_save + (size_t)tile * kActTileBytes : nullptr;
                 // the previous tile's h10 copy must have left the A tile before l1's epilogue
                 // rewrites it; every thread passes the barrier after thread 0 has seen that
                 if (gtid == 0) umma::bulk_wait_read0();
@@ -588,6 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
             }
             float sigma = 0.f;
             float* probe_row = nullptr;
+            uint32_t mw[4] = {0, 0, 0, 0};
 #pragma unroll 1
             for (int l = 0; l < kNumMmaLayers; ++l) {
                 long long t0 = PROBE ? clock64() : 0;
@@ -601,12 +626,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                     if (CT && !PROBE) {
                         epilogue_hidden_ct<8>(l, tacc, c0, a_row_addr, swz, sigma, P.ct);
                     } else if (l == 7) {
-                        epilogue_hidden<1, PROBE, CFG::exp, CT>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row, P.ct, l);
+                        epilogue_hidden<1, PROBE, CFG::exp, CT, 8, -1, SAVE>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row, P.ct, l, mw);
                     } else if (l == 8) {
                         epilogue_hidden<2, PROBE, CFG::exp, CT>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row, P.ct, l);
                     } else {
-                        epilogue_hidden<0, PROBE, CFG::exp, CT>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row, P.ct, l);
+                        epilogue_hidden<0, PROBE, CFG::exp, CT, 8, -1, SAVE>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row, P.ct, l, mw);
                     }
+                    if (SAVE && l != 8 && mask_tile)
+                        *reinterpret_cast<uint4*>(mask_tile + act_mask_slot(l, row, half)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
                     umma::fence_proxy_async_smem();
                     umma::tc_fence_before();
                     umma::mbar_arrive(bar_a_ready + 8 * g);
@@ -629,8 +656,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                 } else {
                     float rgb[3];
                     const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                    epilogue_rgb<PROBE, SAVE, CT>(tacc, half * 64, vt, tail + kTailW11, rgb, probe_row, a_row_addr, swz, P.ct);
+                    epilogue_rgb<PROBE, SAVE, CT>(tacc, half * 64, vt, tail + kTailW11, rgb, probe_row, a_row_addr, swz, P.ct, mw);
                     umma::tc_fence_before();
+                    if (SAVE && mask_tile)
+                        *reinterpret_cast<uint2*>(mask_tile + act_mask_slot(8, row, half)) = make_uint2(mw[0], mw[1]);
                     if (SAVE) {
                         umma::fence_proxy_async_smem();
                         umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);

@@ -49,8 +49,7 @@ __device__ __forceinline__ int in_features(int l) {
 }
 
 // one thread = one 16-byte chunk (8 consecutive k) of one stage row
-__global__ void pack_weights_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_weights_item(const ParamPtrs& p, uint8_t* __restrict__ blob, int gid) {
     if (gid >= kNumStages * kStageRows * 8) return;
     int stage = gid / (kStageRows * 8);
     int r = (gid / 8) % kStageRows;
@@ -77,8 +76,11 @@ __global__ void pack_weights_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
 
 // Transposed weights for the dZ chain (mlp_bwd_layout.h): stage row = input feature n, stage
 // column = output feature k, value W[k][col_off + n].
-__global__ void pack_weights_bwd_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void pack_weights_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
+    pack_weights_item(p, blob, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__device__ __forceinline__ void pack_weights_bwd_item(const ParamPtrs& p, uint8_t* __restrict__ blob, int gid) {
     if (gid >= kBwdStages * kStageRows * 8) return;
     const int stage = gid / (kStageRows * 8);
     const int r = (gid / 8) % kStageRows;
@@ -102,14 +104,20 @@ __global__ void pack_weights_bwd_kernel(ParamPtrs p, uint8_t* __restrict__ blob)
         make_uint4(q[0], q[1], q[2], q[3]);
 }
 
-__global__ void pack_tail_bwd_kernel(ParamPtrs p, float* __restrict__ tail) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void pack_weights_bwd_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
+    pack_weights_bwd_item(p, blob, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__device__ __forceinline__ void pack_tail_bwd_item(const ParamPtrs& p, float* __restrict__ tail, int i) {
     if (i >= kBwdTailFloats) return;
     tail[i] = i < kBwdTailW11 ? p.w[9][i] : p.w[11][i - kBwdTailW11];
 }
 
-__global__ void pack_tail_kernel(ParamPtrs p, float* __restrict__ tail) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void pack_tail_bwd_kernel(ParamPtrs p, float* __restrict__ tail) {
+    pack_tail_bwd_item(p, tail, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+__device__ __forceinline__ void pack_tail_item(const ParamPtrs& p, float* __restrict__ tail, int i) {
     if (i >= kTailFloats) return;
     float v = 0.f;
     if (i < kTailWAlpha) {                       // biases b1..b9
@@ -131,6 +139,40 @@ __global__ void pack_tail_kernel(ParamPtrs p, float* __restrict__ tail) {
         v = p.b[10][i - kTailB10];
     }
     tail[i] = v;
+}
+
+__global__ void pack_tail_kernel(ParamPtrs p, float* __restrict__ tail) {
+    pack_tail_item(p, tail, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// Everything the training step re-packs after an optimizer step, for up to two Models, in ONE
+// launch: forward stages + tail and transposed stages + tail of each.
+constexpr int kPackFwdBlocks = (kNumStages * kStageRows * 8 + 255) / 256;
+constexpr int kPackBwdBlocks = (kBwdStages * kStageRows * 8 + 255) / 256;
+constexpr int kPackTailBlocks = (kTailFloats + 255) / 256;
+constexpr int kPackTailBwdBlocks = (kBwdTailFloats + 255) / 256;
+constexpr int kPackBlocksPerModel = kPackFwdBlocks + kPackBwdBlocks + kPackTailBlocks + kPackTailBwdBlocks;
+
+struct PackAll {
+    ParamPtrs p[2];
+    uint8_t* fwd[2];
+    uint8_t* bwd[2];
+};
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ PackAll A) {
+    const int model = blockIdx.x / kPackBlocksPerModel;
+    int b = blockIdx.x % kPackBlocksPerModel;
+    const ParamPtrs& p = A.p[model];
+    if (b < kPackFwdBlocks) { pack_weights_item(p, A.fwd[model], b * 256 + threadIdx.x); return; }
+    b -= kPackFwdBlocks;
+    if (b < kPackBwdBlocks) { pack_weights_bwd_item(p, A.bwd[model], b * 256 + threadIdx.x); return; }
+    b -= kPackBwdBlocks;
+    if (b < kPackTailBlocks) {
+        pack_tail_item(p, reinterpret_cast<float*>(A.fwd[model] + kWeightBytes), b * 256 + threadIdx.x);
+        return;
+    }
+    b -= kPackTailBlocks;
+    pack_tail_bwd_item(p, reinterpret_cast<float*>(A.bwd[model] + kBwdWeightBytes), b * 256 + threadIdx.x);
 }
 
 // block = 128 threads walks over kViewRows rows (rays) at a time; thread n produces out[row][n]
@@ -243,6 +285,25 @@ extern "C" int nerf_pack_model_bwd(const float* const* host_params, void* packed
     pack_tail_bwd_kernel<<<nerf::blocks_for(kBwdTailFloats, 256), 256, 0, st>>>(
         p, (float*)((uint8_t*)packed_out + kBwdWeightBytes));
     return nerf::check_launch("nerf_pack_model_bwd");
+}
+
+extern "C" int nerf_pack_models_train(int n_models, const float* const* host_params, void* const* packed_out,
+                                      void* const* packed_bwd_out, void* stream) {
+    if (n_models < 1 || n_models > 2 || !host_params || !packed_out || !packed_bwd_out)
+        return nerf::arg_error("nerf_pack_models_train");
+    PackAll A;
+    for (int m = 0; m < n_models; ++m) {
+        for (int i = 0; i < 12; ++i) {
+            A.p[m].w[i] = host_params[m * 24 + 2 * i];
+            A.p[m].b[i] = host_params[m * 24 + 2 * i + 1];
+            if (!A.p[m].w[i] || !A.p[m].b[i]) return nerf::arg_error("nerf_pack_models_train: null parameter");
+        }
+        A.fwd[m] = (uint8_t*)packed_out[m];
+        A.bwd[m] = (uint8_t*)packed_bwd_out[m];
+        if (!A.fwd[m] || !A.bwd[m]) return nerf::arg_error("nerf_pack_models_train: null output");
+    }
+    pack_all_kernel<<<n_models * kPackBlocksPerModel, 256, 0, (cudaStream_t)stream>>>(A);
+    return nerf::check_launch("nerf_pack_models_train");
 }
 
 extern "C" int nerf_viewdir_term(const void* packed, const float* dirs, int dir_stride, int embedded,

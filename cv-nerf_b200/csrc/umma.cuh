@@ -39,16 +39,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs
+// out, and wakes it as soon as the barrier flips: with a generous hint a waiting warp issues a
+// handful of instructions instead of spinning through BRA/TRYWAIT pairs next to the working warps
+// of its scheduler (half of all issued instructions of the field kernel were such spins).
+#ifndef NERF_MBAR_SUSPEND_NS
+#define NERF_MBAR_SUSPEND_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, P;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"((uint32_t)NERF_MBAR_SUSPEND_NS)
         : "memory");
     return ok != 0;
 }

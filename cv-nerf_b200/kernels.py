@@ -309,6 +309,17 @@ def pack_model_bwd(params, out=None):
     return out
 
 
+def pack_models_train(param_lists, packed, packed_bwd):
+    """Forward + transposed blobs of one or two Models in a single launch (in place)."""
+    lib = _lib.load()
+    flat = [f32c(p.detach()) for ps in param_lists for p in ps]
+    assert len(flat) == 24 * len(param_lists) and len(packed) == len(packed_bwd) == len(param_lists)
+    arr = (ctypes.c_void_p * len(flat))(*[ptr(p) for p in flat])
+    out = (ctypes.c_void_p * len(packed))(*[t.data_ptr() for t in packed])
+    outb = (ctypes.c_void_p * len(packed_bwd))(*[t.data_ptr() for t in packed_bwd])
+    check(lib.nerf_pack_models_train(len(param_lists), arr, out, outb, stream_of(flat[0])), "nerf_pack_models_train")
+
+
 def mlp_bwd_dz(packed_bwd, grad_raw, act, rows, dz=None):
     lib = _lib.load()
     grad_raw = f32c(grad_raw)

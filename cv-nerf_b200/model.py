@@ -12,6 +12,11 @@ import torch.nn as nn
 from . import kernels as K
 from ._lib import NerfB200Error, f32c
 
+def _lib_bwd_bytes():
+    from . import _lib
+    return _lib.load().nerf_packed_model_bwd_bytes()
+
+
 STD_CHUNK_SIZE = 65536
 _PARAM_EPOCH = 0
 
@@ -118,6 +123,23 @@ class Model(nn.Module):
                                         and self._packed.device == params[0].device else None)
             self._packed_key = key
         return self._packed
+
+    def _cache_key(self):
+        return (_PARAM_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self.ordered_params())
+
+    def packed_buffers(self):
+        """(packed, packed_bwd) buffers, allocated if needed, WITHOUT re-packing (for
+        kernels.pack_models_train, which fills several Models' blobs in one launch)."""
+        dev = self.l1.weight.device
+        if self._packed is None or self._packed.device != dev:
+            self._packed = torch.empty(K.packed_model_bytes(), dtype=torch.uint8, device=dev)
+        if self._packed_bwd is None or self._packed_bwd.device != dev:
+            self._packed_bwd = torch.empty(int(_lib_bwd_bytes()), dtype=torch.uint8, device=dev)
+        return self._packed, self._packed_bwd
+
+    def mark_packed(self):
+        """The blobs returned by packed_buffers() now hold the current parameters."""
+        self._packed_key = self._packed_bwd_key = self._cache_key()
 
     def host_tail(self):
         """Host copy of the biases and heads for the inference kernel variant (one stream

@@ -182,6 +182,10 @@ class TrainStep:
                 K.adam_step_blob(self.blob[idx], [p.data for p in self.params[idx]], self.m[idx], self.v[idx],
                                  self.lr, self.betas, self.eps, self.it, grad_scale=1. / self.world)
         _model.bump_param_epoch()
+        # re-pack both networks' forward and transposed blobs in one launch
+        bufs = [net.packed_buffers() for net in (self.coarse, self.fine)]
+        K.pack_models_train(self.params, [b[0] for b in bufs], [b[1] for b in bufs])
+        self.coarse.mark_packed(); self.fine.mark_packed()
         # main.py:392-394: the decayed rate takes effect from the next iteration on
         self.lr = decayed_learning_rate(self.it, self.lr_decay * 1000, self.lr0)
 

@@ -163,6 +163,10 @@ int nerf_mlp_fwd_use_pairs(int enable);
  * order, like nerf_pack_model), adding to them when accumulate != 0. */
 size_t nerf_packed_model_bwd_bytes(void);
 int nerf_pack_model_bwd(const float* const* host_params, void* packed_bwd_out, void* stream);
+/* nerf_pack_model + nerf_pack_model_bwd for n_models (1 or 2) Models in one launch (what a train
+ * step re-packs after the optimizer).  host_params: n_models x 24 device pointers. */
+int nerf_pack_models_train(int n_models, const float* const* host_params, void* const* packed_out,
+                           void* const* packed_bwd_out, void* stream);
 size_t nerf_mlp_dz_bytes(long M);
 int nerf_mlp_bwd_dz(const void* packed_bwd, const float* grad_raw, const void* act_save, long M,
                     void* dz_out, void* stream);

@@ -121,10 +121,12 @@ def test_train_step_equals_autograd_path_and_adam(name):
             assert d.max().item() <= 2.1 * 5e-4
             assert (d > 1e-5).float().mean().item() <= 0.02
     assert abs(ts.lr - 5e-4 * 0.1 ** (1 / 250000)) < 1e-12
-    # the packed weights follow the update
-    before = coarse2._packed_key
-    coarse2.packed()
-    assert coarse2._packed_key != before
+    # the packed weights follow the update: apply_gradients re-packed both networks in one launch,
+    # and the blobs equal a fresh stand-alone pack of the updated parameters
+    for net in (coarse2, fine2):
+        assert net._packed_key == net._cache_key()
+        assert torch.equal(net.packed(), K.pack_model(net.ordered_params()))
+        assert torch.equal(net.packed_bwd(), K.pack_model_bwd(net.ordered_params()))
 
 
 def test_short_training_run_reduces_loss():

@@ -59,7 +59,7 @@ for tag, net, S, act in (("coarse", coarse, 64, ts.act_c), ("fine", fine, 192, t
     total += timeit(f"fwd {tag}", lambda: K.mlp_fwd(pk, K.IN_RAYS, rays, z, rows, S, vt, S), flop=rows * 1186816)
     total += timeit(f"fwd+save {tag}", lambda: K.mlp_fwd(pk, K.IN_RAYS, rays, z, rows, S, vt, S, act_save=act),
                     bytes_=rows * 4992, flop=rows * 1186816) * 0
-    total += timeit(f"dz {tag}", lambda: K.mlp_bwd_dz(pkb, graw, act, rows, dz=ts.dz), bytes_=rows * (4352 + 4864),
+    total += timeit(f"dz {tag}", lambda: K.mlp_bwd_dz(pkb, graw, act, rows, dz=ts.dz), bytes_=rows * (288 + 4864),
                     flop=rows * 2 * 557696)
     total += timeit(f"dw {tag}", lambda: _lib.check(lib.nerf_mlp_bwd_dw(act.data_ptr(), ts.dz.data_ptr(), rows, blob.data_ptr(), st), "dw"),
                     bytes_=rows * 9856, flop=rows * 2 * 592768)

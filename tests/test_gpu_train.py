@@ -146,3 +146,52 @@ def test_short_training_run_reduces_loss():
     print("loss first/last", losses[0], losses[-1])
     assert all(np.isfinite(losses))
     assert np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5])
+
+
+def test_reference_train_loop_body_runs_unchanged():
+    """The body of the reference's train loop (main.py:344-394), line for line, on the drop-in
+    modules: create_model kwargs, render(rays=...), mse on rgb and rgb_c, backward, optimizer.step,
+    learning-rate decay through param_groups."""
+    from types import SimpleNamespace
+    from cv_nerf_b200 import main as M
+    torch.manual_seed(0)
+    np.random.seed(0)
+    args = SimpleNamespace(netchunk=65536, lr=5e-4, perturb=1., n_fine_samples=128, n_coarse_samples=64,
+                           white_bkg=True, noise=0., dtype='blender', no_ndc=False, lr_decay=500, n_rays=512)
+    render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer = M.create_model(args)
+    assert len(grad_vars) == 48 and render_kwargs_train['ndc'] is False
+    render_kwargs_train.update(near=2., far=6.)
+    height, width, focal = 40, 40, 55.
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, height), torch.linspace(0, 1, width), indexing="ij")
+    im = torch.stack([xx, yy, 0.5 * torch.ones_like(xx)], -1).to(DEV)
+    pose = O.lego_pose(-180., -30., 4.).to(DEV)
+    mse = lambda x, y: torch.mean((x - y) ** 2)
+    losses = []
+    for i in range(1, 13):
+        ray_ori, ray_dir = M.compute_rays(height, width, focal, pose[:3, :4])                     # main.py:351
+        ys, xs = torch.meshgrid(torch.linspace(0, height - 1, height), torch.linspace(0, width - 1, width), indexing="ij")
+        img_grid = torch.reshape(torch.stack([ys, xs], -1), [-1, 2])                              # main.py:364-367
+        idxs = np.random.choice(img_grid.shape[0], size=[args.n_rays], replace=False)             # main.py:368
+        selected_pixels = img_grid[idxs].long().to(DEV)
+        ray_ori = ray_ori[selected_pixels[:, 0], selected_pixels[:, 1]]                           # main.py:371-372
+        ray_dir = ray_dir[selected_pixels[:, 0], selected_pixels[:, 1]]
+        batch_rays = torch.stack([ray_ori, ray_dir], 0)
+        pixels = im[selected_pixels[:, 0], selected_pixels[:, 1]]
+        rgb, extras = M.render(height, width, focal, 32768, rays=batch_rays, **render_kwargs_train)   # main.py:376
+        optimizer.zero_grad()                                                                     # main.py:379
+        loss = mse(rgb, pixels)
+        if 'rgb_c' in extras:
+            loss = loss + mse(extras['rgb_c'], pixels)
+        loss.backward()
+        optimizer.step()
+        new_lrate = M.decayed_learning_rate(i, args.lr_decay * 1000, args.lr)                     # main.py:392-394
+        for param_group in optimizer.param_groups:
+            param_group['lr'] = new_lrate
+        losses.append(loss.item())
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-3:]) < np.mean(losses[:3])
+    # test-time render with the test kwargs (perturb False, noise 0) on a full small frame
+    render_kwargs_test.update(near=2., far=6.)
+    with torch.no_grad():
+        frame, _ = M.render(height, width, focal, 32768, c2w=pose[:3, :4], **render_kwargs_test)
+    assert frame.shape == (height, width, 3) and bool(torch.isfinite(frame).all())

@@ -1035,6 +1035,8 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
         } else if (lane == 0) {
             // ===================== leader: MMA issuer for the pair =====================
             uint32_t it = 0, n_ready[2] = {0, 0};
+            long long tw_a = 0, tw_w = 0, tw_p = 0;
+            const long long t_begin = clock64();
             constexpr uint32_t kIdescPair256 = umma::instr_desc_bf16(256, 256);
             constexpr uint32_t kIdescPair128 = umma::instr_desc_bf16(256, 128);
             for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
@@ -1042,7 +1044,9 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                     const int chunks = layer_chunks(l);
                     const uint32_t idesc = layer_halves(l) == 2 ? kIdescPair256 : kIdescPair128;
                     for (int g = 0; g < 2; ++g) {
+                        long long t0 = clock64();
                         umma::mbar_wait_cluster(bar_a_ready + 8 * g, n_ready[g] & 1);
+                        tw_a += clock64() - t0;
                         ++n_ready[g];
                         umma::tc_fence_after();
                         const uint32_t d_base = tmem_base + g * 256;
@@ -1055,8 +1059,12 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                             else a_addr = a_tile + j * 16384;
                             const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
                             ++it;
+                            long long t1 = clock64();
                             umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                            long long t2 = clock64();
                             umma::mbar_wait_cluster(bar_w_peer + 8 * slot, ph);
+                            tw_w += t2 - t1;
+                            tw_p += clock64() - t2;
                             umma::tc_fence_after();
                             const uint32_t b_addr = sbase + kOffW + slot * kStageBytes;
 #pragma unroll
@@ -1070,6 +1078,10 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                         umma::mma_commit_pair(bar_acc_full + 8 * g);
                     }
                 }
+            }
+            if (P.stats_out) {
+                long long* o = P.stats_out + (long)blockIdx.x * 8;
+                o[1] = tw_a; o[2] = tw_w; o[6] = tw_p; o[5] = clock64() - t_begin;
             }
         }
     } else {
@@ -1343,6 +1355,11 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
     if (rc) return rc;
     if (M == 0) return 0;
     P.stats_out = stats_out;
+    if (variant == 100) {      // CTA-pair kernel (needs a host tail: the caller's tail is read from the blob here)
+        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return (int)e;
+        return launch_fwd_pair(P, stream);
+    }
     return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }
 

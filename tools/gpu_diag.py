@@ -104,7 +104,7 @@ def timing():
                   f"({n_rays * S / ms / 1e3:.2f} M samples/s)")
 
 
-def pipeline_stats(variants=(1, 3, 4, 5, 6, 7)):
+def pipeline_stats(variants=(1, 3, 7, 100)):
     """Per-role wait-cycle breakdown of the field kernel (debug entry nerf_mlp_fwd_stats)."""
     from cv_nerf_b200 import _lib
     lib = _lib.load()
@@ -119,7 +119,8 @@ def pipeline_stats(variants=(1, 3, 4, 5, 6, 7)):
     vt = K.viewdir_term(packed, rays)
     raw = torch.empty(n_rays * S, 4, device=DEV)
     names = {1: "ring 2x32KB (production layout)", 2: "ring 1x32KB", 3: "ring 3x32KB (PE aliased, timing only)",
-             4: "EXP no A-tile stores", 5: "EXP no bias loads", 6: "EXP no TMEM loads", 7: "EXP none of the three"}
+             4: "EXP no A-tile stores", 5: "EXP no bias loads", 6: "EXP no TMEM loads", 7: "EXP none of the three",
+             100: "CTA pairs (cta_group::2); leader CTAs only; [6] = wait for the peer's half-chunk"}
     st = torch.cuda.current_stream().cuda_stream
     for v in variants:
         stats = torch.zeros(148, 8, dtype=torch.int64, device=DEV)
@@ -132,11 +133,12 @@ def pipeline_stats(variants=(1, 3, 4, 5, 6, 7)):
             torch.cuda.synchronize()
             assert rc == 0, lib.nerf_b200_last_error()
         ms = e0.elapsed_time(e1)
-        s = stats.double().mean(0).cpu()
+        rows = stats[stats[:, 5] > 0].double()
+        s = rows.mean(0).cpu()
         tot = s[5].item()
         print(f"variant {v} {names.get(v, '')}: {ms:.2f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s | "
               f"cycles/CTA {tot:.3e}; wait fractions: producer(empty) {s[0] / tot:.2f}  mma(a_ready) {s[1] / tot:.2f}  "
-              f"mma(w_full) {s[2] / tot:.2f}  epiX(acc) {s[3] / tot:.2f}  epiY(acc) {s[4] / tot:.2f}")
+              f"mma(w_full) {s[2] / tot:.2f}  epiX(acc) {s[3] / tot:.2f}  epiY(acc) {s[4] / tot:.2f}  mma(w_peer) {s[6] / tot:.2f}")
 
 
 if __name__ == "__main__":

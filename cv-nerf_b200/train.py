@@ -124,6 +124,8 @@ class TrainStep:
         """rays [n,11], target [n,3] -> loss tensor; gradients of both networks accumulated into
         self.blob (zeroed first).  ``draws``: main.RenderDraws with injected random numbers."""
         n = rays.shape[0]
+        if n > self.n_rays:
+            raise NerfB200Error(f"TrainStep was sized for {self.n_rays} rays per step, got {n}")
         dev = self.dev
         pick = lambda t, shape, fn: (t.to(dev).float().contiguous() if t is not None else fn(shape, device=dev))
         t_rand = None

@@ -54,7 +54,8 @@ constexpr uint32_t kIdescN128 = umma::instr_desc_bf16(128, 128);
 // only) change the ring depth; ALIAS additionally places the PE tiles on top of the A tiles to
 // free 32 KB for a deeper ring -- numerically wrong, used only to time the pipeline.
 // EXP (timing experiments, wrong numerics): bit0 skip the A-tile stores, bit1 skip the bias loads,
-// bit2 skip the TMEM loads.
+// bit2 skip the TMEM loads, bit3 no weight streaming at all (the MMAs read whatever the ring holds:
+// the speed the kernel would have if weight slots were always ready).
 template <int RING, bool ALIAS, int EXP = 0>
 struct Cfg {
     static constexpr int ring = RING;
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
 
     if (warp == 0) {
         // ===================== producer: weight slots, L2 -> smem =====================
-        if (lane == 0) {
+        if (lane == 0 && !(CFG::exp & 8)) {
             uint32_t it = 0;
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
@@ -477,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                             const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
                             ++it;
                             long long t1 = PROBE ? clock64() : 0;
-                            umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                            if (!(CFG::exp & 8)) umma::mbar_wait(bar_w_full + 8 * slot, ph);
                             if (PROBE) t_wait1 += clock64() - t1;
                             umma::tc_fence_after();
                             // B = [N rows][64] K-major; the two 128-row halves are contiguous
@@ -698,6 +699,284 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
         if (warp == 1) { o[1] = t_wait0; o[2] = t_wait1; }
         if (warp == 2) o[3] = t_wait0;
         if (warp == 2 + kEpiWarpsPerGroup) o[4] = t_wait0;
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------- TS kernel
+// Inference variant whose activations never touch shared memory: the epilogue writes the BF16
+// activations of a layer straight into TENSOR MEMORY (tcgen05.st) and the next layer's MMA reads its
+// A operand from there (tcgen05.mma "TS" form).  Measured on B200 (tools/probes/mma_rate_probe.cu):
+// an M=128 x N=256 x K=16 BF16 MMA issues every 166 cycles in the SS form (both operands from shared
+// memory) and every 137 cycles in the TS form (= 7650 FLOP/cycle/SM, the tensor peak); N=128 MMAs are
+// slower per column in either form (102 / 88 cycles).  The TS form also takes the 64 KB of epilogue
+// stores and the 64 KB of A-operand reads per tile and layer off the shared-memory pipe.
+//
+// Tensor memory (512 columns) is two regions of 256 columns, R0 and R1.  Layer l accumulates into
+// R[l & 1] (N = 256 FP32 columns) from the A operand in R[(l - 1) & 1].  The epilogue converts the
+// accumulator IN PLACE: the thread that owns row r and column group cg reads the 16 FP32 columns
+// [64 j + 16 cg, +16) of K chunk j and writes the 16 BF16 features back as 8 packed columns at
+// [64 j + 16 cg, +8) -- columns only this thread has read -- which is exactly the K = 16 slice
+// (j, kk = cg) the next layer's MMA addresses.  The region the next layer accumulates into held this
+// layer's A operand, which is dead once this layer's MMAs have completed.
+//
+// One 128-row tile per CTA is in flight, so MMA and epilogue overlap INSIDE the tile, by K chunk:
+// the 16-warp epilogue crew (four threads per row) finishes chunk 0 of layer l first and signals it;
+// the MMA warp starts layer l+1 on chunk 0 while the crew converts chunks 1..3.  The tensor core idles
+// only from the last MMA of a layer to the first converted chunk.
+//   warp 0      producer: 32 KB weight slots ([256 out][64 in], all N) through a 5-slot ring
+//   warp 1      MMA issuer
+//   warps 2-17  epilogue crew: warp = (TMEM lane quadrant, column group cg)
+// The PE tile (A operand of l1 and of l6's first K chunk) stays in shared memory (SS form) and is
+// double-buffered across tiles; sigma / rgb heads as in the other variants (FP32, CUDA cores).
+constexpr int kTsRing = 5;
+constexpr uint32_t kTsOffPE = 0;                               // 2 x [128][64] bf16
+constexpr uint32_t kTsOffXchg = 2 * 16384;                     // [128 rows][4] float4
+constexpr uint32_t kTsOffW = kTsOffXchg + 128 * 4 * 16;        // ring x 32 KB (1 KB aligned: 40960)
+constexpr uint32_t kTsOffBar = kTsOffW + kTsRing * kSlotBytes;
+constexpr uint32_t kTsSmemBytes = kTsOffBar + 512;
+static_assert(kTsOffW % 1024 == 0 && kTsSmemBytes <= 232448, "TS kernel shared memory");
+
+// Epilogue of hidden layer L for this thread (row, column group cg): per K chunk j, 16 accumulator
+// columns + bias -> activation -> BF16 -> 8 packed columns in place, then the chunk is signalled.
+// treg: tensor-memory address of (this warp's lane quadrant, first column of the layer's region).
+template <int MODE, int L>
+__device__ __forceinline__ void epilogue_ts(uint32_t treg, int cg, uint32_t bar_a, float& sigma, const ConstTail& ct) {
+    uint32_t v[2][16];
+    umma::tmem_ld16(treg + cg * 16, v[0]);
+    float2 sig2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        umma::tmem_wait_ld();
+        if (j + 1 < 4) umma::tmem_ld16(treg + (j + 1) * 64 + cg * 16, v[(j + 1) & 1]);
+        const uint32_t(&cur)[16] = v[j & 1];
+        const float* bl = ct.bias + L * kHidden + j * 64 + cg * 16;
+        uint32_t o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float2 h = __fadd2_rn(make_float2(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1])),
+                                  make_float2(bl[2 * e], bl[2 * e + 1]));
+            if (MODE == 1) {
+                h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f);
+                const float* wa = ct.walpha + j * 64 + cg * 16 + 2 * e;
+                sig2 = __ffma2_rn(make_float2(wa[0], wa[1]), h, sig2);
+            }
+            o[e] = MODE == 0 ? pack_relu_bf16x2(h.x, h.y) : pack_bf16x2(h.x, h.y);
+        }
+        umma::tmem_st8(treg + j * 64 + cg * 16, o);
+        umma::tmem_wait_st();
+        umma::tc_fence_before();
+        // one arrival per warp: 512 per-thread arrivals on one mbarrier serialise on the shared-memory
+        // atomic unit (4 chunks x 9 layers per tile) and were the critical path of the first version
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar_a + 8 * j);
+    }
+    if (MODE == 1) sigma += sig2.x + sig2.y;
+}
+
+__device__ __forceinline__ void epilogue_ts_layer(int l, uint32_t treg, int cg, uint32_t bar_a, float& sigma,
+                                                  const ConstTail& ct) {
+    switch (l) {
+#define NERF_TS_LAYER(LL, MODE) case LL: epilogue_ts<MODE, LL>(treg, cg, bar_a, sigma, ct); break;
+        NERF_TS_LAYER(0, 0) NERF_TS_LAYER(1, 0) NERF_TS_LAYER(2, 0) NERF_TS_LAYER(3, 0) NERF_TS_LAYER(4, 0)
+        NERF_TS_LAYER(5, 0) NERF_TS_LAYER(6, 0) NERF_TS_LAYER(7, 1)
+        default: epilogue_ts<2, 8>(treg, cg, bar_a, sigma, ct); break;
+#undef NERF_TS_LAYER
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_ts_kernel(const __grid_constant__ FwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = umma::smem_u32(smem);
+    if ((sbase & 1023u) != 0) __trap();
+    const uint32_t bar_w_full = sbase + kTsOffBar;                 // [kTsRing]
+    const uint32_t bar_w_empty = bar_w_full + 8 * kTsRing;         // [kTsRing]
+    const uint32_t bar_pe_ready = bar_w_empty + 8 * kTsRing;       // [2]  PE tile buffer written
+    const uint32_t bar_a = bar_pe_ready + 16;                      // [4]  K chunk j of the next A operand converted
+    const uint32_t bar_acc = bar_a + 32;                           // [2]  layer l accumulated (by layer parity)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kTsOffBar + 8 * (2 * kTsRing + 8));
+    static_assert(8 * (2 * kTsRing + 8) + 4 <= 512, "barrier region");
+    constexpr uint32_t kCrew = 2 * kEpiWarpsPerGroup * 32;         // 512 epilogue threads
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long n_tiles = (P.M + kTileM - 1) / kTileM;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kTsRing; ++s) {
+            umma::mbar_init(bar_w_full + 8 * s, 1);
+            umma::mbar_init(bar_w_empty + 8 * s, 1);
+        }
+        umma::mbar_init(bar_pe_ready, kCrew);
+        umma::mbar_init(bar_pe_ready + 8, kCrew);
+        for (int j = 0; j < 4; ++j) umma::mbar_init(bar_a + 8 * j, kCrew / 32);
+        umma::mbar_init(bar_acc, 1);
+        umma::mbar_init(bar_acc + 8, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) {
+        umma::tmem_alloc(umma::smem_u32(tmem_slot), 512);
+        umma::tmem_relinquish();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < kNumMmaLayers; ++l) {
+                    const int first = layer_first_stage(l), chunks = layer_chunks(l);
+                    const uint32_t bytes = layer_halves(l) * kStageBytes;
+                    for (int j = 0; j < chunks; ++j, ++it) {
+                        const uint32_t slot = it % kTsRing, ph = (it / kTsRing) & 1;
+                        umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                        umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
+                        umma::bulk_g2s(sbase + kTsOffW + slot * kSlotBytes,
+                                       P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes,
+                                       bar_w_full + 8 * slot);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t it = 0, n_a = 0;
+            long n = 0;
+            const bool stats = P.stats_out != nullptr;
+            long long tw_a = 0, tw_w = 0, tw_pe = 0, tw_x = 0, tw_i = 0;
+            uint32_t n_accm[2] = {0, 0};
+            const long long t_begin = stats ? clock64() : 0;
+            for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+                const uint32_t pe_tile = sbase + kTsOffPE + (uint32_t)(n & 1) * 16384;
+                for (int l = 0; l < kNumMmaLayers; ++l) {
+                    const int chunks = layer_chunks(l);
+                    const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
+                    const uint32_t a_in = tmem_base + (uint32_t)((l - 1) & 1) * 256;   // hidden input (l >= 1)
+                    const uint32_t d_addr = tmem_base + (uint32_t)(l & 1) * 256;
+                    if (l == 0) {
+                        // R0 was last read by the previous tile's l10 MMAs (same pipe, in order) and
+                        // converted by its l9 epilogue, which those MMAs waited for
+                        const long long t0 = stats ? clock64() : 0;
+                        umma::mbar_wait(bar_pe_ready + 8 * (uint32_t)(n & 1), (uint32_t)(n >> 1) & 1);
+                        if (stats) tw_pe += clock64() - t0;
+                        umma::tc_fence_after();
+                    }
+                    for (int j = 0; j < chunks; ++j) {
+                        const bool x_is_pe = l == 0 || (l == 5 && j == 0);
+                        const int jj = l == 5 ? j - 1 : j;              // K chunk of the hidden input
+                        if (!x_is_pe) {
+                            const long long t0 = stats ? clock64() : 0;
+                            umma::mbar_wait(bar_a + 8 * (uint32_t)jj, n_a & 1);
+                            if (stats) tw_a += clock64() - t0;
+                            umma::tc_fence_after();
+                        }
+                        const uint32_t slot = it % kTsRing, ph = (it / kTsRing) & 1;
+                        ++it;
+                        const long long t1 = stats ? clock64() : 0;
+                        umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                        if (stats) tw_w += clock64() - t1;
+                        umma::tc_fence_after();
+                        const uint32_t w_addr = sbase + kTsOffW + slot * kSlotBytes;
+                        const long long t3 = stats ? clock64() : 0;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
+                            const uint64_t b_desc = umma::smem_desc_sw128(w_addr + kk * 32);
+                            if (x_is_pe) umma::mma_bf16_ss(d_addr, umma::smem_desc_sw128(pe_tile + kk * 32), b_desc, idesc, acc);
+                            else umma::mma_bf16_ts(d_addr, a_in + (uint32_t)(jj * 64 + kk * 16), b_desc, idesc, acc);
+                        }
+                        umma::mma_commit(bar_w_empty + 8 * slot);
+                        if (stats) tw_i += clock64() - t3;
+                    }
+                    umma::mma_commit(bar_acc + 8 * (uint32_t)(l & 1));
+                    if (stats) {   // time to drain the MMA queue (diagnostic runs only)
+                        const long long t2 = clock64();
+                        umma::mbar_wait(bar_acc + 8 * (uint32_t)(l & 1), n_accm[l & 1] & 1);
+                        ++n_accm[l & 1];
+                        tw_x += clock64() - t2;
+                    }
+                    if (l >= 1) ++n_a;
+                }
+            }
+            if (stats) {   // [1] wait A chunk, [2] wait weights, [6] wait PE, [5] total, [3] crew wait acc, [4] crew busy
+                long long* o = P.stats_out + (long)blockIdx.x * 8;
+                o[1] = tw_a; o[2] = tw_w; o[6] = tw_pe; o[5] = clock64() - t_begin; o[0] = tw_x; o[7] = tw_i;
+            }
+        }
+    } else {
+        // ===================== epilogue crew (16 warps) =====================
+        const int cg = (warp - 2) >> 2;           // column group: 16 of the 64 columns of every K chunk
+        const int quad = warp & 3;                // TMEM lane quadrant
+        const int row = quad * 32 + lane;
+        const uint32_t quad_bar = 1 + quad;       // the four warps sharing rows
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float4* xchg = reinterpret_cast<float4*>(smem + kTsOffXchg) + row * 4;
+        uint32_t n_acc[2] = {0, 0};
+        const bool stats = P.stats_out != nullptr && warp == 2;
+        long long tw_acc = 0, t_epi = 0;
+        auto pe_stage = [&](long tile, long n) {
+            const long grow_raw = tile * kTileM + row;
+            const long grow = grow_raw < P.M ? grow_raw : P.M - 1;
+            uint8_t* pe_tile = smem + kTsOffPE + (n & 1) * 16384;
+            if (cg == 0) input_stage<0>(P, grow, pe_tile, row);
+            else if (cg == 1) input_stage<1>(P, grow, pe_tile, row);
+            umma::fence_proxy_async_smem();
+            umma::mbar_arrive(bar_pe_ready + 8 * (uint32_t)(n & 1));
+        };
+        if ((long)blockIdx.x < n_tiles) pe_stage(blockIdx.x, 0);
+        long n = 0;
+        for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+            float sigma = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < 9; ++l) {
+                const long long t0 = stats ? clock64() : 0;
+                umma::mbar_wait_warp(bar_acc + 8 * (uint32_t)(l & 1), n_acc[l & 1] & 1);
+                const long long t1 = stats ? clock64() : 0;
+                ++n_acc[l & 1];
+                umma::tc_fence_after();
+                epilogue_ts_layer(l, lane_base + (uint32_t)(l & 1) * 256, cg, bar_a, sigma, P.ct);
+                if (stats) { tw_acc += t1 - t0; t_epi += clock64() - t1; }
+                // the other PE buffer was last read by the previous tile's l6: encode the next tile
+                if (l == 0 && tile + gridDim.x < n_tiles) pe_stage(tile + gridDim.x, n + 1);
+            }
+            {   // l10 + l11: R1[0,128) holds the 128 pre-activations
+                umma::mbar_wait_warp(bar_acc + 8, n_acc[1] & 1);
+                ++n_acc[1];
+                umma::tc_fence_after();
+                const long grow_raw = tile * kTileM + row;
+                const bool valid = grow_raw < P.M;
+                const long grow = valid ? grow_raw : P.M - 1;
+                float rgb[3];
+                const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
+                epilogue_rgb<false, false, true, 2>(lane_base + 256, cg * 32, vt, nullptr, rgb, nullptr, 0, 0, P.ct);
+                // R1 is next written by the following tile's l2, which waits for this crew's l1 epilogue
+                if (cg > 0) xchg[cg] = make_float4(rgb[0], rgb[1], rgb[2], sigma);
+                umma::named_bar_sync(quad_bar, 128);
+                if (cg == 0 && valid) {
+                    const float4 p1 = xchg[1], p2 = xchg[2], p3 = xchg[3];
+                    float4 o;
+                    o.x = rgb[0] + p1.x + p2.x + p3.x + P.ct.b11[0];
+                    o.y = rgb[1] + p1.y + p2.y + p3.y + P.ct.b11[1];
+                    o.z = rgb[2] + p1.z + p2.z + p3.z + P.ct.b11[2];
+                    o.w = sigma + p1.w + p2.w + p3.w + P.ct.balpha[0];
+                    reinterpret_cast<float4*>(P.raw_out)[grow] = o;
+                }
+                umma::named_bar_sync(quad_bar, 128);      // the next tile's partials reuse the slots
+            }
+        }
+        if (stats && lane == 0) {
+            long long* o = P.stats_out + (long)blockIdx.x * 8;
+            o[3] = tw_acc; o[4] = t_epi;
+        }
     }
     umma::tc_fence_before();
     __syncthreads();
@@ -954,6 +1233,13 @@ constexpr int kPairRing = 4;
 constexpr uint32_t kPairOffBar = kOffW + kPairRing * kStageBytes;
 static_assert(kPairOffBar == kOffBar, "same footprint as the single-CTA kernel");
 
+// WIDE: one 16-warp epilogue crew (four threads per row, 64 columns each) serves the two sub-tiles of the
+// CTA alternately instead of one 8-warp group per sub-tile.  The pair MMA runs at the tensor peak
+// (128 cycles per M=256 x N=256 x K=16, tools/probes/pair_mma_rate_probe.cu), so a sub-tile's
+// MMA -> epilogue -> MMA chain must fit into about two layer times (2 x 2056 cycles); the 8-warp
+// epilogue alone takes ~3500 cycles, the crew about half of that.  Every crew warp arrives on the
+// leader's barrier itself (16 arrivals per CTA, no group barrier in the chain).
+template <bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -980,7 +1266,7 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
             umma::mbar_init(bar_w_peer + 8 * s, 1);
         }
         for (int g = 0; g < 2; ++g) {
-            umma::mbar_init(bar_a_ready + 8 * g, 2);
+            umma::mbar_init(bar_a_ready + 8 * g, WIDE ? 2 * 2 * kEpiWarpsPerGroup : 2);
             umma::mbar_init(bar_acc_full + 8 * g, 1);
         }
         umma::fence_barrier_init();
@@ -1084,6 +1370,77 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                 o[1] = tw_a; o[2] = tw_w; o[6] = tw_p; o[5] = clock64() - t_begin;
             }
         }
+    } else if (WIDE) {
+        // ===================== one 16-warp epilogue crew, alternating between the sub-tiles =====================
+        const int cg = (warp - 2) >> 2;          // column group: columns [64 cg, 64 cg + 64) of a hidden layer
+        const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;
+        const uint32_t quad_bar = 1 + quad;      // named barrier of the four warps sharing rows
+        const uint32_t swz = (uint32_t)(row & 7) << 4;
+        const uint32_t leader_a_ready = umma::map_to_cta(bar_a_ready, 0);
+        // this warp's part of sub-tile g's A operand (or PE tile) is written: stores fenced towards the
+        // async proxy, TMEM loads towards the tensor core, then one arrive per warp at the leader
+        auto signal_a_ready = [&](int g) {
+            umma::fence_proxy_async_smem();
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive_remote(leader_a_ready + 8 * g);
+        };
+        auto in_stage = [&](int g, long quad_idx) {
+            const long grow_raw = (quad_idx * 4 + rank * 2 + g) * kTileM + row;
+            const long grow = grow_raw < P.M ? grow_raw : P.M - 1;
+            uint8_t* pe_tile = smem + kOffPE + g * 16384;
+            if (cg == 0) input_stage<0>(P, grow, pe_tile, row);
+            else if (cg == 1) input_stage<1>(P, grow, pe_tile, row);
+            signal_a_ready(g);
+        };
+        float sigma[2] = {0.f, 0.f};
+        uint32_t n_full[2] = {0, 0};
+        if (cluster_id < n_quads) { in_stage(0, cluster_id); in_stage(1, cluster_id); }
+        for (long quad_idx = cluster_id; quad_idx < n_quads; quad_idx += n_clusters) {
+#pragma unroll 1
+            for (int l = 0; l < kNumMmaLayers; ++l) {
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
+                    const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
+                    umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full[g] & 1);
+                    ++n_full[g];
+                    umma::tc_fence_after();
+                    if (l < 9) {
+                        float sg = 0.f;
+                        epilogue_hidden_ct<4>(l, tacc, cg * 64, a_row_addr, swz, sg, P.ct);
+                        if (l == 7) sigma[g] = sg;
+                        signal_a_ready(g);
+                    } else {
+                        const long grow_raw = (quad_idx * 4 + rank * 2 + g) * kTileM + row;
+                        const bool valid = grow_raw < P.M;
+                        const long grow = valid ? grow_raw : P.M - 1;
+                        float rgb[3];
+                        const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
+                        epilogue_rgb<false, false, true, 2>(tacc, cg * 32, vt, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
+                        umma::tc_fence_before();
+                        // FP32 hand-over between the four threads of a row, inside the row's own PE
+                        // line (free between l6's MMA and the next tile's encoding)
+                        float4* xchg = reinterpret_cast<float4*>(smem + kOffPE + g * 16384 + row * 128);
+                        if (cg > 0) xchg[cg - 1] = make_float4(rgb[0], rgb[1], rgb[2], sigma[g]);
+                        umma::named_bar_sync(quad_bar, 128);
+                        if (cg == 0 && valid) {
+                            const float4 p1 = xchg[0], p2 = xchg[1], p3 = xchg[2];
+                            float4 o;
+                            o.x = rgb[0] + p1.x + p2.x + p3.x + P.ct.b11[0];
+                            o.y = rgb[1] + p1.y + p2.y + p3.y + P.ct.b11[1];
+                            o.z = rgb[2] + p1.z + p2.z + p3.z + P.ct.b11[2];
+                            o.w = sigma[g] + p1.w + p2.w + p3.w + P.ct.balpha[0];
+                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
+                        }
+                        // the next tile's encoding overwrites the hand-over slots: wait for the reads
+                        umma::named_bar_sync(quad_bar, 128);
+                        if (quad_idx + n_clusters < n_quads) in_stage(g, quad_idx + n_clusters);
+                    }
+                }
+            }
+        }
     } else {
         // ===================== epilogue groups =====================
         const int ew = warp - 2;
@@ -1174,13 +1531,14 @@ FwdKernel fwd_variant(int v) {
         case 8: return mlp_fwd_kernel<false, Cfg<kRing, false>, true>;   // training: saves activations
         case 9: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;   // inference with the host tail
         case 10: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true, true>;   // + 16-warp epilogue crew
+        case 11: return mlp_fwd_kernel<true, Cfg<kRing, false, 8>>;
         default: return nullptr;
     }
 }
 
 int launch_fwd(const FwdParams& P, int variant, void* stream) {
     static int sm_count = 0;
-    static bool configured[11] = {};
+    static bool configured[12] = {};
     FwdKernel k = fwd_variant(variant);
     if (!k) return nerf::arg_error("nerf_mlp_fwd: variant");
     if (sm_count == 0) {
@@ -1211,6 +1569,31 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
 // measured on B200 (profiles/r01_fwd_variants_ncu.txt): 0 is the fastest of the three
 int g_use_pairs = 0;
 
+int launch_fwd_ts(const FwdParams& P, void* stream) {
+    static int sm_count = 0;
+    static bool configured = false;
+    if (sm_count == 0) {
+        sm_count = nerf_b200_sm_count();
+        if (sm_count <= 0) {
+            sm_count = 0;
+            nerf::set_last_error("nerf_mlp_fwd setup: no CUDA device");
+            return (int)cudaErrorNoDevice;
+        }
+    }
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
+        if (e != cudaSuccess) {
+            nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    const long n_tiles = (P.M + kTileM - 1) / kTileM;
+    const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
+    mlp_fwd_ts_kernel<<<grid, kThreads, kTsSmemBytes, (cudaStream_t)stream>>>(P);
+    return nerf::check_launch("nerf_mlp_fwd (TS)");
+}
+
 int launch_fwd_tr(const FwdParams& P, void* stream) {
     static int sm_count = 0;
     static bool configured = false;
@@ -1236,7 +1619,7 @@ int launch_fwd_tr(const FwdParams& P, void* stream) {
     return nerf::check_launch("nerf_mlp_fwd (mixed orientation)");
 }
 
-int launch_fwd_pair(const FwdParams& P, void* stream) {
+int launch_fwd_pair(const FwdParams& P, void* stream, bool wide = false) {
     static int sm_count = 0;
     static bool configured = false;
     if (sm_count == 0) {
@@ -1248,7 +1631,9 @@ int launch_fwd_pair(const FwdParams& P, void* stream) {
         }
     }
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) {
             nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
             return (int)e;
@@ -1258,7 +1643,8 @@ int launch_fwd_pair(const FwdParams& P, void* stream) {
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
     const long n_quads = (n_tiles + 3) / 4;
     const long clusters = n_quads < sm_count / 2 ? n_quads : sm_count / 2;
-    mlp_fwd_pair_kernel<<<(unsigned)(2 * clusters), kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    if (wide) mlp_fwd_pair_kernel<true><<<(unsigned)(2 * clusters), kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    else mlp_fwd_pair_kernel<false><<<(unsigned)(2 * clusters), kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
     return nerf::check_launch("nerf_mlp_fwd (CTA pairs)");
 }
 
@@ -1320,6 +1706,8 @@ extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail,
     if (M == 0) return 0;
     memcpy(&P.ct, host_tail, sizeof(ConstTail));
     if (g_use_pairs == 3) return launch_fwd_tr(P, stream);
+    if (g_use_pairs == 4) return launch_fwd_ts(P, stream);
+    if (g_use_pairs == 5) return launch_fwd_pair(P, stream, true);
     return g_use_pairs == 1 ? launch_fwd_pair(P, stream) : launch_fwd(P, g_use_pairs == 2 ? 10 : 9, stream);
 }
 
@@ -1359,6 +1747,16 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
         return launch_fwd_pair(P, stream);
+    }
+    if (variant == 101) {      // CTA pairs with the 16-warp crew
+        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return (int)e;
+        return launch_fwd_pair(P, stream, true);
+    }
+    if (variant == 200) {      // TS kernel
+        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return (int)e;
+        return launch_fwd_ts(P, stream);
     }
     return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }

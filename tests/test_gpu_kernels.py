@@ -299,10 +299,18 @@ def test_field_kernel_variants_agree(rows, S):
         crew = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
         K.use_pairs(3)
         mixed = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+        K.use_pairs(4)
+        ts = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+        K.use_pairs(5)
+        pairs_crew = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
         torch.cuda.synchronize()
     finally:
         K.use_pairs(old)
     print("mixed-orientation vs base max abs diff", (mixed - base).abs().max().item())
+    print("TS vs base max abs diff", (ts - base).abs().max().item())
+    print("pairs + crew vs base max abs diff", (pairs_crew - base).abs().max().item())
+    assert (pairs_crew - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
+    assert (ts - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
     assert (mixed - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
     assert torch.equal(single, base), (single - base).abs().max().item()
     assert torch.equal(pairs, base), (pairs - base).abs().max().item()

@@ -82,7 +82,8 @@ def timing():
         vt = K.viewdir_term(packed, rays)
         ref = None
         for tag, tail, mode in (("smem bias", None, 0), ("host tail, single CTA", ht, 0), ("host tail, CTA pairs", ht, 1),
-                                ("host tail, single CTA, 16-warp crew", ht, 2), ("host tail, mixed orientation", ht, 3)):
+                                ("host tail, single CTA, 16-warp crew", ht, 2), ("host tail, mixed orientation", ht, 3), ("host tail, TS (activations in TMEM)", ht, 4),
+                                ("host tail, CTA pairs + 16-warp crew", ht, 5)):
             K.use_pairs(mode)
             for _ in range(3):
                 raw = K.mlp_fwd(packed, K.IN_RAYS, rays, z, n_rays * S, S, vt, S, host_tail=tail)
@@ -104,7 +105,7 @@ def timing():
                   f"({n_rays * S / ms / 1e3:.2f} M samples/s)")
 
 
-def pipeline_stats(variants=(1, 3, 7, 100)):
+def pipeline_stats(variants=(1, 100, 101)):
     """Per-role wait-cycle breakdown of the field kernel (debug entry nerf_mlp_fwd_stats)."""
     from cv_nerf_b200 import _lib
     lib = _lib.load()
@@ -120,7 +121,10 @@ def pipeline_stats(variants=(1, 3, 7, 100)):
     raw = torch.empty(n_rays * S, 4, device=DEV)
     names = {1: "ring 2x32KB (production layout)", 2: "ring 1x32KB", 3: "ring 3x32KB (PE aliased, timing only)",
              4: "EXP no A-tile stores", 5: "EXP no bias loads", 6: "EXP no TMEM loads", 7: "EXP none of the three",
-             100: "CTA pairs (cta_group::2); leader CTAs only; [6] = wait for the peer's half-chunk"}
+             11: "EXP no weight streaming (upper bound if weight slots were always ready)",
+             100: "CTA pairs (cta_group::2); leader CTAs only; [6] = wait for the peer's half-chunk",
+             101: "CTA pairs + 16-warp crew; leader CTAs only",
+             200: "TS kernel (activations in TMEM); producer(empty) = MMA thread waits for its own commit (queue drain), epiX = crew wait for acc, epiY = crew hidden-epilogue busy, w_peer = wait PE"}
     st = torch.cuda.current_stream().cuda_stream
     for v in variants:
         stats = torch.zeros(148, 8, dtype=torch.int64, device=DEV)
@@ -138,7 +142,7 @@ def pipeline_stats(variants=(1, 3, 7, 100)):
         tot = s[5].item()
         print(f"variant {v} {names.get(v, '')}: {ms:.2f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s | "
               f"cycles/CTA {tot:.3e}; wait fractions: producer(empty) {s[0] / tot:.2f}  mma(a_ready) {s[1] / tot:.2f}  "
-              f"mma(w_full) {s[2] / tot:.2f}  epiX(acc) {s[3] / tot:.2f}  epiY(acc) {s[4] / tot:.2f}  mma(w_peer) {s[6] / tot:.2f}")
+              f"mma(w_full) {s[2] / tot:.2f}  epiX(acc) {s[3] / tot:.2f}  epiY(acc) {s[4] / tot:.2f}  mma(w_peer) {s[6] / tot:.2f}  [7] {s[7] / tot:.2f}")
 
 
 if __name__ == "__main__":

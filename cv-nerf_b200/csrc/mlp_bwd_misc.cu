@@ -36,13 +36,17 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------ l_alpha / l11
-// 8 warps; warp w owns rows w, w+8, ... of a tile, lane l owns the 16-byte chunk l of the row's
+// WARPS warps; warp w owns rows w, w+WARPS, ... of a tile, lane l owns the 16-byte chunk l of the row's
 // h8 line (features 8l..8l+7) and, for l < 16, of its h10 line: whole 128-byte lines per request,
-// 16 independent requests per lane and tile.  HBM-bound: 96 KB per tile.
-__global__ void __launch_bounds__(256) heads_bwd_kernel(const uint8_t* __restrict__ act,
-                                                        const float* __restrict__ grad_raw, long M,
-                                                        long n_tiles, float* __restrict__ grad) {
-    __shared__ float red[8][256 + 3 * 128 + 4];
+// 8 independent requests per lane in flight.  HBM-bound: 96 KB per tile.  WARPS = 4 (128 threads,
+// <= 80 registers, 10 KB shared memory) fits on an SM BESIDE the persistent dZ-chain CTA, which leaves
+// 10 K registers and ~30 KB: the training step launches it on a side stream under that tensor-bound
+// kernel instead of next to the HBM-bound dW kernel.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) heads_bwd_kernel(const uint8_t* __restrict__ act,
+                                                               const float* __restrict__ grad_raw, long M,
+                                                               long n_tiles, float* __restrict__ grad) {
+    __shared__ float red[WARPS][256 + 3 * 128 + 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float a8[8], r0[8], r1[8], r2[8], gb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -53,27 +57,35 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(const uint8_t* __restric
         const uint8_t* tile = act + (size_t)t * kActTileBytes;
         const uint8_t* h8 = tile + act_hidden(8) + blk_off;
         const uint8_t* h10 = tile + kActH10 + blk_off;
-#pragma unroll 4
-        for (int i = 0; i < kTileRows / 8; ++i) {
-            const int r = i * 8 + warp;
-            const long row = t * kTileRows + r;
-            const float4 g = row < M ? __ldg(reinterpret_cast<const float4*>(grad_raw) + row)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-            const uint32_t off = (uint32_t)r * 128 + ((c16 ^ (uint32_t)(r & 7)) << 4);
-            float h[8];
-            unpack8(ldg_nc_v4(h8 + off), h);
+        // four rows per step: all twelve loads are issued before the first one is used
+#pragma unroll 1
+        for (int i = 0; i < kTileRows / WARPS; i += 4) {
+            uint4 q8[4], q10[4];
+            float4 g[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a8[e] = fmaf(g.w, h[e], a8[e]);
-            if (lane < 16) {
-                unpack8(ldg_nc_v4(h10 + off), h);
+            for (int u = 0; u < 4; ++u) {
+                const int r = (i + u) * WARPS + warp;
+                const long row = t * kTileRows + r;
+                const uint32_t off = (uint32_t)r * 128 + ((c16 ^ (uint32_t)(r & 7)) << 4);
+                q8[u] = ldg_nc_v4(h8 + off);
+                q10[u] = lane < 16 ? ldg_nc_v4(h10 + off) : make_uint4(0u, 0u, 0u, 0u);
+                g[u] = row < M ? __ldg(reinterpret_cast<const float4*>(grad_raw) + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float h[8];
+                unpack8(q8[u], h);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a8[e] = fmaf(g[u].w, h[e], a8[e]);
+                unpack8(q10[u], h);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    r0[e] = fmaf(g.x, h[e], r0[e]);
-                    r1[e] = fmaf(g.y, h[e], r1[e]);
-                    r2[e] = fmaf(g.z, h[e], r2[e]);
+                    r0[e] = fmaf(g[u].x, h[e], r0[e]);
+                    r1[e] = fmaf(g[u].y, h[e], r1[e]);
+                    r2[e] = fmaf(g[u].z, h[e], r2[e]);
                 }
+                if (lane == 0) { gb[0] += g[u].x; gb[1] += g[u].y; gb[2] += g[u].z; gb[3] += g[u].w; }
             }
-            if (lane == 0) { gb[0] += g.x; gb[1] += g.y; gb[2] += g.z; gb[3] += g.w; }
         }
     }
 #pragma unroll
@@ -90,10 +102,10 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(const uint8_t* __restric
         for (int k = 0; k < 4; ++k) red[warp][256 + 384 + k] = gb[k];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 256 + 384 + 4; i += 256) {
+    for (int i = threadIdx.x; i < 256 + 384 + 4; i += WARPS * 32) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][i];
+        for (int w = 0; w < WARPS; ++w) s += red[w][i];
         float* dst = i < 256 ? grad + kG_WAlpha + i
                    : i < 256 + 384 ? grad + kG_W11 + (i - 256)
                    : (i - 640 < 3 ? grad + kG_B11 + (i - 640) : grad + kG_BAlpha);
@@ -102,16 +114,18 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(const uint8_t* __restric
 }
 
 // ------------------------------------------------------------------ l10 view columns / bias
-// One block walks over rays; its 8 warps split a ray's rows, 16 lanes cover one row's 128 dZ10
-// values with 16-byte loads (two rows per warp and request).
+// A block takes eight rays per step: each 16-lane group sums the dZ10 rows of ONE ray (16-byte loads,
+// 128 features per row, eight independent loads in flight per thread), the per-ray sums are exchanged
+// through shared memory, and thread j accumulates feature j's outer product with the rays' view
+// encodings.  Two block barriers per eight rays.
 __global__ void __launch_bounds__(128) viewdir_term_bwd_kernel(const uint8_t* __restrict__ dz,
                                                                const float* __restrict__ dirs, int dir_stride,
                                                                int embedded, long M, int div, long count,
                                                                float* __restrict__ grad) {
-    __shared__ float pe[28];
+    __shared__ float pe[8][28];
     __shared__ float part[8][128];
     const int j = threadIdx.x;
-    const int sub = j >> 4;                 // 8 row groups
+    const int sub = j >> 4;                 // ray slot of this 16-lane group
     const int l16 = j & 15;                 // chunk of the row: features 8*l16 .. 8*l16+7
     const uint32_t blk_off = (uint32_t)(l16 >> 3) * (uint32_t)kBlockBytes;
     const uint32_t c16 = l16 & 7;
@@ -119,44 +133,49 @@ __global__ void __launch_bounds__(128) viewdir_term_bwd_kernel(const uint8_t* __
 #pragma unroll
     for (int e = 0; e < kViewPeDim; ++e) acc[e] = 0.f;
     float accb = 0.f;
-    for (long ray = blockIdx.x; ray < count; ray += gridDim.x) {
-        __syncthreads();
-        const float* d = dirs + ray * dir_stride;
+    for (long ray0 = (long)blockIdx.x * 8; ray0 < count; ray0 += (long)gridDim.x * 8) {
+        __syncthreads();                    // the previous step's reads of pe / part are done
+        const long ray = ray0 + sub;
+        const bool live = ray < count;
+        const float* d = dirs + (live ? ray : 0) * dir_stride;
         if (embedded) {
-            if (j < kViewPeDim) pe[j] = __ldg(d + j);
+            for (int e = l16; e < kViewPeDim; e += 16) pe[sub][e] = live ? __ldg(d + e) : 0.f;
         } else {
-            if (j < 3) pe[j] = __ldg(d + j);
-            if (j >= 32 && j < 32 + 12) {
-                const int k = (j - 32) / 3, a = (j - 32) % 3;
-                float s, c;
-                sincosf(__ldg(d + a) * (float)(1 << k), &s, &c);
-                pe[3 + 6 * k + a] = s;
-                pe[3 + 6 * k + 3 + a] = c;
+            if (l16 < 3) pe[sub][l16] = live ? __ldg(d + l16) : 0.f;
+            if (l16 >= 3 && l16 < 15) {
+                const int k = (l16 - 3) / 3, a = (l16 - 3) % 3;
+                float sn, cs;
+                sincosf((live ? __ldg(d + a) : 0.f) * (float)(1 << k), &sn, &cs);
+                pe[sub][3 + 6 * k + a] = sn;
+                pe[sub][3 + 6 * k + 3 + a] = cs;
             }
         }
         float s8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) s8[e] = 0.f;
-        const long r0 = ray * div, r1 = (r0 + div < M) ? r0 + div : M;
-#pragma unroll 4
-        for (long row = r0 + sub; row < r1; row += 8) {
-            const int r = (int)(row & 127);
-            const uint8_t* p = dz + (size_t)(row >> 7) * kDzTileBytes + kDz10 + blk_off + (uint32_t)r * 128 +
-                               ((c16 ^ (uint32_t)(r & 7)) << 4);
-            float h[8];
-            unpack8(ldg_nc_v4(p), h);
+        if (live) {
+            const long r0 = ray * div, r1 = (r0 + div < M) ? r0 + div : M;
+#pragma unroll 8
+            for (long row = r0; row < r1; ++row) {
+                const int r = (int)(row & 127);
+                const uint8_t* p = dz + (size_t)(row >> 7) * kDzTileBytes + kDz10 + blk_off + (uint32_t)r * 128 +
+                                   ((c16 ^ (uint32_t)(r & 7)) << 4);
+                float h[8];
+                unpack8(ldg_nc_v4(p), h);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s8[e] += h[e];
+                for (int e = 0; e < 8; ++e) s8[e] += h[e];
+            }
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) part[sub][l16 * 8 + e] = s8[e];
         __syncthreads();
-        float dv = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) dv += part[g][j];
+        for (int g = 0; g < 8; ++g) {
+            const float dv = part[g][j];
 #pragma unroll
-        for (int e = 0; e < kViewPeDim; ++e) acc[e] = fmaf(dv, pe[e], acc[e]);
-        accb += dv;
+            for (int e = 0; e < kViewPeDim; ++e) acc[e] = fmaf(dv, pe[g][e], acc[e]);
+            accb += dv;
+        }
     }
 #pragma unroll
     for (int e = 0; e < kViewPeDim; ++e) atomicAdd(grad + kG_W10 + j * 288 + 256 + e, acc[e]);
@@ -233,9 +252,9 @@ extern "C" int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, l
     const long n_tiles = (M + kTileRows - 1) / kTileRows;
     int sms = nerf_b200_sm_count();
     if (sms <= 0) sms = 148;
-    const long grid = n_tiles < 4L * sms ? n_tiles : 4L * sms;
-    heads_bwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)act_save, grad_raw, M, n_tiles,
-                                                                      grad_blob);
+    const long grid = n_tiles < 6L * sms ? n_tiles : 6L * sms;
+    heads_bwd_kernel<4><<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)act_save, grad_raw, M, n_tiles,
+                                                                         grad_blob);
     return nerf::check_launch("nerf_mlp_bwd_heads");
 }
 
@@ -246,7 +265,8 @@ extern "C" int nerf_viewdir_term_bwd(const void* dz, const float* dirs, int dir_
     const long count = (M + vterm_div - 1) / vterm_div;
     int sms = nerf_b200_sm_count();
     if (sms <= 0) sms = 148;
-    const long grid = count < 8L * sms ? count : 8L * sms;
+    const long groups = (count + 7) / 8;
+    const long grid = groups < 8L * sms ? groups : 8L * sms;
     viewdir_term_bwd_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)dz, dirs, dir_stride,
                                                                              embedded, M, vterm_div, count, grad_blob);
     return nerf::check_launch("nerf_viewdir_term_bwd");

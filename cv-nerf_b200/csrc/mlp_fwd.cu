@@ -23,6 +23,7 @@
 // The two sub-tiles ping-pong: while the tensor core runs layer l of Y, group X runs the epilogue
 // of layer l of X, so MMA and epilogue overlap.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
             uint8_t* mask_tile = nullptr;          // every thread stores its own mask words
             if (SAVE) {
                 const long tile = pair * 2 + g;
-                const bool saver = gtid == 0 && tile < n_tiles;
+                const bool saver = gtid == 0 && tile < n_tiles && !(CFG::exp & 16);   // EXP bit4: no record copies (timing)
                 act_tile = saver ? P.act_save + (size_t)tile * kActTileBytes : nullptr;
                 mask_tile = tile < n_tiles ? P.act_save + (size_t)tile * kActTileBytes : nullptr;
                 // the previous tile's h10 copy must have left the A tile before l1's epilogue
@@ -1532,13 +1533,16 @@ FwdKernel fwd_variant(int v) {
         case 9: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;   // inference with the host tail
         case 10: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true, true>;   // + 16-warp epilogue crew
         case 11: return mlp_fwd_kernel<true, Cfg<kRing, false, 8>>;
+        case 12: return mlp_fwd_kernel<false, Cfg<kRing, false, 16>, true>;   // training forward without the record copies (timing)
+        case 13: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true, true>;   // no weight streaming + 16-warp crew (timing)
+        case 14: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true>;         // no weight streaming, host tail (timing)
         default: return nullptr;
     }
 }
 
 int launch_fwd(const FwdParams& P, int variant, void* stream) {
     static int sm_count = 0;
-    static bool configured[12] = {};
+    static bool configured[15] = {};
     FwdKernel k = fwd_variant(variant);
     if (!k) return nerf::arg_error("nerf_mlp_fwd: variant");
     if (sm_count == 0) {
@@ -1677,7 +1681,8 @@ extern "C" int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, c
     if (M == 0) return 0;
     if (act_save && ((uintptr_t)act_save & 15)) return nerf::arg_error("nerf_mlp_fwd: act_save must be 16-byte aligned");
     P.act_save = (uint8_t*)act_save;
-    return launch_fwd(P, act_save ? 8 : 0, stream);
+    static const bool no_copies = getenv("NERF_B200_EXP_NO_RECORD_COPIES") != nullptr;   // timing experiment only
+    return launch_fwd(P, act_save ? (no_copies ? 12 : 8) : 0, stream);
 }
 
 extern "C" size_t nerf_model_host_tail_bytes(void) { return sizeof(ConstTail); }
@@ -1757,6 +1762,10 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
         return launch_fwd_ts(P, stream);
+    }
+    if (variant == 9 || variant == 10 || variant == 13 || variant == 14) {   // host-tail kernels
+        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return (int)e;
     }
     return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }

@@ -330,29 +330,56 @@ def mlp_bwd_dz(packed_bwd, grad_raw, act, rows, dz=None):
     return dz
 
 
-def mlp_bwd_params(act, dz, grad_raw, rows, dirs, vterm_div, embedded, blob, side_stream=None):
-    """dW/db of every layer accumulated into the fp32 gradient blob (3 launches).
+def _cuda_stream(stream, dev):
+    return (stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream
 
-    With ``side_stream`` the two small CUDA-core kernels (l_alpha/l11 heads, l10 view columns) run on
-    that stream next to the HBM-bound tensor-core dW kernel instead of after it (they fit beside its
-    one CTA per SM); the caller's stream waits for them before returning."""
+
+def mlp_bwd_heads(act, grad_raw, rows, blob, stream=None):
+    """dW/db of l_alpha and l11 into the gradient blob (reads the saved h8 / h10 and grad_raw only, so
+    it can run as soon as the compositing backward is done)."""
     lib = _lib.load()
     grad_raw = f32c(grad_raw)
-    main = torch.cuda.current_stream(grad_raw.device)
-    st = main.cuda_stream
-    small = st
-    if side_stream is not None:
-        side_stream.wait_stream(main)
-        small = side_stream.cuda_stream
-    check(lib.nerf_mlp_bwd_dw(act.data_ptr(), dz.data_ptr(), rows, ptr(blob), st), "nerf_mlp_bwd_dw")
-    check(lib.nerf_mlp_bwd_heads(act.data_ptr(), ptr(grad_raw), rows, ptr(blob), small), "nerf_mlp_bwd_heads")
+    check(lib.nerf_mlp_bwd_heads(act.data_ptr(), ptr(grad_raw), rows, ptr(blob), _cuda_stream(stream, blob.device)),
+          "nerf_mlp_bwd_heads")
+    return blob
+
+
+def mlp_bwd_dw(act, dz, rows, blob, stream=None):
+    """dW/db of the eleven tensor-core layers into the gradient blob."""
+    lib = _lib.load()
+    check(lib.nerf_mlp_bwd_dw(act.data_ptr(), dz.data_ptr(), rows, ptr(blob), _cuda_stream(stream, blob.device)),
+          "nerf_mlp_bwd_dw")
+    return blob
+
+
+def viewdir_term_bwd(dz, rows, dirs, vterm_div, embedded, blob, stream=None):
+    """dW of l10's view-direction columns and db of l10 from the per-ray sums of dZ10."""
+    lib = _lib.load()
     if not embedded and dirs.shape[-1] == RAY_STRIDE:
         dptr, stride = dirs.data_ptr() + 32, RAY_STRIDE
     else:
         dirs = f32c(dirs)
         dptr, stride = dirs.data_ptr(), dirs.shape[-1]
-    check(lib.nerf_viewdir_term_bwd(dz.data_ptr(), dptr, stride, int(embedded), rows, vterm_div, ptr(blob), small),
-          "nerf_viewdir_term_bwd")
+    check(lib.nerf_viewdir_term_bwd(dz.data_ptr(), dptr, stride, int(embedded), rows, vterm_div, ptr(blob),
+                                    _cuda_stream(stream, blob.device)), "nerf_viewdir_term_bwd")
+    return blob
+
+
+def mlp_bwd_params(act, dz, grad_raw, rows, dirs, vterm_div, embedded, blob, side_stream=None):
+    """dW/db of every layer accumulated into the fp32 gradient blob (3 launches).
+
+    With ``side_stream`` the two small CUDA-core kernels (l_alpha/l11 heads, l10 view columns) run on
+    that stream next to the tensor-core dW kernel instead of after it; the caller's stream waits for
+    them before returning.  (train.TrainStep schedules the three launches itself: the heads kernel
+    under the dZ chain, the view columns beside dW.)"""
+    main = torch.cuda.current_stream(blob.device)
+    small = None
+    if side_stream is not None:
+        side_stream.wait_stream(main)
+        small = side_stream
+    mlp_bwd_dw(act, dz, rows, blob)
+    mlp_bwd_heads(act, grad_raw, rows, blob, stream=small)
+    viewdir_term_bwd(dz, rows, dirs, vterm_div, embedded, blob, stream=small)
     if side_stream is not None:
         main.wait_stream(side_stream)
     return blob

@@ -106,6 +106,8 @@ class TrainStep:
         self.act_c = torch.empty(K.act_bytes(rows_c), dtype=torch.uint8, device=dev)
         self.act_f = torch.empty(K.act_bytes(rows_f), dtype=torch.uint8, device=dev)
         self.dz = torch.empty(K.dz_bytes(max(rows_c, rows_f)), dtype=torch.uint8, device=dev)
+        self.dz_c = torch.empty(K.dz_bytes(rows_c), dtype=torch.uint8, device=dev)   # own buffer: the coarse
+        # network's view-column kernel may still read it while the fine dZ chain runs
         self.params = [coarse_model.ordered_params(), fine_model.ordered_params()]
         self.m = [[torch.zeros_like(p) for p in ps] for ps in self.params]
         self.v = [[torch.zeros_like(p) for p in ps] for ps in self.params]
@@ -154,12 +156,34 @@ class TrainStep:
         graw_f = K.composite_bwd(raw_f.view(n, self.s_f, 4), z_f, rays, noise_f, self.white_bkg, g_f)
         graw_c = K.composite_bwd(raw_c.view(n, self.s_c, 4), z_c, rays, noise_c, self.white_bkg, g_c)
 
+        # Gradient kernels.  Main stream: dZ chain and dW per network (tensor-core kernels, one CTA per
+        # SM).  Side stream: the CUDA-core kernels, placed under the kernel that leaves them room -- the
+        # l_alpha/l11 heads (inputs: saved activations + grad_raw) start at once and run beside the
+        # tensor-bound dZ chains, which use about half of the HBM bandwidth; the view columns of a network
+        # follow its dZ chain.  Beside the HBM-bound dW kernel they only took bandwidth from it.
         self.blob.zero_()
-        for idx, (net, graw, act, rows, s) in enumerate(((self.coarse, graw_c, self.act_c, rows_c, self.s_c),
-                                                        (self.fine, graw_f, self.act_f, rows_f, self.s_f))):
-            graw = graw.view(rows, 4)
-            K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=self.dz)
-            K.mlp_bwd_params(act, self.dz, graw, rows, rays, s, False, self.blob[idx], side_stream=self.side)
+        main = torch.cuda.current_stream(dev)
+        side = self.side
+        side.wait_stream(main)
+        jobs = ((0, self.coarse, graw_c.view(rows_c, 4), self.act_c, rows_c, self.s_c, self.dz_c),
+                (1, self.fine, graw_f.view(rows_f, 4), self.act_f, rows_f, self.s_f, self.dz))
+        # NERF_B200_BWD_SCHED (A/B timing, tools/time_bwd_schedules.py): 0 everything on one stream,
+        # 1 small kernels beside dW, 2 (default) as described above.  On a power-capped B200 the three
+        # are within run-to-run noise of each other (5.75-6.1 ms per step).
+        sched = int(os.environ.get("NERF_B200_BWD_SCHED", "2"))
+        if sched == 2:
+            for idx, net, graw, act, rows, s, dz in jobs:
+                K.mlp_bwd_heads(act, graw, rows, self.blob[idx], stream=side)
+            for idx, net, graw, act, rows, s, dz in jobs:
+                K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=dz)
+                side.wait_stream(main)
+                K.viewdir_term_bwd(dz, rows, rays, s, False, self.blob[idx], stream=side)
+                K.mlp_bwd_dw(act, dz, rows, self.blob[idx])
+        else:
+            for idx, net, graw, act, rows, s, dz in jobs:
+                K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=dz)
+                K.mlp_bwd_params(act, dz, graw, rows, rays, s, False, self.blob[idx], side_stream=side if sched == 1 else None)
+        main.wait_stream(side)
         return self.loss
 
     @torch.no_grad()

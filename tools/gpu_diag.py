@@ -105,7 +105,7 @@ def timing():
                   f"({n_rays * S / ms / 1e3:.2f} M samples/s)")
 
 
-def pipeline_stats(variants=(1, 100, 101)):
+def pipeline_stats(variants=(1, 9, 14, 100, 101, 200)):
     """Per-role wait-cycle breakdown of the field kernel (debug entry nerf_mlp_fwd_stats)."""
     from cv_nerf_b200 import _lib
     lib = _lib.load()
@@ -121,6 +121,8 @@ def pipeline_stats(variants=(1, 100, 101)):
     raw = torch.empty(n_rays * S, 4, device=DEV)
     names = {1: "ring 2x32KB (production layout)", 2: "ring 1x32KB", 3: "ring 3x32KB (PE aliased, timing only)",
              4: "EXP no A-tile stores", 5: "EXP no bias loads", 6: "EXP no TMEM loads", 7: "EXP none of the three",
+             9: "host tail (production inference kernel); no counters", 10: "host tail + 16-warp crew; no counters",
+             13: "EXP no weight streaming + 16-warp crew; no counters", 14: "EXP no weight streaming, host tail; no counters",
              11: "EXP no weight streaming (upper bound if weight slots were always ready)",
              100: "CTA pairs (cta_group::2); leader CTAs only; [6] = wait for the peer's half-chunk",
              101: "CTA pairs + 16-warp crew; leader CTAs only",
@@ -138,8 +140,8 @@ def pipeline_stats(variants=(1, 100, 101)):
             assert rc == 0, lib.nerf_b200_last_error()
         ms = e0.elapsed_time(e1)
         rows = stats[stats[:, 5] > 0].double()
-        s = rows.mean(0).cpu()
-        tot = s[5].item()
+        s = rows.mean(0).cpu() if rows.shape[0] else torch.zeros(8, dtype=torch.float64)
+        tot = max(s[5].item(), 1.)
         print(f"variant {v} {names.get(v, '')}: {ms:.2f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s | "
               f"cycles/CTA {tot:.3e}; wait fractions: producer(empty) {s[0] / tot:.2f}  mma(a_ready) {s[1] / tot:.2f}  "
               f"mma(w_full) {s[2] / tot:.2f}  epiX(acc) {s[3] / tot:.2f}  epiY(acc) {s[4] / tot:.2f}  mma(w_peer) {s[6] / tot:.2f}  [7] {s[7] / tot:.2f}")

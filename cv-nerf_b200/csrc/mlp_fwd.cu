@@ -22,6 +22,7 @@
 //                CUDA cores from the FP32 accumulators of l8 / l10.
 // The two sub-tiles ping-pong: while the tensor core runs layer l of Y, group X runs the epilogue
 // of layer l of X, so MMA and epilogue overlap.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -94,6 +95,7 @@ struct FwdParams {
     float* probe_out;        // debug: [M][256] post-activation of layer probe_layer (or NULL)
     int probe_layer;
     long long* stats_out;    // debug: [grid][8] cycle counters (or NULL)
+    long long* trace_out;    // debug: [4 roles][1024] time-stamped events of CTA 0's 4th and 5th tile pair (or NULL)
     uint8_t* act_save;       // training: activation records, kActTileBytes per 128-row tile (or NULL)
 };
 
@@ -221,12 +223,15 @@ __device__ __forceinline__ uint32_t bf16x2_positive_mask(uint32_t w) {
 
 // MASKS (training): additionally returns the ReLU mask bits of this thread's columns in mw[0..3]
 // (layout in mlp_bwd_layout.h).
-template <int MODE, bool PROBE, int EXP, bool CT, int NIT = 8, int L = -1, bool MASKS = false>
-__device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
+// C0 >= 0: this thread's first column is a compile-time constant too (the callers branch on the column
+// half), which turns every bias / l_alpha address into a constant-bank immediate.
+template <int MODE, bool PROBE, int EXP, bool CT, int NIT = 8, int L = -1, bool MASKS = false, int C0 = -1>
+__device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0_rt, uint32_t row_addr, uint32_t swz,
                                                 uint32_t bias_addr,
                                                 const float* __restrict__ walpha, float& sigma,
                                                 float* probe_row, const ConstTail& ct, int l,
                                                 uint32_t* mw = nullptr) {
+    const int c0 = C0 >= 0 ? C0 : c0_rt;
     uint32_t v[2][16] = {};
     float4 b[2][4] = {};
     float2 sig2 = make_float2(0.f, 0.f);
@@ -244,7 +249,7 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float2 b0 = make_float2(bc[q].x, bc[q].y), b1 = make_float2(bc[q].z, bc[q].w);
-            if (CT) {
+            if (CT && !(EXP & 2)) {
                 const float4 bl = *reinterpret_cast<const float4*>(ct.bias + (L >= 0 ? L : l) * kHidden + c + q * 4);
                 b0 = make_float2(bl.x, bl.y);
                 b1 = make_float2(bl.z, bl.w);
@@ -299,15 +304,15 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0, uint32_t 
 }
 
 // CT epilogue of hidden layer l (0..8) with the layer index turned into a template constant.
-template <int NIT>
+template <int NIT, int EXP = 0, int C0 = -1>
 __device__ __forceinline__ void epilogue_hidden_ct(int l, uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
                                                    float& sigma, const ConstTail& ct) {
     switch (l) {
 #define NERF_CT_LAYER(LL, MODE) \
-        case LL: epilogue_hidden<MODE, false, 0, true, NIT, LL>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, LL); break;
+        case LL: epilogue_hidden<MODE, false, EXP, true, NIT, LL, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, LL); break;
         NERF_CT_LAYER(0, 0) NERF_CT_LAYER(1, 0) NERF_CT_LAYER(2, 0) NERF_CT_LAYER(3, 0) NERF_CT_LAYER(4, 0)
         NERF_CT_LAYER(5, 0) NERF_CT_LAYER(6, 0) NERF_CT_LAYER(7, 1)
-        default: epilogue_hidden<2, false, 0, true, NIT, 8>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 8); break;
+        default: epilogue_hidden<2, false, EXP, true, NIT, 8, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 8); break;
 #undef NERF_CT_LAYER
     }
 }
@@ -404,7 +409,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kMaxRing + 4));
     static_assert(8 * (2 * kMaxRing + 4) + 4 <= 256, "barrier region");
     long long t_wait0 = 0, t_wait1 = 0, t_begin = 0;
-    if (PROBE) t_begin = clock64();
+    if (PROBE || P.stats_out) t_begin = clock64();
+    // event trace (PROBE only): role 0 producer, 1 MMA issuer, 2 / 3 first warp of epilogue group X / Y;
+    // entry = tag << 56 | layer << 48 | group << 44 | chunk << 40 | cycles since kernel start
+    int n_ev = 0;
+    auto rec = [&](int role, long pair_no, int tag, int l, int g, int j) {
+        if (!PROBE || !P.trace_out || blockIdx.x != 0 || pair_no < 3 || pair_no > 4 || n_ev >= 1024) return;
+        P.trace_out[role * 1024 + n_ev++] = ((long long)tag << 56) | ((long long)l << 48) | ((long long)g << 44) |
+                                            ((long long)j << 40) | ((clock64() - t_begin) & 0xFFFFFFFFFFll);
+    };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
@@ -434,16 +447,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
         // ===================== producer: weight slots, L2 -> smem =====================
         if (lane == 0 && !(CFG::exp & 8)) {
             uint32_t it = 0;
-            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            long pair_no = 0;
+            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_no) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     // one slot = one K chunk with all its N halves (adjacent stages in the blob)
                     const int first = layer_first_stage(l), chunks = layer_chunks(l);
-                    const uint32_t bytes = layer_halves(l) * kStageBytes;
+                    // EXP bit5 (timing): the same copies and hand-offs, but only 1 KB per slot
+                    const uint32_t bytes = (CFG::exp & 32) ? 1024u : layer_halves(l) * kStageBytes;
                     for (int g = 0; g < 2; ++g) {
                         for (int j = 0; j < chunks; ++j, ++it) {
                             const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
                             long long t0 = PROBE ? clock64() : 0;
+                            rec(0, pair_no, 1, l, g, j);                 // waits for a free slot
                             umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                            rec(0, pair_no, 2, l, g, j);                 // slot free: copy issued
                             if (PROBE) t_wait0 += clock64() - t0;
                             umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
                             umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
@@ -454,17 +471,63 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                 }
             }
         }
+    } else if (warp == 1 && !PROBE && (CFG::exp & 128)) {      // EXP bit7 (A/B): measured 3.5 % SLOWER than the lone-lane issuer below
+        // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+        // The 32 lanes run the loop converged and wait on the barriers together; only the tcgen05
+        // instructions sit behind elect.sync.  With a lone lane inside `if (lane == 0)` the compiler
+        // wraps every tcgen05.mma in an elect/branch loop and moves each descriptor through R2UR; here
+        // the descriptors live in uniform registers and the issue sequence of a chunk is straight-line.
+        uint32_t it = 0, n_ready[2] = {0, 0};
+        for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            for (int l = 0; l < kNumMmaLayers; ++l) {
+                const int chunks = layer_chunks(l);
+                const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
+                for (int g = 0; g < 2; ++g) {
+                    umma::mbar_wait_warp(bar_a_ready + 8 * g, n_ready[g] & 1);
+                    ++n_ready[g];
+                    umma::tc_fence_after();
+                    const uint32_t d_base = tmem_base + g * 256;
+                    const uint32_t a_tile = sbase + kOffA + g * 65536;
+                    const uint32_t pe_tile = sbase + kOffPE + g * 16384;
+                    for (int j = 0; j < chunks; ++j) {
+                        uint32_t a_addr;
+                        if (l == 0) a_addr = pe_tile;
+                        else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
+                        else a_addr = a_tile + j * 16384;
+                        const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
+                        ++it;
+                        if (!(CFG::exp & 8)) umma::mbar_wait_warp(bar_w_full + 8 * slot, ph);
+                        umma::tc_fence_after();
+                        const uint32_t b_addr = sbase + kOffW + slot * kSlotBytes;
+                        if (umma::elect_one()) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
+                                                  umma::smem_desc_sw128(b_addr + kk * 32), idesc,
+                                                  (j > 0 || kk > 0) ? 1u : 0u);
+                            }
+                            umma::mma_commit(bar_w_empty + 8 * slot);
+                            if (j == chunks - 1) umma::mma_commit(bar_acc_full + 8 * g);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             uint32_t it = 0, n_ready[2] = {0, 0};
-            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            long pair_no = 0;
+            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_no) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     const int chunks = layer_chunks(l);
                     const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
                     for (int g = 0; g < 2; ++g) {
                         long long t0 = PROBE ? clock64() : 0;
+                        rec(1, pair_no, 1, l, g, 0);                     // waits for the A operand
                         umma::mbar_wait(bar_a_ready + 8 * g, n_ready[g] & 1);
+                        rec(1, pair_no, 2, l, g, 0);                     // A operand ready
                         if (PROBE) t_wait0 += clock64() - t0;
                         ++n_ready[g];
                         umma::tc_fence_after();
@@ -479,7 +542,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                             const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
                             ++it;
                             long long t1 = PROBE ? clock64() : 0;
+                            rec(1, pair_no, 3, l, g, j);                 // waits for the weight slot
                             if (!(CFG::exp & 8)) umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                            rec(1, pair_no, 4, l, g, j);                 // weight slot full
                             if (PROBE) t_wait1 += clock64() - t1;
                             umma::tc_fence_after();
                             // B = [N rows][64] K-major; the two 128-row halves are contiguous
@@ -491,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                                                   (j > 0 || kk > 0) ? 1u : 0u);
                             }
                             umma::mma_commit(bar_w_empty + 8 * slot);
+                            rec(1, pair_no, 5, l, g, j);                 // chunk's four MMAs issued
                         }
                         umma::mma_commit(bar_acc_full + 8 * g);
                     }
@@ -528,9 +594,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                     ++n_full[g];
                     umma::tc_fence_after();
                     if (l < 9) {
-                        const int c0 = cg * 64;
                         float sg = 0.f;
-                        epilogue_hidden_ct<4>(l, tacc, c0, a_row_addr, swz, sg, P.ct);
+                        switch (cg) {
+                            case 0: epilogue_hidden_ct<4, 0, 0>(l, tacc, 0, a_row_addr, swz, sg, P.ct); break;
+                            case 1: epilogue_hidden_ct<4, 0, 64>(l, tacc, 64, a_row_addr, swz, sg, P.ct); break;
+                            case 2: epilogue_hidden_ct<4, 0, 128>(l, tacc, 128, a_row_addr, swz, sg, P.ct); break;
+                            default: epilogue_hidden_ct<4, 0, 192>(l, tacc, 192, a_row_addr, swz, sg, P.ct); break;
+                        }
                         if (l == 7) sigma[g] = sg;
                         umma::fence_proxy_async_smem();
                         umma::tc_fence_before();
@@ -588,7 +658,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
             umma::st_shared_f32(bias_addr + gtid * 4, __ldg(tail + kTailBias + gtid));
             umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
         }
-        for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        long pair_no = 0;
+        const bool tracer = (ew & 7) == 0 && lane == 0;        // first warp of the group
+        for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_no) {
             const long grow_raw = (pair * 2 + g) * kTileM + row;
             const bool valid = grow_raw < P.M;
             const long grow = valid ? grow_raw : P.M - 1;
@@ -618,7 +690,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
 #pragma unroll 1
             for (int l = 0; l < kNumMmaLayers; ++l) {
                 long long t0 = PROBE ? clock64() : 0;
+                if (tracer) rec(2 + g, pair_no, 1, l, g, 0);           // waits for the accumulator
                 umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
+                if (tracer) rec(2 + g, pair_no, 2, l, g, 0);           // accumulator complete
                 if (PROBE) t_wait0 += clock64() - t0;
                 ++n_full;
                 umma::tc_fence_after();
@@ -626,7 +700,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                 if (l < 9) {
                     const int c0 = half * 128;
                     if (CT && !PROBE) {
-                        epilogue_hidden_ct<8>(l, tacc, c0, a_row_addr, swz, sigma, P.ct);
+                        if (CFG::exp & 64) epilogue_hidden_ct<8, CFG::exp & 7>(l, tacc, c0, a_row_addr, swz, sigma, P.ct);   // A/B: run-time column
+                        else if (half == 0) epilogue_hidden_ct<8, CFG::exp & 7, 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
+                        else epilogue_hidden_ct<8, CFG::exp & 7, 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
                     } else if (l == 7) {
                         epilogue_hidden<1, PROBE, CFG::exp, CT, 8, -1, SAVE>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row, P.ct, l, mw);
                     } else if (l == 8) {
@@ -639,6 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                     umma::fence_proxy_async_smem();
                     umma::tc_fence_before();
                     umma::mbar_arrive(bar_a_ready + 8 * g);
+                    if (tracer) rec(2 + g, pair_no, 3, l, g, 0);       // this warp's part of the A operand written
                     // stage the next hidden layer's bias (after l9 comes l1 of the next tile); both
                     // barriers fall into the time the group would wait for the tensor core anyway
                     float bnext = 0.f;
@@ -703,6 +780,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
     }
     umma::tc_fence_before();
     __syncthreads();
+    // every variant reports its cycle count when the debug entry passes a counter block: under the power
+    // cap a variant can be faster in milliseconds (higher clock) without being faster in cycles
+    if (!PROBE && P.stats_out && threadIdx.x == 0) P.stats_out[(long)blockIdx.x * 8 + 5] = clock64() - t_begin;
     if (warp == 1) {
         umma::tc_fence_after();
         umma::tmem_dealloc(tmem_base, 512);
@@ -1240,9 +1320,17 @@ static_assert(kPairOffBar == kOffBar, "same footprint as the single-CTA kernel")
 // MMA -> epilogue -> MMA chain must fit into about two layer times (2 x 2056 cycles); the 8-warp
 // epilogue alone takes ~3500 cycles, the crew about half of that.  Every crew warp arrives on the
 // leader's barrier itself (16 arrivals per CTA, no group barrier in the chain).
-template <bool WIDE>
+// TMAP: the half-chunks are fetched with tensor-map copies (cp.async.bulk.tensor ... cta_group::2) whose
+// completion is counted by the LEADER's slot barrier for both CTAs, so the peer's relay thread and the
+// leader's second wait per chunk disappear from the weight path.
+struct alignas(64) PairMaps {
+    CUtensorMap stage128;     // box = one stage: [128 rows][64 bf16]
+    CUtensorMap stage64;      // box = half a stage: [64 rows][64 bf16] (l10: 64 of its 128 output rows per CTA)
+};
+
+template <bool WIDE, bool TMAP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
+mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P, const __grid_constant__ PairMaps maps) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = umma::smem_u32(smem);
     if ((sbase & 1023u) != 0) __trap();
@@ -1256,6 +1344,14 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = umma::cluster_ctarank();
+    // event trace of cluster 0 (same format and roles as mlp_fwd_kernel's; role 0 = the leader's producer)
+    const long long t_trace0 = P.trace_out ? clock64() : 0;
+    int n_ev = 0;
+    auto rec = [&](int role, long quad_no, int tag, int l, int g, int j) {
+        if (!P.trace_out || blockIdx.x != 0 || quad_no < 3 || quad_no > 4 || n_ev >= 1024) return;
+        P.trace_out[role * 1024 + n_ev++] = ((long long)tag << 56) | ((long long)l << 48) | ((long long)g << 44) |
+                                            ((long long)j << 40) | ((clock64() - t_trace0) & 0xFFFFFFFFFFll);
+    };
     const long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
     const long n_quads = (n_tiles + 3) / 4;
@@ -1267,7 +1363,7 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
             umma::mbar_init(bar_w_peer + 8 * s, 1);
         }
         for (int g = 0; g < 2; ++g) {
-            umma::mbar_init(bar_a_ready + 8 * g, WIDE ? 2 * 2 * kEpiWarpsPerGroup : 2);
+            umma::mbar_init(bar_a_ready + 8 * g, (WIDE ? 2 : 1) * 2 * kEpiWarpsPerGroup);   // one arrive per warp and CTA
             umma::mbar_init(bar_acc_full + 8 * g, 1);
         }
         umma::fence_barrier_init();
@@ -1285,7 +1381,8 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
         // ===================== producer: this CTA's half of every weight chunk =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+            long quad_no = 0;
+            for (long quad = cluster_id; quad < n_quads; quad += n_clusters, ++quad_no) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     const int first = layer_first_stage(l), chunks = layer_chunks(l), halves = layer_halves(l);
                     // N = 256: stage (chunk, half = rank); N = 128 (l10): rows [64 rank, 64 rank + 64) of the stage
@@ -1293,7 +1390,21 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                     for (int g = 0; g < 2; ++g) {
                         for (int j = 0; j < chunks; ++j, ++it) {
                             const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
+                            rec(0, quad_no, 1, l, g, j);
                             umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                            rec(0, quad_no, 2, l, g, j);
+                            if (TMAP) {
+                                // both halves are counted by the leader's barrier (armed by the leader)
+                                if (rank == 0) umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, 2 * bytes);
+                                const uint32_t leader_full = umma::map_to_cta(bar_w_full + 8 * slot, 0);
+                                if (halves == 2)
+                                    umma::tma_load_2d_pair(sbase + kOffW + slot * kStageBytes, &maps.stage128, 0,
+                                                           (first + j * 2 + (int)rank) * kStageRows, leader_full);
+                                else
+                                    umma::tma_load_2d_pair(sbase + kOffW + slot * kStageBytes, &maps.stage64, 0,
+                                                           (first + j) * kStageRows + (int)rank * (kStageRows / 2), leader_full);
+                                continue;
+                            }
                             umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
                             const uint8_t* src = halves == 2
                                 ? P.blob + (size_t)(first + j * 2 + (int)rank) * kStageBytes
@@ -1305,7 +1416,9 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 1) {
+        if (lane == 0 && rank == 1 && TMAP) {
+            // nothing to relay: the peer's copies complete on the leader's barriers
+        } else if (lane == 0 && rank == 1) {
             // ===================== peer: relay slot arrivals to the leader =====================
             uint32_t it = 0;
             const uint32_t leader_w_peer = umma::map_to_cta(bar_w_peer, 0);
@@ -1323,17 +1436,21 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
             // ===================== leader: MMA issuer for the pair =====================
             uint32_t it = 0, n_ready[2] = {0, 0};
             long long tw_a = 0, tw_w = 0, tw_p = 0;
-            const long long t_begin = clock64();
+            const bool stats = P.stats_out != nullptr;      // the counters cost issue slots of the one thread that feeds the tensor core
+            const long long t_begin = stats ? clock64() : 0;
             constexpr uint32_t kIdescPair256 = umma::instr_desc_bf16(256, 256);
             constexpr uint32_t kIdescPair128 = umma::instr_desc_bf16(256, 128);
-            for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+            long quad_no = 0;
+            for (long quad = cluster_id; quad < n_quads; quad += n_clusters, ++quad_no) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     const int chunks = layer_chunks(l);
                     const uint32_t idesc = layer_halves(l) == 2 ? kIdescPair256 : kIdescPair128;
                     for (int g = 0; g < 2; ++g) {
-                        long long t0 = clock64();
+                        long long t0 = stats ? clock64() : 0;
+                        rec(1, quad_no, 1, l, g, 0);
                         umma::mbar_wait_cluster(bar_a_ready + 8 * g, n_ready[g] & 1);
-                        tw_a += clock64() - t0;
+                        rec(1, quad_no, 2, l, g, 0);
+                        if (stats) tw_a += clock64() - t0;
                         ++n_ready[g];
                         umma::tc_fence_after();
                         const uint32_t d_base = tmem_base + g * 256;
@@ -1346,12 +1463,14 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                             else a_addr = a_tile + j * 16384;
                             const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
                             ++it;
-                            long long t1 = clock64();
-                            umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                            long long t2 = clock64();
-                            umma::mbar_wait_cluster(bar_w_peer + 8 * slot, ph);
-                            tw_w += t2 - t1;
-                            tw_p += clock64() - t2;
+                            long long t1 = stats ? clock64() : 0;
+                            rec(1, quad_no, 3, l, g, j);
+                            if (TMAP) umma::mbar_wait_cluster(bar_w_full + 8 * slot, ph);
+                            else umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                            long long t2 = stats ? clock64() : 0;
+                            if (!TMAP) umma::mbar_wait_cluster(bar_w_peer + 8 * slot, ph);
+                            if (stats) { tw_w += t2 - t1; tw_p += clock64() - t2; }
+                            rec(1, quad_no, 4, l, g, j);
                             umma::tc_fence_after();
                             const uint32_t b_addr = sbase + kOffW + slot * kStageBytes;
 #pragma unroll
@@ -1361,12 +1480,13 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                                                        (j > 0 || kk > 0) ? 1u : 0u);
                             }
                             umma::mma_commit_pair(bar_w_empty + 8 * slot);
+                            rec(1, quad_no, 5, l, g, j);
                         }
                         umma::mma_commit_pair(bar_acc_full + 8 * g);
                     }
                 }
             }
-            if (P.stats_out) {
+            if (stats) {
                 long long* o = P.stats_out + (long)blockIdx.x * 8;
                 o[1] = tw_a; o[2] = tw_w; o[6] = tw_p; o[5] = clock64() - t_begin;
             }
@@ -1398,21 +1518,31 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
         float sigma[2] = {0.f, 0.f};
         uint32_t n_full[2] = {0, 0};
         if (cluster_id < n_quads) { in_stage(0, cluster_id); in_stage(1, cluster_id); }
-        for (long quad_idx = cluster_id; quad_idx < n_quads; quad_idx += n_clusters) {
+        long quad_no = 0;
+        const bool tracer = warp == 2 && lane == 0;
+        for (long quad_idx = cluster_id; quad_idx < n_quads; quad_idx += n_clusters, ++quad_no) {
 #pragma unroll 1
             for (int l = 0; l < kNumMmaLayers; ++l) {
 #pragma unroll 1
                 for (int g = 0; g < 2; ++g) {
                     const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
                     const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
+                    if (tracer) rec(2 + g, quad_no, 1, l, g, 0);
                     umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full[g] & 1);
+                    if (tracer) rec(2 + g, quad_no, 2, l, g, 0);
                     ++n_full[g];
                     umma::tc_fence_after();
                     if (l < 9) {
                         float sg = 0.f;
-                        epilogue_hidden_ct<4>(l, tacc, cg * 64, a_row_addr, swz, sg, P.ct);
+                        switch (cg) {
+                            case 0: epilogue_hidden_ct<4, 0, 0>(l, tacc, 0, a_row_addr, swz, sg, P.ct); break;
+                            case 1: epilogue_hidden_ct<4, 0, 64>(l, tacc, 64, a_row_addr, swz, sg, P.ct); break;
+                            case 2: epilogue_hidden_ct<4, 0, 128>(l, tacc, 128, a_row_addr, swz, sg, P.ct); break;
+                            default: epilogue_hidden_ct<4, 0, 192>(l, tacc, 192, a_row_addr, swz, sg, P.ct); break;
+                        }
                         if (l == 7) sigma[g] = sg;
                         signal_a_ready(g);
+                        if (tracer) rec(2 + g, quad_no, 3, l, g, 0);
                     } else {
                         const long grow_raw = (quad_idx * 4 + rank * 2 + g) * kTileM + row;
                         const bool valid = grow_raw < P.M;
@@ -1463,11 +1593,13 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
         auto signal_a_ready = [&]() {
             umma::fence_proxy_async_smem();
             umma::tc_fence_before();
-            umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
-            if (gtid == 0) umma::mbar_arrive_remote(leader_a_ready);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive_remote(leader_a_ready);
         };
         uint32_t n_full = 0;
-        for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+        long quad_no = 0;
+        const bool tracer = (ew & 7) == 0 && lane == 0;
+        for (long quad = cluster_id; quad < n_quads; quad += n_clusters, ++quad_no) {
             const long grow_raw = (quad * 4 + rank * 2 + g) * kTileM + row;
             const bool valid = grow_raw < P.M;
             const long grow = valid ? grow_raw : P.M - 1;
@@ -1477,13 +1609,16 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
             float sigma = 0.f;
 #pragma unroll 1
             for (int l = 0; l < kNumMmaLayers; ++l) {
+                if (tracer) rec(2 + g, quad_no, 1, l, g, 0);
                 umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
+                if (tracer) rec(2 + g, quad_no, 2, l, g, 0);
                 ++n_full;
                 umma::tc_fence_after();
                 if (l < 9) {
-                    const int c0 = half * 128;
-                    epilogue_hidden_ct<8>(l, tacc, c0, a_row_addr, swz, sigma, P.ct);
+                    if (half == 0) epilogue_hidden_ct<8, 0, 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
+                    else epilogue_hidden_ct<8, 0, 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
                     signal_a_ready();
+                    if (tracer) rec(2 + g, quad_no, 3, l, g, 0);
                 } else {
                     float rgb[3];
                     const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
@@ -1536,13 +1671,17 @@ FwdKernel fwd_variant(int v) {
         case 12: return mlp_fwd_kernel<false, Cfg<kRing, false, 16>, true>;   // training forward without the record copies (timing)
         case 13: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true, true>;   // no weight streaming + 16-warp crew (timing)
         case 14: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true>;         // no weight streaming, host tail (timing)
+        case 15: return mlp_fwd_kernel<false, Cfg<kRing, false, 32>, false, true>;        // weight copies cut to 1 KB per slot: the hand-off latencies without the bytes (timing)
+        case 16: return mlp_fwd_kernel<false, Cfg<kRing, false, 64>, false, true>;        // host tail with run-time bias columns (LDC instead of LDCU: A/B)
+        case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
+        case 18: return mlp_fwd_kernel<false, Cfg<kRing, false, 4>, false, true>;         // host tail, no TMEM loads (timing)
         default: return nullptr;
     }
 }
 
 int launch_fwd(const FwdParams& P, int variant, void* stream) {
     static int sm_count = 0;
-    static bool configured[15] = {};
+    static bool configured[19] = {};
     FwdKernel k = fwd_variant(variant);
     if (!k) return nerf::arg_error("nerf_mlp_fwd: variant");
     if (sm_count == 0) {
@@ -1623,7 +1762,43 @@ int launch_fwd_tr(const FwdParams& P, void* stream) {
     return nerf::check_launch("nerf_mlp_fwd (mixed orientation)");
 }
 
-int launch_fwd_pair(const FwdParams& P, void* stream, bool wide = false) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_pair_maps(const uint8_t* blob, PairMaps& maps) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+            nerf::set_last_error("nerf_mlp_fwd setup: cuTensorMapEncodeTiled not available");
+            return (int)cudaErrorNotSupported;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    // the weight stages as one [72 * 128 rows][64 bf16] array of 128-byte rows; the stage images are
+    // already swizzled, so the copy moves raw bytes (no tensor-map swizzle)
+    const cuuint64_t dims[2] = {(cuuint64_t)kStageCols, (cuuint64_t)kNumStages * kStageRows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kStageCols * 2};
+    const cuuint32_t elem[2] = {1, 1};
+    for (int i = 0; i < 2; ++i) {
+        const cuuint32_t box[2] = {(cuuint32_t)kStageCols, (cuuint32_t)(i == 0 ? kStageRows : kStageRows / 2)};
+        CUresult r = encode(i == 0 ? &maps.stage128 : &maps.stage64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)blob, dims,
+                            strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            nerf::set_last_error("nerf_mlp_fwd setup: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return (int)cudaErrorInvalidValue;
+        }
+    }
+    return 0;
+}
+
+// mode: 0 8-warp groups, 1 16-warp crew, 2 8-warp groups + tensor-map weight copies, 3 crew + tensor-map copies
+int launch_fwd_pair(const FwdParams& P, void* stream, int mode = 0) {
     static int sm_count = 0;
     static bool configured = false;
     if (sm_count == 0) {
@@ -1635,20 +1810,33 @@ int launch_fwd_pair(const FwdParams& P, void* stream, bool wide = false) {
         }
     }
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) {
             nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
             return (int)e;
         }
         configured = true;
     }
+    PairMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (mode >= 2) {
+        int rc = make_pair_maps(P.blob, maps);
+        if (rc) return rc;
+    }
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
     const long n_quads = (n_tiles + 3) / 4;
     const long clusters = n_quads < sm_count / 2 ? n_quads : sm_count / 2;
-    if (wide) mlp_fwd_pair_kernel<true><<<(unsigned)(2 * clusters), kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
-    else mlp_fwd_pair_kernel<false><<<(unsigned)(2 * clusters), kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    const unsigned grid = (unsigned)(2 * clusters);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+        case 0: mlp_fwd_pair_kernel<false, false><<<grid, kThreads, kSmemBytes, st>>>(P, maps); break;
+        case 1: mlp_fwd_pair_kernel<true, false><<<grid, kThreads, kSmemBytes, st>>>(P, maps); break;
+        case 2: mlp_fwd_pair_kernel<false, true><<<grid, kThreads, kSmemBytes, st>>>(P, maps); break;
+        default: mlp_fwd_pair_kernel<true, true><<<grid, kThreads, kSmemBytes, st>>>(P, maps); break;
+    }
     return nerf::check_launch("nerf_mlp_fwd (CTA pairs)");
 }
 
@@ -1666,7 +1854,7 @@ int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0,
     P.blob = (const uint8_t*)packed;
     P.in_mode = in_mode; P.in0 = in0; P.in1 = in1; P.in_stride = in_stride;
     P.M = M; P.S = S < 1 ? 1 : S; P.vterm = vterm; P.vterm_div = vterm_div; P.raw_out = raw_out;
-    P.probe_out = nullptr; P.probe_layer = -1; P.stats_out = nullptr; P.act_save = nullptr;
+    P.probe_out = nullptr; P.probe_layer = -1; P.stats_out = nullptr; P.trace_out = nullptr; P.act_save = nullptr;
     return 0;
 }
 
@@ -1712,7 +1900,9 @@ extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail,
     memcpy(&P.ct, host_tail, sizeof(ConstTail));
     if (g_use_pairs == 3) return launch_fwd_tr(P, stream);
     if (g_use_pairs == 4) return launch_fwd_ts(P, stream);
-    if (g_use_pairs == 5) return launch_fwd_pair(P, stream, true);
+    if (g_use_pairs == 5) return launch_fwd_pair(P, stream, 1);
+    if (g_use_pairs == 6) return launch_fwd_pair(P, stream, 2);
+    if (g_use_pairs == 7) return launch_fwd_pair(P, stream, 3);
     return g_use_pairs == 1 ? launch_fwd_pair(P, stream) : launch_fwd(P, g_use_pairs == 2 ? 10 : 9, stream);
 }
 
@@ -1748,6 +1938,11 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
     if (rc) return rc;
     if (M == 0) return 0;
     P.stats_out = stats_out;
+    if (variant >= 1000) {     // event trace behind the 148 x 8 counters (probe kernel, or the CTA-pair kernels 1100..1103)
+        P.trace_out = stats_out + 148 * 8;
+        variant -= 1000;
+        if (variant >= 100) P.stats_out = nullptr;      // the pair kernels trace without the wait counters
+    }
     if (variant == 100) {      // CTA-pair kernel (needs a host tail: the caller's tail is read from the blob here)
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
@@ -1756,14 +1951,19 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
     if (variant == 101) {      // CTA pairs with the 16-warp crew
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
-        return launch_fwd_pair(P, stream, true);
+        return launch_fwd_pair(P, stream, 1);
+    }
+    if (variant == 102 || variant == 103) {      // CTA pairs with tensor-map weight copies (103: + crew)
+        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return (int)e;
+        return launch_fwd_pair(P, stream, variant - 100);
     }
     if (variant == 200) {      // TS kernel
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
         return launch_fwd_ts(P, stream);
     }
-    if (variant == 9 || variant == 10 || variant == 13 || variant == 14) {   // host-tail kernels
+    if (variant == 9 || variant == 10 || (variant >= 13 && variant <= 18)) {   // host-tail kernels
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
     }

@@ -111,6 +111,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
         : "memory");
 }
 
+// Tensor-map copy of one 2-D box, global -> shared, issued inside a CTA pair: the complete_tx goes to
+// the mbarrier at cluster address `bar_cluster`, which may live in the PEER CTA (cta_group::2) -- both
+// CTAs of a pair can report "my half landed" straight to the leader's barrier.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* tmap, int c0, int c1,
+                                                 uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster)
+        : "memory");
+}
+
 // pull a contiguous global range into L2 (no shared-memory destination, no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");

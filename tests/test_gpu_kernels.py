@@ -303,6 +303,10 @@ def test_field_kernel_variants_agree(rows, S):
         ts = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
         K.use_pairs(5)
         pairs_crew = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+        K.use_pairs(6)
+        pairs_tmap = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+        K.use_pairs(7)
+        pairs_tmap_crew = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
         torch.cuda.synchronize()
     finally:
         K.use_pairs(old)
@@ -310,6 +314,8 @@ def test_field_kernel_variants_agree(rows, S):
     print("TS vs base max abs diff", (ts - base).abs().max().item())
     print("pairs + crew vs base max abs diff", (pairs_crew - base).abs().max().item())
     assert (pairs_crew - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
+    assert torch.equal(pairs_tmap, base), (pairs_tmap - base).abs().max().item()
+    assert torch.equal(pairs_tmap_crew, pairs_crew), (pairs_tmap_crew - pairs_crew).abs().max().item()
     assert (ts - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
     assert (mixed - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
     assert torch.equal(single, base), (single - base).abs().max().item()

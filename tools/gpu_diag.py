@@ -83,7 +83,9 @@ def timing():
         ref = None
         for tag, tail, mode in (("smem bias", None, 0), ("host tail, single CTA", ht, 0), ("host tail, CTA pairs", ht, 1),
                                 ("host tail, single CTA, 16-warp crew", ht, 2), ("host tail, mixed orientation", ht, 3), ("host tail, TS (activations in TMEM)", ht, 4),
-                                ("host tail, CTA pairs + 16-warp crew", ht, 5)):
+                                ("host tail, CTA pairs + 16-warp crew", ht, 5),
+                                ("host tail, CTA pairs, tensor-map weight copies", ht, 6),
+                                ("host tail, CTA pairs + crew, tensor-map weight copies", ht, 7)):
             K.use_pairs(mode)
             for _ in range(3):
                 raw = K.mlp_fwd(packed, K.IN_RAYS, rays, z, n_rays * S, S, vt, S, host_tail=tail)
@@ -105,7 +107,41 @@ def timing():
                   f"({n_rays * S / ms / 1e3:.2f} M samples/s)")
 
 
-def pipeline_stats(variants=(1, 9, 14, 100, 101, 200)):
+def ab(variants, rounds=6):
+    """Interleaved A/B timing of debug-entry variants (the power-capped chip drifts by several percent within
+    a process, so variants are timed round-robin and averaged)."""
+    from cv_nerf_b200 import _lib
+    lib = _lib.load()
+    p, packed = packed_model()
+    n_rays, S = 160000, 192
+    rays = torch.zeros(n_rays, 11, device=DEV)
+    rays[:, 0:3] = torch.randn(n_rays, 3, device=DEV) * .3
+    rays[:, 3:6] = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV), dim=-1)
+    rays[:, 6], rays[:, 7] = 2., 6.
+    rays[:, 8:11] = rays[:, 3:6]
+    z = K.sample_coarse(rays, S)
+    vt = K.viewdir_term(packed, rays)
+    raw = torch.empty(n_rays * S, 4, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    tot = {v: 0. for v in variants}
+    for rnd in range(rounds + 1):
+        for v in variants:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                rc = lib.nerf_mlp_fwd_stats(packed.data_ptr(), rays.data_ptr(), z.data_ptr(), n_rays * S, S,
+                                            vt.data_ptr(), raw.data_ptr(), v, 0, st)
+                assert rc == 0, lib.nerf_b200_last_error()
+            e1.record()
+            torch.cuda.synchronize()
+            if rnd > 0:
+                tot[v] += e0.elapsed_time(e1) / 3
+    for v in variants:
+        ms = tot[v] / rounds
+        print(f"variant {v}: {ms:.3f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s (mean of {rounds} interleaved rounds)")
+
+
+def pipeline_stats(variants=(9, 16, 15, 14, 1, 3)):
     """Per-role wait-cycle breakdown of the field kernel (debug entry nerf_mlp_fwd_stats)."""
     from cv_nerf_b200 import _lib
     lib = _lib.load()
@@ -123,9 +159,12 @@ def pipeline_stats(variants=(1, 9, 14, 100, 101, 200)):
              4: "EXP no A-tile stores", 5: "EXP no bias loads", 6: "EXP no TMEM loads", 7: "EXP none of the three",
              9: "host tail (production inference kernel); no counters", 10: "host tail + 16-warp crew; no counters",
              13: "EXP no weight streaming + 16-warp crew; no counters", 14: "EXP no weight streaming, host tail; no counters",
+             15: "EXP weight copies cut to 1 KB per slot (hand-offs without the bytes); no counters", 16: "EXP no bias loads + no weight streaming; no counters",
+             17: "EXP host tail, no A-tile stores; no counters", 18: "EXP host tail, no TMEM loads; no counters",
              11: "EXP no weight streaming (upper bound if weight slots were always ready)",
              100: "CTA pairs (cta_group::2); leader CTAs only; [6] = wait for the peer's half-chunk",
              101: "CTA pairs + 16-warp crew; leader CTAs only",
+             102: "CTA pairs, tensor-map weight copies", 103: "CTA pairs + crew, tensor-map weight copies",
              200: "TS kernel (activations in TMEM); producer(empty) = MMA thread waits for its own commit (queue drain), epiX = crew wait for acc, epiY = crew hidden-epilogue busy, w_peer = wait PE"}
     st = torch.cuda.current_stream().cuda_stream
     for v in variants:
@@ -142,7 +181,8 @@ def pipeline_stats(variants=(1, 9, 14, 100, 101, 200)):
         rows = stats[stats[:, 5] > 0].double()
         s = rows.mean(0).cpu() if rows.shape[0] else torch.zeros(8, dtype=torch.float64)
         tot = max(s[5].item(), 1.)
-        print(f"variant {v} {names.get(v, '')}: {ms:.2f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s | "
+        print(f"variant {v} {names.get(v, '')}: {ms:.2f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s  "
+              f"clock {tot / ms / 1e3:.0f} MHz | "
               f"cycles/CTA {tot:.3e}; wait fractions: producer(empty) {s[0] / tot:.2f}  mma(a_ready) {s[1] / tot:.2f}  "
               f"mma(w_full) {s[2] / tot:.2f}  epiX(acc) {s[3] / tot:.2f}  epiY(acc) {s[4] / tot:.2f}  mma(w_peer) {s[6] / tot:.2f}  [7] {s[7] / tot:.2f}")
 
@@ -152,7 +192,11 @@ if __name__ == "__main__":
     ap.add_argument("--rows", type=int, default=1000)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--stats", action="store_true")
+    ap.add_argument("--ab", type=str, default="", help="comma-separated debug-entry variants to time round-robin")
     a = ap.parse_args()
+    if a.ab:
+        ab([int(x) for x in a.ab.split(",")])
+        sys.exit(0)
     if a.stats:
         pipeline_stats()
         sys.exit(0)

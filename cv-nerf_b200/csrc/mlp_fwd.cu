@@ -58,12 +58,21 @@ constexpr uint32_t kIdescN128 = umma::instr_desc_bf16(128, 128);
 // EXP (timing experiments, wrong numerics): bit0 skip the A-tile stores, bit1 skip the bias loads,
 // bit2 skip the TMEM loads, bit3 no weight streaming at all (the MMAs read whatever the ring holds:
 // the speed the kernel would have if weight slots were always ready).
-template <int RING, bool ALIAS, int EXP = 0>
+// PEA ("PE in the A tile", inference): the positional-encoding tile does not get shared memory of its
+// own.  It is written into block 0 of the sub-tile's A tile for l1, and ENCODED AGAIN into the same
+// block for l6 once the MMAs that read h5's block 0 have completed (l6 accumulates its four h5 chunks
+// first and the PE chunk last; the group's re-encoding runs under the other sub-tile's MMAs).  The
+// 32 KB this frees hold a THIRD weight slot: measured with the timing-only ALIAS layout, 3 x 32 KB
+// instead of 2 x 32 KB takes 7.4 % off the kernel's cycles (the refill of a slot takes ~1000-1400
+// cycles after its MMAs complete; a slot is consumed in 640).
+template <int RING, bool ALIAS, int EXP = 0, bool PEA = false>
 struct Cfg {
     static constexpr int ring = RING;
     static constexpr int exp = EXP;
+    static constexpr bool pea = PEA;
     static constexpr uint32_t off_pe = ALIAS ? 0u : kOffPE;
-    static constexpr uint32_t off_w = ALIAS ? kOffPE : kOffW;
+    static constexpr uint32_t off_w = (ALIAS || PEA) ? kOffPE : kOffW;
+    static_assert(!(ALIAS && PEA), "ALIAS is the timing-only precursor of PEA");
     static_assert(off_w + RING * kSlotBytes <= kOffBar, "ring does not fit");
 };
 
@@ -393,6 +402,8 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
 template <bool PROBE, class CFG, bool SAVE = false, bool CT = false, bool WIDE = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
     static_assert(!WIDE || (CT && !SAVE && !PROBE), "WIDE is an inference-only variant");
+    constexpr bool kPEA = CFG::pea;
+    static_assert(!kPEA || (!SAVE && !WIDE && !PROBE), "PEA is implemented for the 8-warp inference epilogue");
     constexpr bool kStageBias = !CT;          // per-layer bias staged in shared memory
     constexpr bool kGroupSync = !CT || SAVE;  // group barriers around the staging / the record copies
     constexpr int kRing = CFG::ring;
@@ -406,8 +417,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
     const uint32_t bar_w_empty = bar_w_full + 8 * kMaxRing;   // [kMaxRing]
     const uint32_t bar_a_ready = bar_w_empty + 8 * kMaxRing;  // [2]
     const uint32_t bar_acc_full = bar_a_ready + 16;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kMaxRing + 4));
-    static_assert(8 * (2 * kMaxRing + 4) + 4 <= 256, "barrier region");
+    const uint32_t bar_pe_free = bar_acc_full + 16;           // [2]  PEA: l6's MMAs on A block 0 (h5) completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kMaxRing + 6));
+    static_assert(8 * (2 * kMaxRing + 6) + 4 <= 256, "barrier region");
     long long t_wait0 = 0, t_wait1 = 0, t_begin = 0;
     if (PROBE || P.stats_out) t_begin = clock64();
     // event trace (PROBE only): role 0 producer, 1 MMA issuer, 2 / 3 first warp of epilogue group X / Y;
@@ -431,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
         for (int g = 0; g < 2; ++g) {
             umma::mbar_init(bar_a_ready + 8 * g, (WIDE ? 2 : 1) * kEpiWarpsPerGroup * 32);
             umma::mbar_init(bar_acc_full + 8 * g, 1);
+            umma::mbar_init(bar_pe_free + 8 * g, 1);
         }
         umma::fence_barrier_init();
     }
@@ -454,19 +467,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                     const int first = layer_first_stage(l), chunks = layer_chunks(l);
                     // EXP bit5 (timing): the same copies and hand-offs, but only 1 KB per slot
                     const uint32_t bytes = (CFG::exp & 32) ? 1024u : layer_halves(l) * kStageBytes;
-                    for (int g = 0; g < 2; ++g) {
-                        for (int j = 0; j < chunks; ++j, ++it) {
-                            const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-                            long long t0 = PROBE ? clock64() : 0;
-                            rec(0, pair_no, 1, l, g, j);                 // waits for a free slot
-                            umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
-                            rec(0, pair_no, 2, l, g, j);                 // slot free: copy issued
-                            if (PROBE) t_wait0 += clock64() - t0;
-                            umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
-                            umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
-                                           P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes,
-                                           bar_w_full + 8 * slot);
-                        }
+                    auto fetch = [&](int g, int j) {
+                        const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
+                        ++it;
+                        long long t0 = PROBE ? clock64() : 0;
+                        rec(0, pair_no, 1, l, g, j);                 // waits for a free slot
+                        umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                        rec(0, pair_no, 2, l, g, j);                 // slot free: copy issued
+                        if (PROBE) t_wait0 += clock64() - t0;
+                        umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
+                        umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
+                                       P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes,
+                                       bar_w_full + 8 * slot);
+                    };
+                    if (kPEA && l == 5) {      // the MMA warp's order for l6: h5 chunks of X, of Y, PE chunk of X, of Y
+                        for (int g = 0; g < 2; ++g)
+                            for (int j = 1; j < chunks; ++j) fetch(g, j);
+                        for (int g = 0; g < 2; ++g) fetch(g, 0);
+                    } else {
+                        // l6 accumulates its PE chunk (chunk 0) last in every variant of this kernel, so that
+                        // they all sum in the same order
+                        for (int g = 0; g < 2; ++g)
+                            for (int jj = 0; jj < chunks; ++jj) fetch(g, l == 5 ? (jj + 1) % chunks : jj);
                     }
                 }
             }
@@ -489,7 +511,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                     const uint32_t d_base = tmem_base + g * 256;
                     const uint32_t a_tile = sbase + kOffA + g * 65536;
                     const uint32_t pe_tile = sbase + kOffPE + g * 16384;
-                    for (int j = 0; j < chunks; ++j) {
+                    for (int jj = 0; jj < chunks; ++jj) {
+                        const int j = l == 5 ? (jj + 1) % chunks : jj;          // l6: PE chunk last
                         uint32_t a_addr;
                         if (l == 0) a_addr = pe_tile;
                         else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
@@ -504,10 +527,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                             for (int kk = 0; kk < 4; ++kk) {
                                 umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
                                                   umma::smem_desc_sw128(b_addr + kk * 32), idesc,
-                                                  (j > 0 || kk > 0) ? 1u : 0u);
+                                                  (jj > 0 || kk > 0) ? 1u : 0u);
                             }
                             umma::mma_commit(bar_w_empty + 8 * slot);
-                            if (j == chunks - 1) umma::mma_commit(bar_acc_full + 8 * g);
+                            if (jj == chunks - 1) umma::mma_commit(bar_acc_full + 8 * g);
                         }
                         __syncwarp();
                     }
@@ -523,7 +546,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     const int chunks = layer_chunks(l);
                     const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
-                    for (int g = 0; g < 2; ++g) {
+                    // waits until sub-tile g's A operand (or its re-encoded PE block) is written
+                    auto wait_a = [&](int g) {
                         long long t0 = PROBE ? clock64() : 0;
                         rec(1, pair_no, 1, l, g, 0);                     // waits for the A operand
                         umma::mbar_wait(bar_a_ready + 8 * g, n_ready[g] & 1);
@@ -531,32 +555,59 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                         if (PROBE) t_wait0 += clock64() - t0;
                         ++n_ready[g];
                         umma::tc_fence_after();
+                    };
+                    // one K chunk: weight slot, four MMAs (the first one overwrites D when `fresh`), slot release
+                    auto chunk = [&](int g, int j, uint32_t a_addr, bool fresh) {
+                        const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
+                        ++it;
+                        long long t1 = PROBE ? clock64() : 0;
+                        rec(1, pair_no, 3, l, g, j);                 // waits for the weight slot
+                        if (!(CFG::exp & 8)) umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                        rec(1, pair_no, 4, l, g, j);                 // weight slot full
+                        if (PROBE) t_wait1 += clock64() - t1;
+                        umma::tc_fence_after();
+                        // B = [N rows][64] K-major; the two 128-row halves are contiguous
+                        const uint32_t b_addr = sbase + kOffW + slot * kSlotBytes;
                         const uint32_t d_base = tmem_base + g * 256;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
+                                              umma::smem_desc_sw128(b_addr + kk * 32), idesc,
+                                              (!fresh || kk > 0) ? 1u : 0u);
+                        }
+                        umma::mma_commit(bar_w_empty + 8 * slot);
+                        rec(1, pair_no, 5, l, g, j);                 // chunk's four MMAs issued
+                    };
+                    if (kPEA && l == 5) {
+                        // l6 with the PE block re-encoded in place: h5 chunks first; block 0 is released to
+                        // the epilogue group as soon as its MMAs are done; the PE chunks of both sub-tiles
+                        // follow the h5 chunks of both, so the re-encoding of X runs under Y's MMAs
+                        for (int g = 0; g < 2; ++g) {
+                            wait_a(g);
+                            const uint32_t a_tile = sbase + kOffA + g * 65536;
+                            for (int j = 1; j < chunks; ++j) {
+                                chunk(g, j, a_tile + (j - 1) * 16384, j == 1);
+                                if (j == 1) umma::mma_commit(bar_pe_free + 8 * g);
+                            }
+                        }
+                        for (int g = 0; g < 2; ++g) {
+                            wait_a(g);
+                            chunk(g, 0, sbase + kOffA + g * 65536, false);
+                            umma::mma_commit(bar_acc_full + 8 * g);
+                        }
+                        continue;
+                    }
+                    for (int g = 0; g < 2; ++g) {
+                        wait_a(g);
                         const uint32_t a_tile = sbase + kOffA + g * 65536;
-                        const uint32_t pe_tile = sbase + kOffPE + g * 16384;
-                        for (int j = 0; j < chunks; ++j) {
+                        const uint32_t pe_tile = kPEA ? a_tile : sbase + kOffPE + g * 16384;
+                        for (int jj = 0; jj < chunks; ++jj) {
+                            const int j = l == 5 ? (jj + 1) % chunks : jj;      // l6: PE chunk last
                             uint32_t a_addr;
                             if (l == 0) a_addr = pe_tile;
                             else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
                             else a_addr = a_tile + j * 16384;
-                            const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-                            ++it;
-                            long long t1 = PROBE ? clock64() : 0;
-                            rec(1, pair_no, 3, l, g, j);                 // waits for the weight slot
-                            if (!(CFG::exp & 8)) umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                            rec(1, pair_no, 4, l, g, j);                 // weight slot full
-                            if (PROBE) t_wait1 += clock64() - t1;
-                            umma::tc_fence_after();
-                            // B = [N rows][64] K-major; the two 128-row halves are contiguous
-                            const uint32_t b_addr = sbase + kOffW + slot * kSlotBytes;
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
-                                                  umma::smem_desc_sw128(b_addr + kk * 32), idesc,
-                                                  (j > 0 || kk > 0) ? 1u : 0u);
-                            }
-                            umma::mma_commit(bar_w_empty + 8 * slot);
-                            rec(1, pair_no, 5, l, g, j);                 // chunk's four MMAs issued
+                            chunk(g, j, a_addr, jj == 0);
                         }
                         umma::mma_commit(bar_acc_full + 8 * g);
                     }
@@ -647,10 +698,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
         const uint32_t bias_addr = sbase + kOffBias + g * 1024;
         const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
         const uint32_t swz = (uint32_t)(row & 7) << 4;
-        uint8_t* pe_tile = smem + kOffPE + g * 16384;
+        // PEA: the PE tile is block 0 of the group's A tile
+        uint8_t* pe_tile = kPEA ? smem + kOffA + g * 65536 : smem + kOffPE + g * 16384;
         // FP32 hand-over slot between the two threads of a row, inside the row's own PE line
-        // (free between l6's MMA and the next tile's encoding)
+        // (free between l6's MMA and the next tile's encoding; PEA: block 0 of h9, dead after l10's MMAs)
         float4* xchg = reinterpret_cast<float4*>(pe_tile + row * 128);
+        uint32_t n_pe_free = 0;
         const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
         const float* tail = reinterpret_cast<const float*>(P.blob + kWeightBytes);
         uint32_t n_full = 0;
@@ -732,6 +785,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                     }
                     if (kStageBias) umma::st_shared_f32(bias_addr + gtid * 4, bnext);
                     if (kGroupSync) umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+                    if (kPEA && l == 4) {
+                        // l6's MMAs on block 0 (h5) have completed: encode the points again into it
+                        umma::mbar_wait_warp(bar_pe_free + 8 * g, n_pe_free & 1);
+                        ++n_pe_free;
+                        if (half == 0) input_stage<0>(P, grow, pe_tile, row);
+                        else input_stage<1>(P, grow, pe_tile, row);
+                        umma::fence_proxy_async_smem();
+                        umma::mbar_arrive(bar_a_ready + 8 * g);
+                    }
                 } else {
                     float rgb[3];
                     const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
@@ -1656,7 +1718,7 @@ using FwdKernel = void (*)(const FwdParams);   // (__grid_constant__ does not ch
 // 2, 3 = pipeline-timing experiments (probe kernels with other ring depths)
 FwdKernel fwd_variant(int v) {
     switch (v) {
-        case 0: return mlp_fwd_kernel<false, Cfg<kRing, false>>;
+        case 0: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>>;                    // PE in the A tile, three weight slots
         case 1: return mlp_fwd_kernel<true, Cfg<kRing, false>>;
         case 2: return mlp_fwd_kernel<true, Cfg<1, false>>;
         case 3: return mlp_fwd_kernel<true, Cfg<3, true>>;
@@ -1665,16 +1727,16 @@ FwdKernel fwd_variant(int v) {
         case 6: return mlp_fwd_kernel<true, Cfg<kRing, false, 4>>;
         case 7: return mlp_fwd_kernel<true, Cfg<kRing, false, 7>>;
         case 8: return mlp_fwd_kernel<false, Cfg<kRing, false>, true>;   // training: saves activations
-        case 9: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;   // inference with the host tail
+        case 9: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>, false, true>;      // inference with the host tail (production)
         case 10: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true, true>;   // + 16-warp epilogue crew
         case 11: return mlp_fwd_kernel<true, Cfg<kRing, false, 8>>;
         case 12: return mlp_fwd_kernel<false, Cfg<kRing, false, 16>, true>;   // training forward without the record copies (timing)
         case 13: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true, true>;   // no weight streaming + 16-warp crew (timing)
         case 14: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true>;         // no weight streaming, host tail (timing)
         case 15: return mlp_fwd_kernel<false, Cfg<kRing, false, 32>, false, true>;        // weight copies cut to 1 KB per slot: the hand-off latencies without the bytes (timing)
-        case 16: return mlp_fwd_kernel<false, Cfg<kRing, false, 64>, false, true>;        // host tail with run-time bias columns (LDC instead of LDCU: A/B)
+        case 16: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;            // host tail, round-1 layout: PE tiles + two weight slots (A/B)
         case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
-        case 18: return mlp_fwd_kernel<false, Cfg<kRing, false, 4>, false, true>;         // host tail, no TMEM loads (timing)
+        case 18: return mlp_fwd_kernel<false, Cfg<3, true>, false, true>;                 // host tail, 3 x 32 KB ring with the PE tiles aliased (timing only)
         default: return nullptr;
     }
 }

@@ -290,6 +290,13 @@ def test_field_kernel_variants_agree(rows, S):
     dirs = torch.nn.functional.normalize(torch.randn(n_rays, 3), dim=-1).to(DEV)
     vt = K.viewdir_term(packed, dirs)
     base = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S)
+    # the probe build keeps the round-1 layout (PE tiles of their own, two weight slots) with the same
+    # summation order: bit-identical raw values pin the in-place PE re-encoding of the production layout
+    probe_raw, _ = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, probe_layer=3)
+    act = torch.zeros(K.act_bytes(rows), dtype=torch.uint8, device=DEV)
+    saved_raw = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, act_save=act)
+    assert torch.equal(probe_raw, base), (probe_raw - base).abs().max().item()
+    assert torch.equal(saved_raw, base), (saved_raw - base).abs().max().item()
     old = K.use_pairs(0)
     try:
         single = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
@@ -310,15 +317,21 @@ def test_field_kernel_variants_agree(rows, S):
         torch.cuda.synchronize()
     finally:
         K.use_pairs(old)
+    # Two summation orders exist for l6: mlp_fwd_kernel (base, single, crew) adds the PE chunk after the
+    # four h5 chunks (the production layout re-encodes the PE block inside the A tile), the other kernels
+    # before them.  Inside a family the results are bit-identical; across families an fp32 sum can land
+    # on the other side of a BF16 rounding boundary of h6 (one ulp of a few activations: up to 4e-4 on raw
+    # with this test's x5 l_alpha weights -- the size of the kernel's distance to its BF16 emulation).
+    scale = max(1., base.abs().max().item())
     print("mixed-orientation vs base max abs diff", (mixed - base).abs().max().item())
     print("TS vs base max abs diff", (ts - base).abs().max().item())
-    print("pairs + crew vs base max abs diff", (pairs_crew - base).abs().max().item())
-    assert (pairs_crew - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
-    assert torch.equal(pairs_tmap, base), (pairs_tmap - base).abs().max().item()
-    assert torch.equal(pairs_tmap_crew, pairs_crew), (pairs_tmap_crew - pairs_crew).abs().max().item()
-    assert (ts - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
-    assert (mixed - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())
+    print("CTA pairs vs base max abs diff", (pairs - base).abs().max().item())
     assert torch.equal(single, base), (single - base).abs().max().item()
-    assert torch.equal(pairs, base), (pairs - base).abs().max().item()
+    assert torch.equal(mixed, pairs), (mixed - pairs).abs().max().item()
+    assert torch.equal(pairs_tmap, pairs), (pairs_tmap - pairs).abs().max().item()
+    assert torch.equal(pairs_tmap_crew, pairs_crew), (pairs_tmap_crew - pairs_crew).abs().max().item()
+    assert (pairs_crew - pairs).abs().max().item() <= 2e-6 * scale
+    assert (ts - pairs).abs().max().item() <= 2e-6 * scale
+    assert (pairs - base).abs().max().item() <= 1e-3 * scale
     # four partial sums per row instead of two in the fp32 heads: same values up to fp32 reassociation
     assert (crew - base).abs().max().item() <= 2e-6 * max(1., base.abs().max().item())

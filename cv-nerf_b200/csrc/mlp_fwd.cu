@@ -241,18 +241,24 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0_rt, uint32
                                                 float* probe_row, const ConstTail& ct, int l,
                                                 uint32_t* mw = nullptr) {
     const int c0 = C0 >= 0 ? C0 : c0_rt;
-    uint32_t v[2][16] = {};
+    // NB accumulator buffers: tcgen05.wait::ld waits for every load issued so far, so with NB = 3 the
+    // youngest load outstanding at a wait is one whole step old (two steps of cover per load).
+    // EXP bit6 selects three (A/B): +2.5..7 % in short bursts, -1.6 % over 60 interleaved rounds of
+    // sustained load (the kernel spills at its 96-register cap), so two stay the default.
+    constexpr int NB = (CT && C0 >= 0 && (EXP & 64)) ? 3 : 2;
+    uint32_t v[NB][16] = {};
     float4 b[2][4] = {};
     float2 sig2 = make_float2(0.f, 0.f);
     if (!(EXP & 4)) umma::tmem_ld16(tacc + c0, v[0]);
+    if (NB == 3 && NIT > 1 && !(EXP & 4)) umma::tmem_ld16(tacc + c0 + 16, v[1]);
     if (!CT && !(EXP & 2)) lds_bias16(bias_addr + c0 * 4, b[0]);
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
         const int c = c0 + it * 16;
         if (!CT && it + 1 < NIT && !(EXP & 2)) lds_bias16(bias_addr + (c + 16) * 4, b[(it + 1) & 1]);
         if (!(EXP & 4)) umma::tmem_wait_ld();
-        if (it + 1 < NIT && !(EXP & 4)) umma::tmem_ld16(tacc + c + 16, v[(it + 1) & 1]);
-        const uint32_t(&cur)[16] = v[it & 1];
+        if (it + NB - 1 < NIT && !(EXP & 4)) umma::tmem_ld16(tacc + c + 16 * (NB - 1), v[(it + NB - 1) % NB]);
+        const uint32_t(&cur)[16] = v[it % NB];
         const float4(&bc)[4] = b[it & 1];
         float2 h[8];
 #pragma unroll
@@ -753,9 +759,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                 if (l < 9) {
                     const int c0 = half * 128;
                     if (CT && !PROBE) {
-                        if (CFG::exp & 64) epilogue_hidden_ct<8, CFG::exp & 7>(l, tacc, c0, a_row_addr, swz, sigma, P.ct);   // A/B: run-time column
-                        else if (half == 0) epilogue_hidden_ct<8, CFG::exp & 7, 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
-                        else epilogue_hidden_ct<8, CFG::exp & 7, 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
+                        if (half == 0) epilogue_hidden_ct<8, CFG::exp & (7 | 64), 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
+                        else epilogue_hidden_ct<8, CFG::exp & (7 | 64), 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
                     } else if (l == 7) {
                         epilogue_hidden<1, PROBE, CFG::exp, CT, 8, -1, SAVE>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row, P.ct, l, mw);
                     } else if (l == 8) {
@@ -1733,7 +1738,7 @@ FwdKernel fwd_variant(int v) {
         case 12: return mlp_fwd_kernel<false, Cfg<kRing, false, 16>, true>;   // training forward without the record copies (timing)
         case 13: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true, true>;   // no weight streaming + 16-warp crew (timing)
         case 14: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true>;         // no weight streaming, host tail (timing)
-        case 15: return mlp_fwd_kernel<false, Cfg<kRing, false, 32>, false, true>;        // weight copies cut to 1 KB per slot: the hand-off latencies without the bytes (timing)
+        case 15: return mlp_fwd_kernel<false, Cfg<3, false, 64, true>, false, true>;      // production with three accumulator buffers in the epilogue (A/B)
         case 16: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;            // host tail, round-1 layout: PE tiles + two weight slots (A/B)
         case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
         case 18: return mlp_fwd_kernel<false, Cfg<3, true>, false, true>;                 // host tail, 3 x 32 KB ring with the PE tiles aliased (timing only)

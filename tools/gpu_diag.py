@@ -194,9 +194,10 @@ if __name__ == "__main__":
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--stats", action="store_true")
     ap.add_argument("--ab", type=str, default="", help="comma-separated debug-entry variants to time round-robin")
+    ap.add_argument("--rounds", type=int, default=6)
     a = ap.parse_args()
     if a.ab:
-        ab([int(x) for x in a.ab.split(",")])
+        ab([int(x) for x in a.ab.split(",")], a.rounds)
         sys.exit(0)
     if a.stats:
         pipeline_stats()

@@ -478,7 +478,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                         ++it;
                         long long t0 = PROBE ? clock64() : 0;
                         rec(0, pair_no, 1, l, g, j);                 // waits for a free slot
-                        umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                        if (CFG::exp & 256) {     // EXP bit8 (A/B): the producer spins on test_wait instead of suspending
+                            while (!umma::mbar_test_wait(bar_w_empty + 8 * slot, ph ^ 1)) {}
+                        } else {
+                            umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                        }
                         rec(0, pair_no, 2, l, g, j);                 // slot free: copy issued
                         if (PROBE) t_wait0 += clock64() - t0;
                         umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
@@ -547,7 +551,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t it = 0, n_ready[2] = {0, 0};
+            // Everything this one thread executes between tcgen05.mma instructions is tensor-pipe idle time
+            // once the pipe's short queue has drained (four clock64 per chunk cost the probe build 20 %), so
+            // the ring position is kept incrementally and the descriptors are built from precomputed words.
+            uint32_t slot = 0, ph = 0, n_ready[2] = {0, 0};
+            constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << (46 - 32)) | (2u << (61 - 32));   // smem_desc_sw128, high word
+            auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+            auto desc_lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+            const uint32_t w_lo = desc_lo(sbase + kOffW);
             long pair_no = 0;
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_no) {
                 for (int l = 0; l < kNumMmaLayers; ++l) {
@@ -565,24 +576,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                     };
                     // one K chunk: weight slot, four MMAs (the first one overwrites D when `fresh`), slot release
                     auto chunk = [&](int g, int j, uint32_t a_addr, bool fresh) {
-                        const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-                        ++it;
                         long long t1 = PROBE ? clock64() : 0;
                         rec(1, pair_no, 3, l, g, j);                 // waits for the weight slot
+                        // (no tcgen05 fence here: the slot was written by the TMA engine, whose complete_tx
+                        // on this barrier orders it before the MMAs that follow the wait)
                         if (!(CFG::exp & 8)) umma::mbar_wait(bar_w_full + 8 * slot, ph);
                         rec(1, pair_no, 4, l, g, j);                 // weight slot full
                         if (PROBE) t_wait1 += clock64() - t1;
-                        umma::tc_fence_after();
                         // B = [N rows][64] K-major; the two 128-row halves are contiguous
-                        const uint32_t b_addr = sbase + kOffW + slot * kSlotBytes;
+                        const uint32_t b_lo = w_lo + slot * (kSlotBytes >> 4);
+                        const uint32_t a_lo = desc_lo(a_addr);
                         const uint32_t d_base = tmem_base + g * 256;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
-                                              umma::smem_desc_sw128(b_addr + kk * 32), idesc,
+                            umma::mma_bf16_ss(d_base, desc(a_lo + kk * 2), desc(b_lo + kk * 2), idesc,
                                               (!fresh || kk > 0) ? 1u : 0u);
                         }
                         umma::mma_commit(bar_w_empty + 8 * slot);
+                        if (++slot == (uint32_t)kRing) { slot = 0; ph ^= 1; }
                         rec(1, pair_no, 5, l, g, j);                 // chunk's four MMAs issued
                     };
                     if (kPEA && l == 5) {
@@ -1739,7 +1750,7 @@ FwdKernel fwd_variant(int v) {
         case 12: return mlp_fwd_kernel<false, Cfg<kRing, false, 16>, true>;   // training forward without the record copies (timing)
         case 13: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true, true>;   // no weight streaming + 16-warp crew (timing)
         case 14: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true>;         // no weight streaming, host tail (timing)
-        case 15: return mlp_fwd_kernel<false, Cfg<3, false, 64, true>, false, true>;      // production with three accumulator buffers in the epilogue (A/B)
+        case 15: return mlp_fwd_kernel<false, Cfg<3, false, 256, true>, false, true>;     // production with a spinning producer (A/B)
         case 16: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;            // host tail, round-1 layout: PE tiles + two weight slots (A/B)
         case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
         case 18: return mlp_fwd_kernel<false, Cfg<3, true>, false, true>;                 // host tail, 3 x 32 KB ring with the PE tiles aliased (timing only)

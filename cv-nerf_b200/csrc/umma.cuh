@@ -60,6 +60,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
+// non-blocking test of a phase (no suspend): for spin loops of threads that must react at once
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // Bounded wait: a protocol bug must end in a trap (launch error), never in a hung GPU.
 #ifndef NERF_MBAR_TIMEOUT_CYCLES
 #define NERF_MBAR_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 1.9 GHz

@@ -1513,6 +1513,47 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P, const __grid_constant__
             }
         } else if (lane == 0) {
             // ===================== leader: MMA issuer for the pair =====================
+            if (TMAP && !P.stats_out && !P.trace_out) {
+                // lean loop (no counters, no trace): as in mlp_fwd_kernel, every instruction between the
+                // tcgen05.mma of this thread is tensor time -- and the pair MMA leaves 128 cycles per step
+                uint32_t slot = 0, ph = 0, n_ready[2] = {0, 0};
+                constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << (46 - 32)) | (2u << (61 - 32));
+                auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+                auto desc_lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+                const uint32_t w_lo = desc_lo(sbase + kOffW);
+                constexpr uint32_t kIdescPair256 = umma::instr_desc_bf16(256, 256);
+                constexpr uint32_t kIdescPair128 = umma::instr_desc_bf16(256, 128);
+                for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+                    for (int l = 0; l < kNumMmaLayers; ++l) {
+                        const int chunks = layer_chunks(l);
+                        const uint32_t idesc = layer_halves(l) == 2 ? kIdescPair256 : kIdescPair128;
+                        for (int g = 0; g < 2; ++g) {
+                            umma::mbar_wait_cluster(bar_a_ready + 8 * g, n_ready[g] & 1);
+                            ++n_ready[g];
+                            umma::tc_fence_after();
+                            const uint32_t d_base = tmem_base + g * 256;
+                            const uint32_t a_tile = sbase + kOffA + g * 65536;
+                            const uint32_t pe_tile = sbase + kOffPE + g * 16384;
+                            for (int j = 0; j < chunks; ++j) {
+                                uint32_t a_addr;
+                                if (l == 0) a_addr = pe_tile;
+                                else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
+                                else a_addr = a_tile + j * 16384;
+                                umma::mbar_wait(bar_w_full + 8 * slot, ph);      // both halves' complete_tx land here
+                                const uint32_t b_lo = w_lo + slot * (kStageBytes >> 4);
+                                const uint32_t a_lo = desc_lo(a_addr);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma::mma_bf16_ss_pair(d_base, desc(a_lo + kk * 2), desc(b_lo + kk * 2), idesc,
+                                                           (j > 0 || kk > 0) ? 1u : 0u);
+                                umma::mma_commit_pair(bar_w_empty + 8 * slot);
+                                if (++slot == (uint32_t)kPairRing) { slot = 0; ph ^= 1; }
+                            }
+                            umma::mma_commit_pair(bar_acc_full + 8 * g);
+                        }
+                    }
+                }
+            } else {
             uint32_t it = 0, n_ready[2] = {0, 0};
             long long tw_a = 0, tw_w = 0, tw_p = 0;
             const bool stats = P.stats_out != nullptr;      // the counters cost issue slots of the one thread that feeds the tensor core
@@ -1568,6 +1609,7 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P, const __grid_constant__
             if (stats) {
                 long long* o = P.stats_out + (long)blockIdx.x * 8;
                 o[1] = tw_a; o[2] = tw_w; o[6] = tw_p; o[5] = clock64() - t_begin;
+            }
             }
         }
     } else if (WIDE) {

@@ -25,7 +25,7 @@ namespace {
 using namespace nerf;
 
 constexpr int kTileM = 128;
-constexpr int kRing = 2;
+constexpr int kRing = 3;                                 // 32 KB weight slots (three fit beside the two A tiles)
 constexpr int kSlotBytes = 2 * kStageBytes;
 constexpr int kEpiWarpsPerGroup = 8;
 constexpr int kGroupThreads = kEpiWarpsPerGroup * 32;
@@ -214,7 +214,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams 
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t it = 0, n_ready[2] = {0, 0};
+            // lean issue loop as in mlp_fwd.cu: ring position kept incrementally, descriptors from
+            // precomputed words, no tcgen05 fence after the TMA-signalled slot barrier
+            uint32_t slot = 0, ph = 0, n_ready[2] = {0, 0};
+            constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << (46 - 32)) | (2u << (61 - 32));
+            auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+            auto desc_lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+            const uint32_t w_lo = desc_lo(sbase + kOffW);
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 for (int j = 0; j < kBwdLayers; ++j) {
                     const int chunks = bwd_chunks(j);
@@ -223,21 +229,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams 
                         ++n_ready[g];
                         umma::tc_fence_after();
                         const uint32_t d_base = tmem_base + g * 256;
-                        const uint32_t a_tile = sbase + kOffA + g * 65536;
+                        const uint32_t a_tile_lo = desc_lo(sbase + kOffA + g * 65536);
                         for (int c = 0; c < chunks; ++c) {
-                            const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-                            ++it;
                             umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                            umma::tc_fence_after();
-                            const uint32_t a_addr = a_tile + c * 16384;
-                            const uint32_t b_addr = sbase + kOffW + slot * kSlotBytes;
+                            const uint32_t a_lo = a_tile_lo + c * (16384 >> 4);
+                            const uint32_t b_lo = w_lo + slot * (kSlotBytes >> 4);
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
-                                umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
-                                                  umma::smem_desc_sw128(b_addr + kk * 32), kIdescN256,
+                                umma::mma_bf16_ss(d_base, desc(a_lo + kk * 2), desc(b_lo + kk * 2), kIdescN256,
                                                   (c > 0 || kk > 0) ? 1u : 0u);
                             }
                             umma::mma_commit(bar_w_empty + 8 * slot);
+                            if (++slot == (uint32_t)kRing) { slot = 0; ph ^= 1; }
                         }
                         umma::mma_commit(bar_acc_full + 8 * g);
                     }

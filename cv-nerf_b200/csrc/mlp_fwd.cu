@@ -42,6 +42,10 @@ constexpr int kMaxRing = 8;
 constexpr int kSlotBytes = 2 * kStageBytes;           // one K chunk, both N halves: [256][64] bf16
 constexpr int kEpiWarpsPerGroup = 8;
 constexpr int kThreads = 64 + 2 * kEpiWarpsPerGroup * 32;   // 576
+// mlp_fwd_kernel can run a SECOND producer warp (warp 18, Cfg::two_producers): every 32 KB slot is then
+// fetched as two 16 KB bulk copies issued by two threads (copies issued by one thread do not overlap:
+// tools/probes/sw64_mma_probe.cu), which lands a slot ~150-200 cycles earlier.
+constexpr int kThreadsFwd2 = kThreads + 32;           // 608
 constexpr uint32_t kOffA = 0;                         // 2 x [4][128][64] bf16
 constexpr uint32_t kOffPE = 2 * 65536;                // 2 x [128][64] bf16
 constexpr uint32_t kOffW = kOffPE + 2 * 16384;        // ring x 32 KB
@@ -68,6 +72,7 @@ constexpr uint32_t kIdescN128 = umma::instr_desc_bf16(128, 128);
 template <int RING, bool ALIAS, int EXP = 0, bool PEA = false>
 struct Cfg {
     static constexpr int ring = RING;
+    static constexpr bool two_producers = (EXP & 512) != 0;     // EXP bit9
     static constexpr int exp = EXP;
     static constexpr bool pea = PEA;
     static constexpr uint32_t off_pe = ALIAS ? 0u : kOffPE;
@@ -406,7 +411,8 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
 // The MMA -> epilogue -> MMA chain of a sub-tile is latency-bound on the epilogue; with twice the
 // warps on it the next layer's operand is ready in about half the time and the tensor core idles less.
 template <bool PROBE, class CFG, bool SAVE = false, bool CT = false, bool WIDE = false>
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
+__global__ void __launch_bounds__(CFG::two_producers ? kThreadsFwd2 : kThreads, 1)
+mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
     static_assert(!WIDE || (CT && !SAVE && !PROBE), "WIDE is an inference-only variant");
     constexpr bool kPEA = CFG::pea;
     static_assert(!kPEA || (!SAVE && !WIDE && !PROBE), "PEA is implemented for the 8-warp inference epilogue");
@@ -462,8 +468,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
     umma::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== producer: weight slots, L2 -> smem =====================
+    if (warp == 0 || warp == 18) {
+        // ===================== producer(s): weight slots, L2 -> smem =====================
+        // two_producers: warp 0 arms the slot barrier with the whole byte count and copies the first half
+        // of the slot, warp 18 the second half
+        constexpr bool kTwo = CFG::two_producers;
+        const bool second = warp == 18;
         if (lane == 0 && !(CFG::exp & 8)) {
             uint32_t it = 0;
             long pair_no = 0;
@@ -485,9 +495,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_kernel(const __grid_const
                         }
                         rec(0, pair_no, 2, l, g, j);                 // slot free: copy issued
                         if (PROBE) t_wait0 += clock64() - t0;
-                        umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
-                        umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
-                                       P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes,
+                        if (!second) umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
+                        const uint32_t part = kTwo ? bytes / 2 : bytes, off = second ? part : 0u;
+                        umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes + off,
+                                       P.blob + (size_t)first * kStageBytes + (size_t)j * bytes + off, part,
                                        bar_w_full + 8 * slot);
                     };
                     if (kPEA && l == 5) {      // the MMA warp's order for l6: h5 chunks of X, of Y, PE chunk of X, of Y
@@ -1792,7 +1803,7 @@ FwdKernel fwd_variant(int v) {
         case 12: return mlp_fwd_kernel<false, Cfg<kRing, false, 16>, true>;   // training forward without the record copies (timing)
         case 13: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true, true>;   // no weight streaming + 16-warp crew (timing)
         case 14: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true>;         // no weight streaming, host tail (timing)
-        case 15: return mlp_fwd_kernel<false, Cfg<3, false, 256, true>, false, true>;     // production with a spinning producer (A/B)
+        case 15: return mlp_fwd_kernel<false, Cfg<3, false, 512, true>, false, true>;     // production with two producer warps (A/B; 608 threads)
         case 16: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;            // host tail, round-1 layout: PE tiles + two weight slots (A/B)
         case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
         case 18: return mlp_fwd_kernel<false, Cfg<3, true>, false, true>;                 // host tail, 3 x 32 KB ring with the PE tiles aliased (timing only)
@@ -1826,7 +1837,7 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
     const long n_pairs = (n_tiles + 1) / 2;
     const unsigned grid = (unsigned)(n_pairs < sm_count ? n_pairs : sm_count);
-    k<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    k<<<grid, variant == 15 ? kThreadsFwd2 : kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
     return nerf::check_launch("nerf_mlp_fwd");
 }
 

@@ -141,7 +141,7 @@ def ab(variants, rounds=6):
         print(f"variant {v}: {ms:.3f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s (mean of {rounds} interleaved rounds)")
 
 
-def pipeline_stats(variants=(9, 16, 18, 14)):
+def pipeline_stats(variants=(9, 15, 16, 14)):
     """Per-role wait-cycle breakdown of the field kernel (debug entry nerf_mlp_fwd_stats)."""
     from cv_nerf_b200 import _lib
     lib = _lib.load()
@@ -160,7 +160,7 @@ def pipeline_stats(variants=(9, 16, 18, 14)):
              9: "host tail (production inference kernel); no counters", 10: "host tail + 16-warp crew; no counters",
              13: "EXP no weight streaming + 16-warp crew; no counters", 14: "EXP no weight streaming, host tail; no counters",
              16: "host tail, round-1 layout (PE tiles, 2 x 32 KB ring); no counters",
-             15: "EXP weight copies cut to 1 KB per slot (hand-offs without the bytes); no counters", 16: "EXP no bias loads + no weight streaming; no counters",
+             15: "production with two producer warps; no counters", 16: "EXP no bias loads + no weight streaming; no counters",
              17: "EXP host tail, whole-warp MMA issuer; no counters", 18: "EXP host tail, 3 x 32 KB ring (PE aliased: timing only); no counters",
              11: "EXP no weight streaming (upper bound if weight slots were always ready)",
              100: "CTA pairs (cta_group::2); leader CTAs only; [6] = wait for the peer's half-chunk",

@@ -100,22 +100,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dw_kernel(const __grid_co
 
     if (warp == 0) {
         // ===================== producer =====================
-        if (lane == 0) {
+        // The up to eight 4 KB pieces of a slot are issued by eight LANES in one warp instruction: bulk
+        // copies issued one after the other by a single thread do not overlap (16 KB copies: 30 B/cycle
+        // from one thread, 60 from two, tools/probes/sw64_mma_probe.cu), and eight serial 4 KB copies per
+        // 32 KB slot capped this HBM-bound kernel at the issue rate of one thread.
+        {
             uint32_t it = 0;
             const uint32_t bytes = (uint32_t)(J.a_blocks + J.b_blocks) * kPieceBytes;
+            const bool mine_a = lane < J.a_blocks;
+            const bool mine_b = lane >= 4 && lane - 4 < J.b_blocks;
             for (long t = t_begin; t < t_end; ++t) {
                 const uint8_t* a_src = P.dz + (size_t)t * kDzTileBytes + J.a_off;
                 const uint8_t* b_src = P.act + (size_t)t * kActTileBytes + J.b_off;
                 for (int ks = 0; ks < kSlicesPerTile; ++ks, ++it) {
                     const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-                    umma::mbar_wait(bar_empty + 8 * slot, ph ^ 1);
-                    umma::mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+                    umma::mbar_wait_warp(bar_empty + 8 * slot, ph ^ 1);
+                    if (lane == 0) umma::mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+                    __syncwarp();
                     const uint32_t dst = sbase + slot * kSlotBytes;
-                    for (int b = 0; b < J.a_blocks; ++b)
-                        umma::bulk_g2s(dst + b * kPieceBytes, a_src + (size_t)b * kBlockBytes + ks * kPieceBytes,
+                    if (mine_a)
+                        umma::bulk_g2s(dst + lane * kPieceBytes, a_src + (size_t)lane * kBlockBytes + ks * kPieceBytes,
                                        kPieceBytes, bar_full + 8 * slot);
-                    for (int b = 0; b < J.b_blocks; ++b)
-                        umma::bulk_g2s(dst + (4 + b) * kPieceBytes, b_src + (size_t)b * kBlockBytes + ks * kPieceBytes,
+                    else if (mine_b)
+                        umma::bulk_g2s(dst + lane * kPieceBytes, b_src + (size_t)(lane - 4) * kBlockBytes + ks * kPieceBytes,
                                        kPieceBytes, bar_full + 8 * slot);
                 }
             }

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(CFG::two_producers ? kThreadsFwd2 : kThreads, 
 mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
     static_assert(!WIDE || (CT && !SAVE && !PROBE), "WIDE is an inference-only variant");
     constexpr bool kPEA = CFG::pea;
-    static_assert(!kPEA || (!SAVE && !WIDE && !PROBE), "PEA is implemented for the 8-warp inference epilogue");
+    static_assert(!kPEA || (!WIDE && !PROBE), "PEA is implemented for the 8-warp epilogue groups");
     constexpr bool kStageBias = !CT;          // per-layer bias staged in shared memory
     constexpr bool kGroupSync = !CT || SAVE;  // group barriers around the staging / the record copies
     constexpr int kRing = CFG::ring;
@@ -729,9 +729,10 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
         const uint32_t swz = (uint32_t)(row & 7) << 4;
         // PEA: the PE tile is block 0 of the group's A tile
         uint8_t* pe_tile = kPEA ? smem + kOffA + g * 65536 : smem + kOffPE + g * 16384;
-        // FP32 hand-over slot between the two threads of a row, inside the row's own PE line
-        // (free between l6's MMA and the next tile's encoding; PEA: block 0 of h9, dead after l10's MMAs)
-        float4* xchg = reinterpret_cast<float4*>(pe_tile + row * 128);
+        // FP32 hand-over slot between the two threads of a row, inside the row's own PE line (free between
+        // l6's MMA and the next tile's encoding); PEA: the row's line in block 3 of the A tile (h9, dead after
+        // l10's MMAs; the training build parks h10 in blocks 0..1 at that point)
+        float4* xchg = reinterpret_cast<float4*>((kPEA ? smem + kOffA + g * 65536 + 3 * 16384 : pe_tile) + row * 128);
         uint32_t n_pe_free = 0;
         const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
         const float* tail = reinterpret_cast<const float*>(P.blob + kWeightBytes);
@@ -746,6 +747,12 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
             const long grow_raw = (pair * 2 + g) * kTileM + row;
             const bool valid = grow_raw < P.M;
             const long grow = valid ? grow_raw : P.M - 1;
+            if (SAVE && kPEA) {
+                // the previous tile's h10 copy reads blocks 0..1 of the A tile: it must be done before the
+                // PE is encoded into block 0
+                if (gtid == 0) umma::bulk_wait_read0();
+                umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+            }
             if (half == 0) input_stage<0>(P, grow, pe_tile, row);
             else input_stage<1>(P, grow, pe_tile, row);
             umma::fence_proxy_async_smem();
@@ -762,7 +769,7 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                 if (gtid == 0) umma::bulk_wait_read0();
                 umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
                 if (act_tile) {
-                    umma::bulk_s2g(act_tile + kActPE, sbase + kOffPE + g * 16384, 16384);
+                    umma::bulk_s2g(act_tile + kActPE, kPEA ? sbase + kOffA + g * 65536 : sbase + kOffPE + g * 16384, 16384);
                     umma::bulk_commit();
                 }
             }
@@ -779,6 +786,11 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                 ++n_full;
                 umma::tc_fence_after();
                 if (PROBE) probe_row = (P.probe_out && P.probe_layer == l && valid) ? P.probe_out + grow * 256 : nullptr;
+                if (SAVE && kPEA && l == 0) {
+                    // the PE record copy reads block 0, which l1's epilogue is about to overwrite
+                    if (gtid == 0) umma::bulk_wait_read0();
+                    umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
+                }
                 if (l < 9) {
                     const int c0 = half * 128;
                     if (CT && !PROBE) {
@@ -1796,11 +1808,11 @@ FwdKernel fwd_variant(int v) {
         case 5: return mlp_fwd_kernel<true, Cfg<kRing, false, 2>>;
         case 6: return mlp_fwd_kernel<true, Cfg<kRing, false, 4>>;
         case 7: return mlp_fwd_kernel<true, Cfg<kRing, false, 7>>;
-        case 8: return mlp_fwd_kernel<false, Cfg<kRing, false>, true>;   // training: saves activations
+        case 8: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>, true>;   // training: saves activations (PE in the A tile, three slots)
         case 9: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>, false, true>;      // inference with the host tail (production)
         case 10: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true, true>;   // + 16-warp epilogue crew
         case 11: return mlp_fwd_kernel<true, Cfg<kRing, false, 8>>;
-        case 12: return mlp_fwd_kernel<false, Cfg<kRing, false, 16>, true>;   // training forward without the record copies (timing)
+        case 12: return mlp_fwd_kernel<false, Cfg<kRing, false>, true>;       // training forward, round-1 layout: PE tiles + two slots (A/B)
         case 13: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true, true>;   // no weight streaming + 16-warp crew (timing)
         case 14: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true>;         // no weight streaming, host tail (timing)
         case 15: return mlp_fwd_kernel<false, Cfg<3, false, 512, true>, false, true>;     // production with two producer warps (A/B; 608 threads)
@@ -2001,8 +2013,8 @@ extern "C" int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, c
     if (M == 0) return 0;
     if (act_save && ((uintptr_t)act_save & 15)) return nerf::arg_error("nerf_mlp_fwd: act_save must be 16-byte aligned");
     P.act_save = (uint8_t*)act_save;
-    static const bool no_copies = getenv("NERF_B200_EXP_NO_RECORD_COPIES") != nullptr;   // timing experiment only
-    return launch_fwd(P, act_save ? (no_copies ? 12 : 8) : 0, stream);
+    static const bool old_layout = getenv("NERF_B200_EXP_SAVE_OLD_LAYOUT") != nullptr;   // A/B timing only
+    return launch_fwd(P, act_save ? (old_layout ? 12 : 8) : 0, stream);
 }
 
 extern "C" size_t nerf_model_host_tail_bytes(void) { return sizeof(ConstTail); }

@@ -173,8 +173,9 @@ __device__ __forceinline__ void encode_half(float px, float py, float pz, float 
     }
 }
 
+// the 32 PE columns of this thread's half row as four packed 16-byte chunks
 template <int HALF>
-__device__ __forceinline__ void input_stage(const FwdParams& P, long grow, uint8_t* pe_tile, int row) {
+__device__ __forceinline__ void input_encode(const FwdParams& P, long grow, uint4 (&o)[4]) {
     float f[32];
     if (P.in_mode == NERF_IN_EMBEDDED) {
         const float* x = P.in0 + grow * P.in_stride + HALF * 32;
@@ -197,14 +198,27 @@ __device__ __forceinline__ void input_stage(const FwdParams& P, long grow, uint8
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        uint4 o;
-        o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-        o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-        o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-        o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-        const int c16 = HALF * 4 + q;
-        *reinterpret_cast<uint4*>(pe_tile + row * 128 + ((c16 ^ (row & 7)) << 4)) = o;
+        o[q].x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+        o[q].y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+        o[q].z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+        o[q].w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
     }
+}
+
+template <int HALF>
+__device__ __forceinline__ void input_store(const uint4 (&o)[4], uint8_t* pe_tile, int row) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c16 = HALF * 4 + q;
+        *reinterpret_cast<uint4*>(pe_tile + row * 128 + ((c16 ^ (row & 7)) << 4)) = o[q];
+    }
+}
+
+template <int HALF>
+__device__ __forceinline__ void input_stage(const FwdParams& P, long grow, uint8_t* pe_tile, int row) {
+    uint4 o[4];
+    input_encode<HALF>(P, grow, o);
+    input_store<HALF>(o, pe_tile, row);
 }
 
 // ---------------------------------------------------------------------------- epilogues
@@ -743,6 +757,8 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
         }
         long pair_no = 0;
         const bool tracer = (ew & 7) == 0 && lane == 0;        // first warp of the group
+        uint4 pe_regs[4];
+        bool pe_ahead = false;
         for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_no) {
             const long grow_raw = (pair * 2 + g) * kTileM + row;
             const bool valid = grow_raw < P.M;
@@ -753,8 +769,16 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                 if (gtid == 0) umma::bulk_wait_read0();
                 umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
             }
-            if (half == 0) input_stage<0>(P, grow, pe_tile, row);
-            else input_stage<1>(P, grow, pe_tile, row);
+            // the tile's PE: encoded ahead of time (into registers, while the group waited for the previous
+            // tile's l10 accumulator) whenever there was a previous tile -- at a tile boundary only the stores
+            // are left on the sub-tile's MMA -> epilogue -> MMA chain
+            if (!pe_ahead) {
+                if (half == 0) input_encode<0>(P, grow, pe_regs);
+                else input_encode<1>(P, grow, pe_regs);
+            }
+            if (half == 0) input_store<0>(pe_regs, pe_tile, row);
+            else input_store<1>(pe_regs, pe_tile, row);
+            pe_ahead = false;
             umma::fence_proxy_async_smem();
             umma::mbar_arrive(bar_a_ready + 8 * g);
             uint8_t* act_tile = nullptr;
@@ -779,6 +803,12 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
 #pragma unroll 1
             for (int l = 0; l < kNumMmaLayers; ++l) {
                 long long t0 = PROBE ? clock64() : 0;
+                if (!SAVE && l == 9 && pair + gridDim.x < n_pairs) {
+                    const long nxt = ((pair + gridDim.x) * 2 + g) * kTileM + row;
+                    if (half == 0) input_encode<0>(P, nxt < P.M ? nxt : P.M - 1, pe_regs);
+                    else input_encode<1>(P, nxt < P.M ? nxt : P.M - 1, pe_regs);
+                    pe_ahead = true;
+                }
                 if (tracer) rec(2 + g, pair_no, 1, l, g, 0);           // waits for the accumulator
                 umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
                 if (tracer) rec(2 + g, pair_no, 2, l, g, 0);           // accumulator complete

@@ -515,11 +515,7 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                                        P.blob + (size_t)first * kStageBytes + (size_t)j * bytes + off, part,
                                        bar_w_full + 8 * slot);
                     };
-                    if (kPEA && l == 5) {      // the MMA warp's order for l6: h5 chunks of X, of Y, PE chunk of X, of Y
-                        for (int g = 0; g < 2; ++g)
-                            for (int j = 1; j < chunks; ++j) fetch(g, j);
-                        for (int g = 0; g < 2; ++g) fetch(g, 0);
-                    } else {
+                    {
                         // l6 accumulates its PE chunk (chunk 0) last in every variant of this kernel, so that
                         // they all sum in the same order
                         for (int g = 0; g < 2; ++g)
@@ -590,10 +586,15 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                     const int chunks = layer_chunks(l);
                     const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
                     // waits until sub-tile g's A operand (or its re-encoded PE block) is written
+                    // EXP bit11: wait profile of the production layout, sampled on one tile pair in eight (two
+                    // clock64 around every wait would cost ~10 % if taken always): cycles per (layer, sub-tile)
+                    // waiting for the A operand and per (layer, chunk) waiting for the weight slot
+                    const bool sampled = (CFG::exp & 2048) && P.trace_out && (pair_no & 7) == 3;
                     auto wait_a = [&](int g) {
-                        long long t0 = PROBE ? clock64() : 0;
+                        long long t0 = (PROBE || sampled) ? clock64() : 0;
                         rec(1, pair_no, 1, l, g, 0);                     // waits for the A operand
                         umma::mbar_wait(bar_a_ready + 8 * g, n_ready[g] & 1);
+                        if (sampled) atomicAdd((unsigned long long*)P.trace_out + 64 + l * 2 + g, (unsigned long long)(clock64() - t0));
                         rec(1, pair_no, 2, l, g, 0);                     // A operand ready
                         if (PROBE) t_wait0 += clock64() - t0;
                         ++n_ready[g];
@@ -601,11 +602,15 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                     };
                     // one K chunk: weight slot, four MMAs (the first one overwrites D when `fresh`), slot release
                     auto chunk = [&](int g, int j, uint32_t a_addr, bool fresh) {
-                        long long t1 = PROBE ? clock64() : 0;
+                        long long t1 = (PROBE || sampled) ? clock64() : 0;
                         rec(1, pair_no, 3, l, g, j);                 // waits for the weight slot
                         // (no tcgen05 fence here: the slot was written by the TMA engine, whose complete_tx
                         // on this barrier orders it before the MMAs that follow the wait)
                         if (!(CFG::exp & 8)) umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                        if (sampled) {
+                            atomicAdd((unsigned long long*)P.trace_out + l * 5 + j, (unsigned long long)(clock64() - t1));
+                            if (l == 0 && j == 0 && g == 0) atomicAdd((unsigned long long*)P.trace_out + 100, 1ull);
+                        }
                         rec(1, pair_no, 4, l, g, j);                 // weight slot full
                         if (PROBE) t_wait1 += clock64() - t1;
                         // B = [N rows][64] K-major; the two 128-row halves are contiguous
@@ -622,9 +627,10 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                         rec(1, pair_no, 5, l, g, j);                 // chunk's four MMAs issued
                     };
                     if (kPEA && l == 5) {
-                        // l6 with the PE block re-encoded in place: h5 chunks first; block 0 is released to
-                        // the epilogue group as soon as its MMAs are done; the PE chunks of both sub-tiles
-                        // follow the h5 chunks of both, so the re-encoding of X runs under Y's MMAs
+                        // l6 with the PE block restored in place: the four h5 chunks first; block 0 is
+                        // released to the epilogue group as soon as its MMAs are done, the group stores the PE
+                        // chunks it kept in registers (a few dozen cycles, under the three remaining h5
+                        // chunks), then the PE chunk closes the layer
                         for (int g = 0; g < 2; ++g) {
                             wait_a(g);
                             const uint32_t a_tile = sbase + kOffA + g * 65536;
@@ -632,10 +638,8 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                                 chunk(g, j, a_tile + (j - 1) * 16384, j == 1);
                                 if (j == 1) umma::mma_commit(bar_pe_free + 8 * g);
                             }
-                        }
-                        for (int g = 0; g < 2; ++g) {
                             wait_a(g);
-                            chunk(g, 0, sbase + kOffA + g * 65536, false);
+                            chunk(g, 0, a_tile, false);
                             umma::mma_commit(bar_acc_full + 8 * g);
                         }
                         continue;
@@ -856,11 +860,12 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                     if (kStageBias) umma::st_shared_f32(bias_addr + gtid * 4, bnext);
                     if (kGroupSync) umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
                     if (kPEA && l == 4) {
-                        // l6's MMAs on block 0 (h5) have completed: encode the points again into it
+                        // l6's MMAs on block 0 (h5) have completed: put the tile's PE (still in pe_regs -- the
+                        // compiler parks them in local memory across l2..l5) back into it
                         umma::mbar_wait_warp(bar_pe_free + 8 * g, n_pe_free & 1);
                         ++n_pe_free;
-                        if (half == 0) input_stage<0>(P, grow, pe_tile, row);
-                        else input_stage<1>(P, grow, pe_tile, row);
+                        if (half == 0) input_store<0>(pe_regs, pe_tile, row);
+                        else input_store<1>(pe_regs, pe_tile, row);
                         umma::fence_proxy_async_smem();
                         umma::mbar_arrive(bar_a_ready + 8 * g);
                     }
@@ -1848,7 +1853,7 @@ FwdKernel fwd_variant(int v) {
         case 15: return mlp_fwd_kernel<false, Cfg<3, false, 512, true>, false, true>;     // production with two producer warps (A/B; 608 threads)
         case 16: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;            // host tail, round-1 layout: PE tiles + two weight slots (A/B)
         case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
-        case 18: return mlp_fwd_kernel<false, Cfg<3, true>, false, true>;                 // host tail, 3 x 32 KB ring with the PE tiles aliased (timing only)
+        case 18: return mlp_fwd_kernel<false, Cfg<3, false, 2048, true>, false, true>;    // production + sampled wait profile (trace_out[0..50) slot waits, [64..84) A waits, [100] pairs)
         default: return nullptr;
     }
 }

@@ -1850,7 +1850,7 @@ FwdKernel fwd_variant(int v) {
         case 12: return mlp_fwd_kernel<false, Cfg<kRing, false>, true>;       // training forward, round-1 layout: PE tiles + two slots (A/B)
         case 13: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true, true>;   // no weight streaming + 16-warp crew (timing)
         case 14: return mlp_fwd_kernel<false, Cfg<kRing, false, 8>, false, true>;         // no weight streaming, host tail (timing)
-        case 15: return mlp_fwd_kernel<false, Cfg<3, false, 512, true>, false, true>;     // production with two producer warps (A/B; 608 threads)
+        case 15: return mlp_fwd_kernel<false, Cfg<3, false, 64, true>, false, true>;      // production with three accumulator buffers in the epilogue (A/B)
         case 16: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;            // host tail, round-1 layout: PE tiles + two weight slots (A/B)
         case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
         case 18: return mlp_fwd_kernel<false, Cfg<3, false, 2048, true>, false, true>;    // production + sampled wait profile (trace_out[0..50) slot waits, [64..84) A waits, [100] pairs)
@@ -1884,7 +1884,7 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
     const long n_pairs = (n_tiles + 1) / 2;
     const unsigned grid = (unsigned)(n_pairs < sm_count ? n_pairs : sm_count);
-    k<<<grid, variant == 15 ? kThreadsFwd2 : kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    k<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
     return nerf::check_launch("nerf_mlp_fwd");
 }
 

@@ -159,9 +159,9 @@ def pipeline_stats(variants=(9, 15, 16, 14)):
              4: "EXP no A-tile stores", 5: "EXP no bias loads", 6: "EXP no TMEM loads", 7: "EXP none of the three",
              9: "host tail (production inference kernel); no counters", 10: "host tail + 16-warp crew; no counters",
              13: "EXP no weight streaming + 16-warp crew; no counters", 14: "EXP no weight streaming, host tail; no counters",
-             16: "host tail, round-1 layout (PE tiles, 2 x 32 KB ring); no counters",
-             15: "production with two producer warps; no counters", 16: "EXP no bias loads + no weight streaming; no counters",
-             17: "EXP host tail, whole-warp MMA issuer; no counters", 18: "EXP host tail, 3 x 32 KB ring (PE aliased: timing only); no counters",
+             16: "host tail, earlier layout (PE tiles of their own, 2 x 32 KB ring); no counters",
+             15: "production with three accumulator buffers in the epilogue; no counters", 16: "EXP no bias loads + no weight streaming; no counters",
+             17: "EXP host tail, whole-warp MMA issuer; no counters", 18: "production + sampled wait profile (tools/wait_profile.py); no counters",
              11: "EXP no weight streaming (upper bound if weight slots were always ready)",
              100: "CTA pairs (cta_group::2); leader CTAs only; [6] = wait for the peer's half-chunk",
              101: "CTA pairs + 16-warp crew; leader CTAs only",

@@ -334,12 +334,19 @@ def _cuda_stream(stream, dev):
     return (stream if stream is not None else torch.cuda.current_stream(dev)).cuda_stream
 
 
+def _byte_ptr(t, what):
+    """Device pointer of a uint8 record buffer (activation / dZ tile images)."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise _lib.NerfB200Error(f"{what} must be a CUDA tensor; there is no CPU fallback")
+    return t.data_ptr()
+
+
 def mlp_bwd_heads(act, grad_raw, rows, blob, stream=None):
     """dW/db of l_alpha and l11 into the gradient blob (reads the saved h8 / h10 and grad_raw only, so
     it can run as soon as the compositing backward is done)."""
     lib = _lib.load()
     grad_raw = f32c(grad_raw)
-    check(lib.nerf_mlp_bwd_heads(act.data_ptr(), ptr(grad_raw), rows, ptr(blob), _cuda_stream(stream, blob.device)),
+    check(lib.nerf_mlp_bwd_heads(_byte_ptr(act, "act"), ptr(grad_raw), rows, ptr(blob), _cuda_stream(stream, blob.device)),
           "nerf_mlp_bwd_heads")
     return blob
 
@@ -347,7 +354,7 @@ def mlp_bwd_heads(act, grad_raw, rows, blob, stream=None):
 def mlp_bwd_dw(act, dz, rows, blob, stream=None):
     """dW/db of the eleven tensor-core layers into the gradient blob."""
     lib = _lib.load()
-    check(lib.nerf_mlp_bwd_dw(act.data_ptr(), dz.data_ptr(), rows, ptr(blob), _cuda_stream(stream, blob.device)),
+    check(lib.nerf_mlp_bwd_dw(_byte_ptr(act, "act"), _byte_ptr(dz, "dz"), rows, ptr(blob), _cuda_stream(stream, blob.device)),
           "nerf_mlp_bwd_dw")
     return blob
 
@@ -360,7 +367,7 @@ def viewdir_term_bwd(dz, rows, dirs, vterm_div, embedded, blob, stream=None):
     else:
         dirs = f32c(dirs)
         dptr, stride = dirs.data_ptr(), dirs.shape[-1]
-    check(lib.nerf_viewdir_term_bwd(dz.data_ptr(), dptr, stride, int(embedded), rows, vterm_div, ptr(blob),
+    check(lib.nerf_viewdir_term_bwd(_byte_ptr(dz, "dz"), dptr, stride, int(embedded), rows, vterm_div, ptr(blob),
                                     _cuda_stream(stream, blob.device)), "nerf_viewdir_term_bwd")
     return blob
 

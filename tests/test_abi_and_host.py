@@ -43,6 +43,20 @@ def test_no_cpu_fallback():
         MD.FreqEmbedding(10).embed(torch.rand(3, 3))
 
 
+def test_gradient_wrappers_refuse_host_buffers():
+    """the split gradient launches (heads / dW / view columns) check every buffer they hand to the C ABI"""
+    import cv_nerf_b200
+    from cv_nerf_b200 import kernels as K
+    act = torch.zeros(64, dtype=torch.uint8)
+    blob = torch.zeros(16)
+    with pytest.raises(cv_nerf_b200.NerfB200Error):
+        K.mlp_bwd_heads(act, torch.zeros(4, 4), 4, blob)
+    with pytest.raises(cv_nerf_b200.NerfB200Error):
+        K.mlp_bwd_dw(act, act, 4, blob)
+    with pytest.raises(cv_nerf_b200.NerfB200Error):
+        K.viewdir_term_bwd(act, 4, torch.zeros(1, 11), 4, False, blob)
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "cv-nerf_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -228,7 +228,8 @@ def freq_encode(x, n_freq):
 
 def use_pairs(enable=None):
     """Select the CTA-pair (tcgen05 cta_group::2) field kernel for the inference fast path (default
-    on); returns the previous setting.  ``None`` only queries."""
+    OFF: the single-CTA kernel is faster); returns the previous setting.  ``None``
+    only queries."""
     return int(_lib.load().nerf_mlp_fwd_use_pairs(-1 if enable is None else int(enable)))
 
 

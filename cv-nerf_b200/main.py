@@ -121,9 +121,13 @@ def render_rays(ray_batch, coarse_model, q_fn=None, n_coarse_samples=64, perturb
 
 def batch_rays(rays_flat, chunk=32768, *, draws=None, **kwargs):
     """Chunked render_rays (main.py:90-99).  ``chunk`` exists in the reference to bound the
-    [chunk*S,90] encoding tensor; the fused path has no such tensor, so chunks are merged up to
-    MAX_RAYS_PER_LAUNCH rays per launch."""
-    step = max(int(chunk), MAX_RAYS_PER_LAUNCH)
+    [chunk*S,90] encoding tensor; the inference path has no such tensor (about 6 KB of raw/depth
+    scratch per ray), so without autograd chunks are merged up to MAX_RAYS_PER_LAUNCH rays per
+    launch.  With autograd recording, the field saves about 1.35 MB of activations per ray
+    (675 840 B per 128-sample tile x 256 samples), so there ``chunk`` is honoured as the memory
+    bound it is in the reference."""
+    chunk = max(int(chunk), 1)
+    step = chunk if torch.is_grad_enabled() else max(chunk, MAX_RAYS_PER_LAUNCH)
     res = {}
     for i in range(0, rays_flat.shape[0], step):
         d = None if draws is None else draws.rows(i, i + step)
@@ -204,11 +208,28 @@ def render_full(render_poses, hwf, chunk, render_kwargs, save_dir=None, factor=0
             rgbs = P.gather_frames(local, n, process_group).cpu().numpy()
     if save_dir is not None and rank == 0:
         os.makedirs(save_dir, exist_ok=True)
-        for i in range(n):
-            np.save(os.path.join(save_dir, '{:03d}.npy'.format(i)), rgbs[i] if as_bytes else to_byte(rgbs[i]))
+        for i in range(n):      # main.py:117-120 writes '{:03d}.png' of the 8-bit frame
+            write_png(os.path.join(save_dir, '{:03d}.png'.format(i)), rgbs[i] if as_bytes else to_byte(rgbs[i]))
     if verbose and rank == 0:
         print(f"rendered {n} frames in {time.time() - t:.3f}s")
     return rgbs
+
+
+def write_png(path, rgb8):
+    """[H,W,3] uint8 -> 8-bit RGB PNG (the reference uses imageio.imwrite, main.py:120; imageio is
+    not a dependency here, and a PNG is two zlib calls)."""
+    import struct
+    import zlib
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w, _ = rgb8.shape
+    rows = np.concatenate([np.zeros((h, 1), np.uint8), rgb8.reshape(h, w * 3)], 1).tobytes()   # filter 0 per row
+
+    def chunk(tag, data):
+        body = tag + data
+        return struct.pack(">I", len(data)) + body + struct.pack(">I", zlib.crc32(body) & 0xffffffff)
+    with open(path, "wb") as fh:
+        fh.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0))
+                 + chunk(b"IDAT", zlib.compress(rows, 6)) + chunk(b"IEND", b""))
 
 
 def create_model(args):

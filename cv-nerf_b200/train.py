@@ -15,6 +15,7 @@ Two entry levels:
 """
 import math
 import os
+import warnings
 
 import torch
 
@@ -60,6 +61,12 @@ def decayed_learning_rate(step, decay_steps, initial_lr, decay_rate=0.1):
     return initial_lr * (decay_rate ** (step / decay_steps))
 
 
+def rank_seed(seed, rank):
+    """Key of a rank's private random streams (pixel permutation, jitter, resampling uniforms, density
+    noise): distinct for every (seed, rank) pair, so data-parallel ranks never draw the same batch."""
+    return (int(seed) * 0x100000001B3 + int(rank) * 0x9E3779B1 + 1) & 0x7FFFFFFFFFFFFFFF
+
+
 class TrainStep:
     """One object per process (= per GPU).  ``step(image, pose)`` runs one iteration and returns
     the loss as a 1-element device tensor (no host synchronisation)."""
@@ -76,15 +83,21 @@ class TrainStep:
         self.perturb, self.noise, self.white_bkg, self.ndc = perturb, noise, bool(white_bkg), bool(ndc)
         self.near, self.far = near, far
         self.lr0, self.lr, self.lr_decay, self.betas, self.eps = lr, lr, lr_decay, betas, eps
-        self.seed, self.it = int(seed), 0
         self.pg = process_group
-        self.world = 1
+        self.world, self.rank = 1, 0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        # Data-parallel ranks must draw DIFFERENT ray batches (rays are sharded; identical batches
+        # would make N GPUs do the work of one): the rank is folded into the pixel-permutation key and
+        # into the generator that draws the stratified jitter / resampling uniforms / density noise.
+        self.seed, self.it = rank_seed(seed, self.rank), 0
         dev = next(coarse_model.parameters()).device
         if dev.type != "cuda":
             raise NerfB200Error("TrainStep needs the models on a CUDA device; there is no CPU fallback")
         self.dev = dev
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(self.seed)
         g = K.grad_blob_floats()
         self.blob = torch.zeros((2, g), dtype=torch.float32, device=dev)          # [coarse, fine]
         # Data parallel: put the blobs into symmetric (peer-mapped) memory so that the fused
@@ -98,10 +111,11 @@ class TrainStep:
                 self.symm = symm_mem.rendezvous(blob, group)
                 blob.zero_()
                 self.blob = blob
-                self.rank = torch.distributed.get_rank(process_group)
             except Exception as exc:                      # no peer access / unsupported backend
                 self.symm = None
                 self.symm_error = repr(exc)
+                warnings.warn(f"cv_nerf_b200.TrainStep: peer-memory gradient exchange unavailable ({exc!r}); "
+                              "using the NCCL all-reduce path")
         rows_c, rows_f = self.n_rays * self.s_c, self.n_rays * self.s_f
         self.act_c = torch.empty(K.act_bytes(rows_c), dtype=torch.uint8, device=dev)
         self.act_f = torch.empty(K.act_bytes(rows_f), dtype=torch.uint8, device=dev)
@@ -129,7 +143,8 @@ class TrainStep:
         if n > self.n_rays:
             raise NerfB200Error(f"TrainStep was sized for {self.n_rays} rays per step, got {n}")
         dev = self.dev
-        pick = lambda t, shape, fn: (t.to(dev).float().contiguous() if t is not None else fn(shape, device=dev))
+        pick = lambda t, shape, fn: (t.to(dev).float().contiguous() if t is not None
+                                     else fn(shape, device=dev, generator=self.gen))
         t_rand = None
         if self.perturb > 0.:
             t_rand = pick(draws.t_rand if draws else None, (n, self.s_c), torch.rand)
@@ -205,8 +220,10 @@ class TrainStep:
             if self.world > 1 and allreduce:
                 torch.distributed.all_reduce(self.blob, group=self.pg)
             for idx in range(2):
+                # without a reduction the blob holds this rank's own mean gradient: no 1/world
                 K.adam_step_blob(self.blob[idx], [p.data for p in self.params[idx]], self.m[idx], self.v[idx],
-                                 self.lr, self.betas, self.eps, self.it, grad_scale=1. / self.world)
+                                 self.lr, self.betas, self.eps, self.it,
+                                 grad_scale=1. / self.world if allreduce else 1.)
         _model.bump_param_epoch()
         # re-pack both networks' forward and transposed blobs in one launch
         bufs = [net.packed_buffers() for net in (self.coarse, self.fine)]
@@ -247,7 +264,7 @@ def save_checkpoint(path, step, coarse_model, fine_model, optimizer=None, train_
 
 
 def load_checkpoint(path, coarse_model, fine_model, optimizer=None, train_step=None, map_location=None):
-    blob = torch.load(path, map_location=map_location, weights_only=False)
+    blob = torch.load(path, map_location=map_location, weights_only=True)   # tensors, numbers, lists, dicts only
     coarse_model.load_state_dict(blob["coarse_state_dict"])
     fine_model.load_state_dict(blob["fine_state_dict"])
     _model.bump_param_epoch()

@@ -102,3 +102,18 @@ def grad_stats(got, want):
     rel = (got - want).norm().item() / max(denom, 1e-30)
     cos = float(torch.dot(got, want) / max(got.norm().item() * denom, 1e-30))
     return {"rel_l2": rel, "cos": cos, "max_abs": (got - want).abs().max().item(), "ref_norm": denom}
+
+
+# ------------------------------------------------------------------ measured-parity log
+def record(kind, values):
+    """Append one measured-parity line to gpurun_out/parity_log.jsonl (copied into profiles/ by hand
+    after a GPU run; the file is a by-product, tests never read it)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.environ.get("NERF_B200_PARITY_LOG", os.path.join(root, "gpurun_out", "parity_log.jsonl"))
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "a") as fh:
+            fh.write(json.dumps({"kind": kind, **values}) + "\n")
+    except OSError:
+        pass

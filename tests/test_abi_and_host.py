@@ -140,3 +140,29 @@ def test_checkpoint_round_trip_keeps_reference_keys(tmp_path):
     assert load_checkpoint(str(path), c, d) == 123
     assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), c.state_dict().values()))
     assert all(torch.equal(x, y) for x, y in zip(b.state_dict().values(), d.state_dict().values()))
+
+
+def test_write_png_round_trips(tmp_path):
+    """render_full writes '{:03d}.png' like the reference (main.py:117-120); decode the file by hand."""
+    import struct
+    import zlib
+    import numpy as np
+    from cv_nerf_b200.main import write_png
+    img = (np.arange(7 * 5 * 3, dtype=np.uint32) * 37 % 256).astype(np.uint8).reshape(7, 5, 3)
+    path = tmp_path / "000.png"
+    write_png(str(path), img)
+    data = path.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, hdr = 8, b"", None
+    while pos < len(data):
+        (n,), tag = struct.unpack(">I", data[pos:pos + 4]), data[pos + 4:pos + 8]
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xffffffff
+        if tag == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        if tag == b"IDAT":
+            idat += body
+        pos += 12 + n
+    assert hdr == (5, 7, 8, 2, 0, 0, 0)
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(7, 1 + 5 * 3)
+    assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(7, 5, 3), img)

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import nerf_oracle as O
-from tests.helpers import (bf16, decode_tile_image, focal_of, golden, grad_stats, load_model_params)
+from tests.helpers import (bf16, decode_tile_image, focal_of, golden, grad_stats, load_model_params, record)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -137,6 +137,8 @@ def test_field_backward_stages(rows, S):
         #     fp32 forward, which moves single elements by O(|dh|); judged by norm and direction
         st = grad_stats(got, dz_ref[i])
         print(f"dZ{i} vs emulation", se, "vs fp32 reference", st)
+        record("grad_stage", dict(rows=rows, tensor=f"dZ{i}", emu_rel_l2=se["rel_l2"], emu_cos=se["cos"],
+                                  fp32_rel_l2=st["rel_l2"], fp32_cos=st["cos"]))
         assert se["rel_l2"] <= 1e-2 and se["cos"] >= 0.9999, (i, se)
         assert st["rel_l2"] <= 0.15 and st["cos"] >= 0.99, (i, st)
 
@@ -151,6 +153,8 @@ def test_field_backward_stages(rows, S):
         se = grad_stats(got.cpu(), g_emu[name])
         st = grad_stats(got.cpu(), g_ref[name])
         print(name, "vs emulation", se, "vs fp32 reference", st)
+        record("grad_stage", dict(rows=rows, tensor=name, emu_rel_l2=se["rel_l2"], emu_cos=se["cos"],
+                                  fp32_rel_l2=st["rel_l2"], fp32_cos=st["cos"]))
         assert se["rel_l2"] <= 1e-2 and se["cos"] >= 0.9999, (name, se)
         assert st["rel_l2"] <= 0.15 and st["cos"] >= 0.99, (name, st)
     # accumulate mode adds
@@ -258,6 +262,8 @@ def test_train_step_gradients_match_reference_fixture(name):
             got_n = prm.grad.norm().item()
             rel_norm = abs(got_n - st["ref_norm"]) / max(st["ref_norm"], 1e-30)
             print(tag, k, "norm rel err", rel_norm, st)
+            record("grad_e2e", dict(fixture=name, net=tag, tensor=k, norm_rel_err=rel_norm, rel_l2=st["rel_l2"],
+                                    cos=st["cos"], n_flip=n_flip))
             worst_norm, worst_cos = max(worst_norm, rel_norm), min(worst_cos, st["cos"])
             # BF16 contractions + ReLU masks of a BF16 forward on <= 96 rays: norm within 5 %,
             # direction cos >= 0.98 per tensor (the kernels' own arithmetic is pinned to 1e-2 rel-L2,

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import nerf_oracle as O
-from tests.helpers import flip_aware_stats, focal_of, golden, load_model_params, psnr
+from tests.helpers import flip_aware_stats, focal_of, golden, load_model_params, psnr, record
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -51,7 +51,13 @@ def _render_both(name):
     return g, kw, rays, draws, (coarse_p, fine_p, odraws, h, w, f)
 
 
-@pytest.mark.parametrize("name", ["lego_test", "fern_test", "lego_train", "fern_train", "lego_test_stock"])
+# skull frames 0 and 60: NDC origins of ~2.3e8 -> |raw| ~ 1e6, every colour saturates
+DEGENERATE = ("lego_test_stock", "skull_f000_test", "skull_f060_test")
+
+
+@pytest.mark.parametrize("name", ["lego_test", "fern_test", "lego_train", "fern_train", "lego_test_stock",
+                                  "lego800_test", "skull_f000_test", "skull_f030_test", "skull_f060_test",
+                                  "skull_f090_test"])
 def test_render_matches_reference_fixture(name):
     from cv_nerf_b200 import main as M
     g, kw, rays, draws, (coarse_p, fine_p, odraws, h, w, f) = _render_both(name)
@@ -70,9 +76,10 @@ def test_render_matches_reference_fixture(name):
         got = (extras[key] if key == "rgb_c" else rgb).cpu()
         st = flip_aware_stats(got, torch.from_numpy(want), ours[sig_key][:, -1, 3].cpu(), ref[sig_key][:, -1, 3])
         print(name, key, st, "psnr_vs_ref", psnr(got, torch.from_numpy(want)))
+        record("render_fixture", dict(fixture=name, output=key, rays=int(got.shape[0]), **st))
         assert st["max_noflip"] <= RGB_TOL, (name, key, st)
         assert st["n_flip"] <= max(2, got.shape[0] // 20), (name, key, st)
-    if name != "lego_test_stock":
+    if name not in DEGENERATE:
         # opacity accumulated before the far sample (delta_last = 1e10 makes that one absorb the rest)
         acc = ref["w_f"][:, :-1].sum(-1).mean().item()
         assert 0.05 < acc < 0.999, f"test scene is degenerate (acc {acc})"

@@ -88,7 +88,12 @@ def _replay(g, extras=False):
                                         white_bkg=bool(g["white_bkg"]), extras=extras)
 
 
-@pytest.mark.parametrize("name", ["lego_test", "lego_test_stock", "fern_test", "lego_train", "fern_train"])
+RENDER_FIXTURES = ["lego_test", "lego_test_stock", "fern_test", "lego_train", "fern_train",
+                   # round 2 (make_golden_r02.py): headline 800x800 config, the reference's skull spiral poses
+                   "lego800_test", "skull_f000_test", "skull_f030_test", "skull_f060_test", "skull_f090_test"]
+
+
+@pytest.mark.parametrize("name", RENDER_FIXTURES)
 def test_render_matches_reference(golden_dir, name):
     g = _load(golden_dir, f"render_{name}.npz")
     sb = g["sigma_bias"]

@@ -97,3 +97,21 @@ def test_sharding_arithmetic():
             assert b[0] == 0 and b[-1] == h and all(y >= x for x, y in zip(b, b[1:]))
             assert max(y - x for x, y in zip(b, b[1:])) - min(y - x for x, y in zip(b, b[1:])) <= 1
     assert sorted(sum((P.frame_indices(120, 8, r) for r in range(8)), [])) == list(range(120))
+
+
+def _seed_case(rank, world, P):
+    from cv_nerf_b200.train import rank_seed
+    mine = torch.tensor([rank_seed(0, rank), rank_seed(5, rank)], dtype=torch.int64)
+    got = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(got, mine)
+    return [t.tolist() for t in got]
+
+
+def test_data_parallel_ranks_get_distinct_random_streams():
+    """TrainStep folds the rank into the key of its pixel permutation and of its draw generator: with
+    the default seed every rank would otherwise render the same batch (N GPUs doing the work of one)."""
+    res = _run(_seed_case)
+    seeds = res[0]
+    assert seeds == res[1], "all_gather disagreement"
+    assert seeds[0][0] != seeds[1][0] and seeds[0][1] != seeds[1][1]
+    assert len({s for per_rank in seeds for s in per_rank}) == 4

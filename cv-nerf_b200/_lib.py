@@ -41,6 +41,18 @@ _SIGNATURES = {
                                        c_float_p, ctypes.c_void_p]),
     "nerf_resample_merge": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_long, ctypes.c_int,
                                            ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "nerf_sample_coarse_rng": (ctypes.c_int, [c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_long,
+                                              c_float_p, ctypes.c_void_p]),
+    "nerf_resample_merge_rng": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_ulonglong, ctypes.c_long, ctypes.c_long,
+                                               ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "nerf_composite_fwd_rng": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_float,
+                                              ctypes.c_ulonglong, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int,
+                                              ctypes.c_int, c_float_p, c_float_p, ctypes.c_void_p]),
+    "nerf_composite_bwd_rng": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, ctypes.c_int, ctypes.c_float,
+                                              ctypes.c_ulonglong, ctypes.c_int, ctypes.c_long, ctypes.c_long, ctypes.c_int,
+                                              ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
+    "nerf_rng_fill": (ctypes.c_int, [ctypes.c_int, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_long, ctypes.c_long,
+                                     ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "nerf_packed_model_bytes": (ctypes.c_size_t, []),
     "nerf_pack_model": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p]),
     "nerf_viewdir_term": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_long,

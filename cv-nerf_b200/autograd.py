@@ -14,7 +14,10 @@ class CompositeFn(torch.autograd.Function):
     def forward(ctx, raw, z, dirs, noise, white_bkg):
         n, s = z.shape
         rgb, w = K.composite_fwd(raw.reshape(n, s, 4), z, dirs, noise, white_bkg)
-        ctx.save_for_backward(raw, z, dirs, noise)
+        # noise: None, a tensor, or a kernels.RngNoise key (the backward regenerates the same draws)
+        is_tensor = isinstance(noise, torch.Tensor)
+        ctx.save_for_backward(raw, z, dirs, noise if is_tensor else None)
+        ctx.noise_key = None if is_tensor else noise
         ctx.white_bkg = white_bkg
         ctx.set_materialize_grads(False)
         return rgb, w
@@ -22,6 +25,7 @@ class CompositeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_rgb, grad_w):
         raw, z, dirs, noise = ctx.saved_tensors
+        noise = ctx.noise_key if noise is None else noise
         n, s = z.shape
         if grad_rgb is None and grad_w is None:
             return None, None, None, None, None
@@ -32,8 +36,8 @@ class CompositeFn(torch.autograd.Function):
         return g.reshape(raw.shape), None, None, None, None
 
 
-def composite(raw, z, dirs, noise, white_bkg):
+def composite(raw, z, dirs, noise, white_bkg, want_weights=True):
     if torch.is_grad_enabled() and raw.requires_grad:
         return CompositeFn.apply(raw, z, dirs, noise, white_bkg)
     n, s = z.shape
-    return K.composite_fwd(raw.reshape(n, s, 4), z, dirs, noise, white_bkg)
+    return K.composite_fwd(raw.reshape(n, s, 4), z, dirs, noise, white_bkg, want_weights=want_weights)

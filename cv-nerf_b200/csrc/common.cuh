@@ -24,6 +24,26 @@ inline int arg_error(const char* what) {
     return NERF_ERR_ARG;
 }
 
+// Every entry point launches on the caller's stream; the CUDA *current device* must be the one that
+// owns the buffers (grid sizing reads its SM count, and a launch on another device's stream fails).
+// The guard looks the device up from an output pointer and switches to it for the duration of the
+// call -- a caller holding tensors on cuda:1 while cuda:0 is current gets the right launch.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const void* device_ptr) {
+        if (!device_ptr) return;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, device_ptr) != cudaSuccess) { cudaGetLastError(); return; }
+        if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (attr.device != prev && cudaSetDevice(attr.device) == cudaSuccess) switched = true;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 inline unsigned blocks_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace nerf

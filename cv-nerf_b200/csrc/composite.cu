@@ -11,6 +11,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace {
 
@@ -75,10 +76,36 @@ __device__ __forceinline__ SampleTerms sample_terms(float sigma, float noise, fl
     return s;
 }
 
-template <int C>
+// Density noise (main.py:186-189): a caller-provided [n,S] tensor (already scaled), or -- for
+// throughput runs -- standard normals drawn in place from the Philox counter (seed; ray0 + ray,
+// i / 4; stream) and scaled by `scale`.  Forward and backward regenerate identical values.
+struct NoiseSource {
+    const float* ptr;
+    float scale;
+    unsigned long long seed;
+    long ray0;
+    int stream;
+};
+
+template <bool RNG>
+struct NoiseReader {
+    float4 cache;
+    int group = -1;
+    __device__ __forceinline__ float at(const NoiseSource& ns, long ray, long base, int i) {
+        if (!RNG) return ns.ptr ? __ldg(ns.ptr + base + i) : 0.f;
+        if (!(ns.scale > 0.f)) return 0.f;
+        if ((i >> 2) != group) {
+            group = i >> 2;
+            cache = nerf::normal4(nerf::draw_group(ns.seed, ns.stream, ns.ray0 + ray, group));
+        }
+        return nerf::pick4(cache, i & 3) * ns.scale;
+    }
+};
+
+template <int C, bool RNG>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
-                     const float* __restrict__ dirs, int dir_stride, const float* __restrict__ noise,
+                     const float* __restrict__ dirs, int dir_stride, const NoiseSource noise,
                      long n, int S, int white_bkg, float* __restrict__ rgb_out,
                      float* __restrict__ weights_out) {
     const int lane = threadIdx.x & 31;
@@ -88,6 +115,7 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
     const long base = ray * S;
     float alpha[C], rgb[C][3];
     float prod = 1.f;
+    NoiseReader<RNG> nreader;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         int i = lane * C + c;
@@ -97,7 +125,7 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
             float4 r = __ldg(raw + base + i);
             float z0 = __ldg(z + base + i);
             float z1 = (i + 1 < S) ? __ldg(z + base + i + 1) : 0.f;
-            float nz = noise ? __ldg(noise + base + i) : 0.f;
+            float nz = nreader.at(noise, ray, base, i);
             SampleTerms s = sample_terms(r.w, nz, z0, z1, i + 1 == S, nrm);
             alpha[c] = s.alpha;
             prod *= s.t;
@@ -131,10 +159,10 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 //   dL/dalpha_i = T_i G_i - (sum_{j>i} w_j G_j) / t_i
 //   dL/dsigma_i = dL/dalpha_i * delta_i * (1 - alpha_i) * [sigma_i + noise_i > 0]
 //   dL/drgbraw_i = w_i * g * rgb_i (1 - rgb_i)
-template <int C>
+template <int C, bool RNG>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
-                     const float* __restrict__ dirs, int dir_stride, const float* __restrict__ noise,
+                     const float* __restrict__ dirs, int dir_stride, const NoiseSource noise,
                      long n, int S, int white_bkg, const float* __restrict__ grad_rgb,
                      const float* __restrict__ grad_w, float4* __restrict__ grad_raw) {
     const int lane = threadIdx.x & 31;
@@ -148,6 +176,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
     SampleTerms st[C];
     float rgb[C][3], G[C];
     float prod = 1.f;
+    NoiseReader<RNG> nreader;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         int i = lane * C + c;
@@ -158,7 +187,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
             float4 r = __ldg(raw + base + i);
             float z0 = __ldg(z + base + i);
             float z1 = (i + 1 < S) ? __ldg(z + base + i + 1) : 0.f;
-            float nz = noise ? __ldg(noise + base + i) : 0.f;
+            float nz = nreader.at(noise, ray, base, i);
             st[c] = sample_terms(r.w, nz, z0, z1, i + 1 == S, nrm);
             prod *= st[c].t;
             rgb[c][0] = sigmoidf(r.x); rgb[c][1] = sigmoidf(r.y); rgb[c][2] = sigmoidf(r.z);
@@ -286,12 +315,153 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
         out[ray * m + k] = invert_cdf(s_cdf[wib], s_bins[wib], B, __ldg(u + ray * m + k));
 }
 
+// ---- values-only sort of [coarse depths | new samples] (main.py:251) -------------------------------
+// In-register bitonic network over one warp: lane l holds KPL keys, element e = l*KPL + k.  Strides
+// below KPL are compare-exchanges inside a lane, the others one shuffle per key.
+template <int KPL, bool DESCENDING>
+__device__ __forceinline__ void warp_bitonic_sort(uint32_t (&a)[KPL], int lane) {
+    constexpr int N = 32 * KPL;
+#pragma unroll
+    for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride < KPL) {
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) {
+                    const int p = k ^ stride;
+                    if (p > k) {
+                        const bool up = ((((lane * KPL + k) & size) == 0) != DESCENDING);
+                        const uint32_t lo = min(a[k], a[p]), hi = max(a[k], a[p]);
+                        a[k] = up ? lo : hi;
+                        a[p] = up ? hi : lo;
+                    }
+                }
+            } else {
+                const int lstride = stride / KPL;
+                const bool lower = (lane & lstride) == 0;
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) {
+                    const bool up = ((((lane * KPL + k) & size) == 0) != DESCENDING);
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, a[k], lstride);
+                    a[k] = (lower == up) ? min(a[k], o) : max(a[k], o);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float decode_key(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Fast path (S <= 128 coarse depths, m <= 128 new samples; the reference uses 64 + 128).
+// One warp per ray, four samples per lane:
+//   1. cdf of the coarse weights in shared memory (lane-contiguous chunks + shuffle scan);
+//   2. inverse-CDF for the lane's four uniforms (read as one float4, or drawn in place from the
+//      Philox counter (seed; ray0 + ray, lane) when u == NULL);
+//   3. 128-key bitonic sort in registers (28 compare-exchange steps, 15 of them shuffles);
+//   4. the coarse depths, already ascending in every configuration of the reference, enter as the
+//      descending second half of a 256-key bitonic sequence (slots 4..7; padded with +inf keys), so
+//      ONE bitonic merge (8 steps) finishes the sort; an unsorted coarse row is sorted first by the
+//      same network.  Keys never pass through shared memory;
+//   5. lane l holds output positions [4l, 4l+4) and [128 + 4l, 128 + 4l + 4): two 16-byte stores.
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 resample_merge_kernel(const float* __restrict__ z_c, const float* __restrict__ w_c,
-                      const float* __restrict__ u, long n, int S, int m, float* __restrict__ z_f) {
-    __shared__ __align__(16) float s_cdf[WARPS_PER_BLOCK][MAX_SORT];
+                      const float* __restrict__ u, unsigned long long seed, long ray0, long n, int S, int m,
+                      float* __restrict__ z_f) {
+    __shared__ float s_cdf[WARPS_PER_BLOCK][128];
+    __shared__ float s_bins[WARPS_PER_BLOCK][128];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long ray = (long)blockIdx.x * WARPS_PER_BLOCK + wib;
+    if (ray >= n) return;
+    const int B = S - 1, total = S + m;
+    const float* zr = z_c + ray * S;
+    float* cdf = s_cdf[wib];
+    float* bins = s_bins[wib];
+    for (int i = lane; i < B; i += 32) bins[i] = .5f * (__ldg(zr + i + 1) + __ldg(zr + i));   // main.py:248
+    build_cdf(w_c + ray * S + 1, S - 2, cdf, lane);                                            // weights[..., 1:-1]
+    // second half of the final bitonic sequence: element 128 + t holds coarse rank 127 - t
+    uint32_t key[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = 127 - (lane * 4 + j);
+        key[4 + j] = c < S ? order_key(__ldg(zr + c)) : 0xffffffffu;
+    }
+    __syncwarp();
+    // first half: the new samples
+    float4 uu;
+    const float* ur = u ? u + ray * m : nullptr;
+    if (!u) {
+        uu = nerf::uniform4(nerf::draw_group(seed, NERF_RNG_STREAM_U, ray0 + ray, lane));
+    } else if ((m & 3) == 0) {
+        uu = lane * 4 < m ? __ldg(reinterpret_cast<const float4*>(ur) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        uu.x = lane * 4 + 0 < m ? __ldg(ur + lane * 4 + 0) : 0.f;
+        uu.y = lane * 4 + 1 < m ? __ldg(ur + lane * 4 + 1) : 0.f;
+        uu.z = lane * 4 + 2 < m ? __ldg(ur + lane * 4 + 2) : 0.f;
+        uu.w = lane * 4 + 3 < m ? __ldg(ur + lane * 4 + 3) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        key[j] = lane * 4 + j < m ? order_key(invert_cdf(cdf, bins, B, nerf::pick4(uu, j))) : 0xffffffffu;
+    uint32_t (&samp)[4] = reinterpret_cast<uint32_t (&)[4]>(key[0]);
+    uint32_t (&coarse)[4] = reinterpret_cast<uint32_t (&)[4]>(key[4]);
+    warp_bitonic_sort<4, false>(samp, lane);
+    // descending check of the coarse half: element t must be >= element t+1
+    bool ok = coarse[0] >= coarse[1] && coarse[1] >= coarse[2] && coarse[2] >= coarse[3];
+    const uint32_t next = __shfl_down_sync(0xffffffffu, coarse[0], 1);
+    ok = ok && (lane == 31 || coarse[3] >= next);
+    if (!__all_sync(0xffffffffu, ok)) warp_bitonic_sort<4, true>(coarse, lane);
+    // bitonic merge of the 256 keys, element e = h*128 + lane*4 + j with h = slot / 4
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t lo = min(key[j], key[4 + j]), hi = max(key[j], key[4 + j]);
+        key[j] = lo; key[4 + j] = hi;
+    }
+#pragma unroll
+    for (int lstride = 16; lstride > 0; lstride >>= 1) {
+        const bool lower = (lane & lstride) == 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, key[k], lstride);
+            key[k] = lower ? min(key[k], o) : max(key[k], o);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        uint32_t lo = min(key[h + 0], key[h + 2]), hi = max(key[h + 0], key[h + 2]);
+        key[h + 0] = lo; key[h + 2] = hi;
+        lo = min(key[h + 1], key[h + 3]); hi = max(key[h + 1], key[h + 3]);
+        key[h + 1] = lo; key[h + 3] = hi;
+        lo = min(key[h + 0], key[h + 1]); hi = max(key[h + 0], key[h + 1]);
+        key[h + 0] = lo; key[h + 1] = hi;
+        lo = min(key[h + 2], key[h + 3]); hi = max(key[h + 2], key[h + 3]);
+        key[h + 2] = lo; key[h + 3] = hi;
+    }
+    float* out = z_f + ray * total;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int p = h * 128 + lane * 4;
+        if ((total & 3) == 0) {
+            if (p < total)
+                *reinterpret_cast<float4*>(out + p) = make_float4(decode_key(key[4 * h]), decode_key(key[4 * h + 1]),
+                                                                  decode_key(key[4 * h + 2]), decode_key(key[4 * h + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (p + j < total) out[p + j] = decode_key(key[4 * h + j]);
+        }
+    }
+}
+
+// Other shapes (S > 128 or m > 128, S + m <= 256): rank sort in shared memory.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+resample_merge_general_kernel(const float* __restrict__ z_c, const float* __restrict__ w_c,
+                              const float* __restrict__ u, unsigned long long seed, long ray0, long n, int S,
+                              int m, float* __restrict__ z_f) {
+    __shared__ float s_cdf[WARPS_PER_BLOCK][MAX_SORT];
     __shared__ float s_bins[WARPS_PER_BLOCK][MAX_SORT];
-    __shared__ __align__(16) uint32_t s_key[WARPS_PER_BLOCK][MAX_SORT];
+    __shared__ uint32_t s_key[WARPS_PER_BLOCK][MAX_SORT];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long ray = (long)blockIdx.x * WARPS_PER_BLOCK + wib;
     if (ray >= n) return;
@@ -300,57 +470,18 @@ resample_merge_kernel(const float* __restrict__ z_c, const float* __restrict__ w
     for (int i = lane; i < S; i += 32) {
         float zi = __ldg(zr + i);
         s_key[wib][i] = order_key(zi);
-        if (i < B) s_bins[wib][i] = .5f * (__ldg(zr + i + 1) + zi);  // main.py:248
+        if (i < B) s_bins[wib][i] = .5f * (__ldg(zr + i + 1) + zi);
     }
-    build_cdf(w_c + ray * S + 1, S - 2, s_cdf[wib], lane);           // weights[..., 1:-1]
+    build_cdf(w_c + ray * S + 1, S - 2, s_cdf[wib], lane);
     __syncwarp();
-    for (int k = lane; k < m; k += 32)
-        s_key[wib][S + k] = order_key(invert_cdf(s_cdf[wib], s_bins[wib], B, __ldg(u + ray * m + k)));
+    for (int k = lane; k < m; k += 32) {
+        const float uk = u ? __ldg(u + ray * m + k)
+                           : nerf::pick4(nerf::uniform4(nerf::draw_group(seed, NERF_RNG_STREAM_U, ray0 + ray, k >> 2)), k & 3);
+        s_key[wib][S + k] = order_key(invert_cdf(s_cdf[wib], s_bins[wib], B, uk));
+    }
     __syncwarp();
-    // Values-only sort of [coarse depths | new samples] (main.py:251).  The coarse depths are already
-    // ascending in every configuration of the reference (linspace, stratified jitter keeps the
-    // order): then only the m new samples need ranking among themselves (m^2/32 compares per lane,
-    // four keys per shared-memory load) and the two sorted lists are merged by binary search.
-    // Ties: coarse first (strict / non-strict counts), which is a permutation and gives the same
-    // VALUES as any other tie order.  Unsorted coarse depths take the general rank sort.
-    bool sorted = true;
-    for (int i = lane; i + 1 < S; i += 32) sorted &= s_key[wib][i] <= s_key[wib][i + 1];
-    sorted = __all_sync(0xffffffffu, sorted);
     float* out = z_f + ray * total;
-    auto decode = [](uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); };
-    if (sorted && (m & 3) == 0 && (S & 3) == 0) {
-        uint32_t* samp = s_key[wib] + S;                     // m keys, 16-byte aligned (S % 4 == 0)
-        uint32_t* ranked = reinterpret_cast<uint32_t*>(s_cdf[wib]);   // cdf no longer needed
-        for (int i = lane; i < m; i += 32) {
-            const uint32_t ki = samp[i];
-            int rank = 0;
-            for (int j = 0; j < m; j += 4) {
-                const uint4 q = *reinterpret_cast<const uint4*>(samp + j);
-                rank += (q.x < ki) || (q.x == ki && j + 0 < i);
-                rank += (q.y < ki) || (q.y == ki && j + 1 < i);
-                rank += (q.z < ki) || (q.z == ki && j + 2 < i);
-                rank += (q.w < ki) || (q.w == ki && j + 3 < i);
-            }
-            ranked[rank] = ki;
-        }
-        __syncwarp();
-        for (int i = lane; i < total; i += 32) {
-            if (i < S) {                                     // coarse i: + #samples strictly below
-                const uint32_t k = s_key[wib][i];
-                int lo = 0, hi = m;
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (ranked[mid] < k) lo = mid + 1; else hi = mid; }
-                out[i + lo] = decode(k);
-            } else {                                         // sample of rank r: + #coarse at or below
-                const int r = i - S;
-                const uint32_t k = ranked[r];
-                int lo = 0, hi = S;
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (s_key[wib][mid] <= k) lo = mid + 1; else hi = mid; }
-                out[r + lo] = decode(k);
-            }
-        }
-        return;
-    }
-    // general rank sort: rank = #{j : key_j < key_i or (key_j == key_i and j < i)}
+    // rank = #{j : key_j < key_i or (key_j == key_i and j < i)}
     for (int i = lane; i < total; i += 32) {
         uint32_t ki = s_key[wib][i];
         int rank = 0;
@@ -358,7 +489,7 @@ resample_merge_kernel(const float* __restrict__ z_c, const float* __restrict__ w
             uint32_t kj = s_key[wib][j];
             rank += (kj < ki) || (kj == ki && j < i);
         }
-        out[rank] = decode(ki);
+        out[rank] = decode_key(ki);
     }
 }
 
@@ -380,39 +511,109 @@ int dispatch_c(int S, F&& f) {
 
 }  // namespace
 
-extern "C" int nerf_composite_fwd(const float* raw, const float* z, const float* dirs,
-                                  int dir_stride, const float* noise, long n, int S, int white_bkg,
-                                  float* rgb_out, float* weights_out, void* stream) {
-    if (n < 0 || S < 1 || (n > 0 && (!raw || !z || !dirs || !rgb_out))) return nerf::arg_error("nerf_composite_fwd");
+static int launch_composite_fwd(const char* what, const float* raw, const float* z, const float* dirs, int dir_stride,
+                                const NoiseSource& noise, long n, int S, int white_bkg, float* rgb_out,
+                                float* weights_out, void* stream) {
+    if (n < 0 || S < 1 || (n > 0 && (!raw || !z || !dirs || !rgb_out))) return nerf::arg_error(what);
     if (n == 0) return 0;
     unsigned grid = nerf::blocks_for(n, WARPS_PER_BLOCK);
     int rc = dispatch_c(S, [&](auto c) {
-        composite_fwd_kernel<decltype(c)::value><<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-            (const float4*)raw, z, dirs, dir_stride, noise, n, S, white_bkg, rgb_out, weights_out);
+        if (noise.ptr || !(noise.scale > 0.f))
+            composite_fwd_kernel<decltype(c)::value, false><<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                (const float4*)raw, z, dirs, dir_stride, noise, n, S, white_bkg, rgb_out, weights_out);
+        else
+            composite_fwd_kernel<decltype(c)::value, true><<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                (const float4*)raw, z, dirs, dir_stride, noise, n, S, white_bkg, rgb_out, weights_out);
     });
-    if (rc) { nerf::set_last_error("nerf_composite_fwd: S=%d > 256 unsupported", S); return NERF_ERR_UNSUPPORTED; }
-    return nerf::check_launch("nerf_composite_fwd");
+    if (rc) { nerf::set_last_error("%s: S=%d > 256 unsupported", what, S); return NERF_ERR_UNSUPPORTED; }
+    return nerf::check_launch(what);
+}
+
+static int launch_composite_bwd(const char* what, const float* raw, const float* z, const float* dirs, int dir_stride,
+                                const NoiseSource& noise, long n, int S, int white_bkg, const float* grad_rgb,
+                                const float* grad_weights, float* grad_raw, void* stream) {
+    if (n < 0 || S < 1 || (n > 0 && (!raw || !z || !dirs || !grad_rgb || !grad_raw))) return nerf::arg_error(what);
+    if (n == 0) return 0;
+    unsigned grid = nerf::blocks_for(n, WARPS_PER_BLOCK);
+    int rc = dispatch_c(S, [&](auto c) {
+        if (noise.ptr || !(noise.scale > 0.f))
+            composite_bwd_kernel<decltype(c)::value, false><<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                (const float4*)raw, z, dirs, dir_stride, noise, n, S, white_bkg, grad_rgb, grad_weights,
+                (float4*)grad_raw);
+        else
+            composite_bwd_kernel<decltype(c)::value, true><<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+                (const float4*)raw, z, dirs, dir_stride, noise, n, S, white_bkg, grad_rgb, grad_weights,
+                (float4*)grad_raw);
+    });
+    if (rc) { nerf::set_last_error("%s: S=%d > 256 unsupported", what, S); return NERF_ERR_UNSUPPORTED; }
+    return nerf::check_launch(what);
+}
+
+extern "C" int nerf_composite_fwd(const float* raw, const float* z, const float* dirs,
+                                  int dir_stride, const float* noise, long n, int S, int white_bkg,
+                                  float* rgb_out, float* weights_out, void* stream) {
+    nerf::DeviceGuard device_guard(rgb_out);
+    return launch_composite_fwd("nerf_composite_fwd", raw, z, dirs, dir_stride, NoiseSource{noise, 0.f, 0ull, 0, 0}, n, S,
+                                white_bkg, rgb_out, weights_out, stream);
+}
+
+extern "C" int nerf_composite_fwd_rng(const float* raw, const float* z, const float* dirs, int dir_stride,
+                                      float noise_scale, unsigned long long seed, int rng_stream, long ray0, long n,
+                                      int S, int white_bkg, float* rgb_out, float* weights_out, void* stream) {
+    nerf::DeviceGuard device_guard(rgb_out);
+    return launch_composite_fwd("nerf_composite_fwd_rng", raw, z, dirs, dir_stride,
+                                NoiseSource{nullptr, noise_scale, seed, ray0, rng_stream}, n, S, white_bkg, rgb_out,
+                                weights_out, stream);
 }
 
 extern "C" int nerf_composite_bwd(const float* raw, const float* z, const float* dirs,
                                   int dir_stride, const float* noise, long n, int S, int white_bkg,
                                   const float* grad_rgb, const float* grad_weights, float* grad_raw,
                                   void* stream) {
-    if (n < 0 || S < 1 || (n > 0 && (!raw || !z || !dirs || !grad_rgb || !grad_raw)))
-        return nerf::arg_error("nerf_composite_bwd");
-    if (n == 0) return 0;
-    unsigned grid = nerf::blocks_for(n, WARPS_PER_BLOCK);
-    int rc = dispatch_c(S, [&](auto c) {
-        composite_bwd_kernel<decltype(c)::value><<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-            (const float4*)raw, z, dirs, dir_stride, noise, n, S, white_bkg, grad_rgb, grad_weights,
-            (float4*)grad_raw);
-    });
-    if (rc) { nerf::set_last_error("nerf_composite_bwd: S=%d > 256 unsupported", S); return NERF_ERR_UNSUPPORTED; }
-    return nerf::check_launch("nerf_composite_bwd");
+    nerf::DeviceGuard device_guard(grad_raw);
+    return launch_composite_bwd("nerf_composite_bwd", raw, z, dirs, dir_stride, NoiseSource{noise, 0.f, 0ull, 0, 0}, n, S,
+                                white_bkg, grad_rgb, grad_weights, grad_raw, stream);
+}
+
+extern "C" int nerf_composite_bwd_rng(const float* raw, const float* z, const float* dirs, int dir_stride,
+                                      float noise_scale, unsigned long long seed, int rng_stream, long ray0, long n,
+                                      int S, int white_bkg, const float* grad_rgb, const float* grad_weights,
+                                      float* grad_raw, void* stream) {
+    nerf::DeviceGuard device_guard(grad_raw);
+    return launch_composite_bwd("nerf_composite_bwd_rng", raw, z, dirs, dir_stride,
+                                NoiseSource{nullptr, noise_scale, seed, ray0, rng_stream}, n, S, white_bkg, grad_rgb,
+                                grad_weights, grad_raw, stream);
+}
+
+// The numbers the *_rng entry points draw, written out (tests feed them to the CPU oracle; callers
+// that want the reference's `extras` can look at them).  kind 0: uniforms, 1: standard normals.
+__global__ void rng_fill_kernel(int kind, unsigned long long seed, int stream_id, long ray0, long n, int cols,
+                                float* __restrict__ out) {
+    const int groups = (cols + 3) / 4;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * groups) return;
+    const long ray = idx / groups;
+    const int g = (int)(idx % groups);
+    const uint4 w = nerf::draw_group(seed, stream_id, ray0 + ray, g);
+    const float4 v = kind == 0 ? nerf::uniform4(w) : nerf::normal4(w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (g * 4 + j < cols) out[ray * cols + g * 4 + j] = nerf::pick4(v, j);
+}
+
+extern "C" int nerf_rng_fill(int kind, unsigned long long seed, int rng_stream, long ray0, long n, int cols,
+                             float* out, void* stream) {
+    nerf::DeviceGuard device_guard(out);
+    if (n < 0 || cols < 0 || kind < 0 || kind > 1 || (n > 0 && cols > 0 && !out)) return nerf::arg_error("nerf_rng_fill");
+    if (n == 0 || cols == 0) return 0;
+    const long work = n * ((cols + 3) / 4);
+    rng_fill_kernel<<<nerf::blocks_for(work, 256), 256, 0, (cudaStream_t)stream>>>(kind, seed, rng_stream, ray0, n, cols, out);
+    return nerf::check_launch("nerf_rng_fill");
 }
 
 extern "C" int nerf_sample_pdf(const float* bins, const float* weights, const float* u, long n,
                                int B, int m, float* samples_out, void* stream) {
+    nerf::DeviceGuard device_guard(samples_out);
     if (n < 0 || B < 2 || m < 0 || (n > 0 && m > 0 && (!bins || !weights || !u || !samples_out)))
         return nerf::arg_error("nerf_sample_pdf");
     if (B > MAX_SORT) { nerf::set_last_error("nerf_sample_pdf: B=%d > 256 unsupported", B); return NERF_ERR_UNSUPPORTED; }
@@ -422,19 +623,36 @@ extern "C" int nerf_sample_pdf(const float* bins, const float* weights, const fl
     return nerf::check_launch("nerf_sample_pdf");
 }
 
+static int launch_resample_merge(const char* what, const float* z_c, const float* w_c, const float* u,
+                                 unsigned long long seed, long ray0, long n, int S, int m, float* z_f, void* stream) {
+    if (n < 0 || S < 3 || m < 0 || (n > 0 && (!z_c || !w_c || !z_f))) return nerf::arg_error(what);
+    if (S + m > MAX_SORT) { nerf::set_last_error("%s: S+m=%d > 256 unsupported", what, S + m); return NERF_ERR_UNSUPPORTED; }
+    if (n == 0) return 0;
+    const unsigned grid = nerf::blocks_for(n, WARPS_PER_BLOCK);
+    if (S <= 128 && m <= 128)
+        resample_merge_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(z_c, w_c, u, seed, ray0, n, S, m, z_f);
+    else
+        resample_merge_general_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(z_c, w_c, u, seed, ray0, n,
+                                                                                        S, m, z_f);
+    return nerf::check_launch(what);
+}
+
 extern "C" int nerf_resample_merge(const float* z_c, const float* w_c, const float* u, long n, int S,
                                    int m, float* z_f, void* stream) {
-    if (n < 0 || S < 3 || m < 0 || (n > 0 && (!z_c || !w_c || !z_f || (m > 0 && !u))))
-        return nerf::arg_error("nerf_resample_merge");
-    if (S + m > MAX_SORT) { nerf::set_last_error("nerf_resample_merge: S+m=%d > 256 unsupported", S + m); return NERF_ERR_UNSUPPORTED; }
-    if (n == 0) return 0;
-    resample_merge_kernel<<<nerf::blocks_for(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
-        z_c, w_c, u, n, S, m, z_f);
-    return nerf::check_launch("nerf_resample_merge");
+    nerf::DeviceGuard device_guard(z_f);
+    if (m > 0 && n > 0 && !u) return nerf::arg_error("nerf_resample_merge");
+    return launch_resample_merge("nerf_resample_merge", z_c, w_c, u, 0ull, 0, n, S, m, z_f, stream);
+}
+
+extern "C" int nerf_resample_merge_rng(const float* z_c, const float* w_c, unsigned long long seed, long ray0,
+                                       long n, int S, int m, float* z_f, void* stream) {
+    nerf::DeviceGuard device_guard(z_f);
+    return launch_resample_merge("nerf_resample_merge_rng", z_c, w_c, nullptr, seed, ray0, n, S, m, z_f, stream);
 }
 
 extern "C" int nerf_composite_maps(const float* weights, const float* z, long n, int S, float* maps_out,
                                    void* stream) {
+    nerf::DeviceGuard device_guard(maps_out);
     if (n < 0 || S < 1 || (n > 0 && (!weights || !z || !maps_out))) return nerf::arg_error("nerf_composite_maps");
     if (n == 0) return 0;
     composite_maps_kernel<<<nerf::blocks_for(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(

@@ -226,6 +226,7 @@ extern "C" size_t nerf_grad_blob_bytes(void) { return (size_t)nerf::kGradFloats 
 
 // dW / db of l1..l10 (tensor-core layers) accumulated into grad_blob (+=).
 extern "C" int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, float* grad_blob, void* stream) {
+    nerf::DeviceGuard device_guard(grad_blob);
     if (M < 0 || (M > 0 && (!act_save || !dz || !grad_blob))) return nerf::arg_error("nerf_mlp_bwd_dw");
     if (M == 0) return 0;
     static int sm_count = 0;

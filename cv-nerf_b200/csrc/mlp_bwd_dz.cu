@@ -339,6 +339,7 @@ extern "C" size_t nerf_mlp_dz_bytes(long M) {
 
 extern "C" int nerf_mlp_bwd_dz(const void* packed_bwd, const float* grad_raw, const void* act_save, long M,
                                void* dz_out, void* stream) {
+    nerf::DeviceGuard device_guard(dz_out);
     if (M < 0 || (M > 0 && (!packed_bwd || !grad_raw || !act_save || !dz_out))) return nerf::arg_error("nerf_mlp_bwd_dz");
     if (M == 0) return 0;
     if (((uintptr_t)act_save | (uintptr_t)dz_out | (uintptr_t)grad_raw) & 15)

@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restr
 
 extern "C" int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, long M, float* grad_blob,
                                   void* stream) {
+    nerf::DeviceGuard device_guard(grad_blob);
     if (M < 0 || (M > 0 && (!act_save || !grad_raw || !grad_blob))) return nerf::arg_error("nerf_mlp_bwd_heads");
     if (M == 0) return 0;
     const long n_tiles = (M + kTileRows - 1) / kTileRows;
@@ -260,6 +261,7 @@ extern "C" int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, l
 
 extern "C" int nerf_viewdir_term_bwd(const void* dz, const float* dirs, int dir_stride, int embedded, long M,
                                      int vterm_div, float* grad_blob, void* stream) {
+    nerf::DeviceGuard device_guard(grad_blob);
     if (M < 0 || vterm_div < 1 || (M > 0 && (!dz || !dirs || !grad_blob))) return nerf::arg_error("nerf_viewdir_term_bwd");
     if (M == 0) return 0;
     const long count = (M + vterm_div - 1) / vterm_div;
@@ -273,6 +275,7 @@ extern "C" int nerf_viewdir_term_bwd(const void* dz, const float* dirs, int dir_
 }
 
 extern "C" int nerf_grad_unpack(const float* grad_blob, float* const* host_grads, int accumulate, void* stream) {
+    nerf::DeviceGuard device_guard(grad_blob);
     if (!grad_blob || !host_grads) return nerf::arg_error("nerf_grad_unpack");
     UnpackPtrs out;
     for (int i = 0; i < NERF_N_PARAM_TENSORS; ++i) {
@@ -285,6 +288,7 @@ extern "C" int nerf_grad_unpack(const float* grad_blob, float* const* host_grads
 
 extern "C" int nerf_mse_loss_grad(const float* x, const float* target, long n, float* grad_out, float* loss_accum,
                                   void* stream) {
+    nerf::DeviceGuard device_guard(loss_accum);
     if (n < 0 || (n > 0 && (!x || !target))) return nerf::arg_error("nerf_mse_loss_grad");
     if (n == 0) return 0;
     long grid = (n + 255) / 256;

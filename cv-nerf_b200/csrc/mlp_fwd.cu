@@ -2054,6 +2054,7 @@ int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0,
 extern "C" int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, const float* in1,
                             int in_stride, long M, int S, const float* vterm, int vterm_div,
                             float* raw_out, void* act_save, void* stream) {
+    nerf::DeviceGuard device_guard(raw_out);
     FwdParams P;
     int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out);
     if (rc) return rc;
@@ -2069,6 +2070,7 @@ extern "C" size_t nerf_model_host_tail_bytes(void) { return sizeof(ConstTail); }
 // Copies the part of the packed blob's fp32 tail that the epilogues consume into HOST memory
 // (asynchronously: synchronise the stream before passing it to nerf_mlp_fwd_host_tail).
 extern "C" int nerf_model_host_tail(const void* packed, void* host_tail_out, void* stream) {
+    nerf::DeviceGuard device_guard(packed);
     if (!packed || !host_tail_out) return nerf::arg_error("nerf_model_host_tail");
     cudaError_t e = cudaMemcpyAsync(host_tail_out, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail),
                                     cudaMemcpyDeviceToHost, (cudaStream_t)stream);
@@ -2083,6 +2085,7 @@ extern "C" int nerf_model_host_tail(const void* packed, void* host_tail_out, voi
 extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail, int in_mode, const float* in0,
                                       const float* in1, int in_stride, long M, int S, const float* vterm,
                                       int vterm_div, float* raw_out, void* stream) {
+    nerf::DeviceGuard device_guard(raw_out);
     if (!host_tail) return nerf::arg_error("nerf_mlp_fwd_host_tail: host_tail");
     FwdParams P;
     int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out);
@@ -2111,6 +2114,7 @@ extern "C" int nerf_mlp_fwd_use_pairs(int enable) {
 extern "C" int nerf_mlp_fwd_probe(const void* packed, int in_mode, const float* in0, const float* in1,
                                   int in_stride, long M, int S, const float* vterm, int vterm_div,
                                   float* raw_out, int probe_layer, float* probe_out, void* stream) {
+    nerf::DeviceGuard device_guard(raw_out);
     FwdParams P;
     int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out);
     if (rc) return rc;
@@ -2124,6 +2128,7 @@ extern "C" int nerf_mlp_fwd_probe(const void* packed, int in_mode, const float* 
 extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const float* z, long M, int S,
                                   const float* vterm, float* raw_out, int variant, long long* stats_out,
                                   void* stream) {
+    nerf::DeviceGuard device_guard(raw_out);
     FwdParams P;
     int rc = fill_params(P, packed, NERF_IN_RAYS, rays, z, 0, M, S, vterm, S, raw_out);
     if (rc) return rc;

@@ -245,6 +245,7 @@ __global__ void freq_encode_kernel(const float* __restrict__ x, long n, int dim,
 }  // namespace
 
 extern "C" int nerf_freq_encode(const float* x, long n, int dim, int n_freq, float* out, void* stream) {
+    nerf::DeviceGuard device_guard(out);
     if (n < 0 || dim < 1 || n_freq < 0 || (n > 0 && (!x || !out))) return nerf::arg_error("nerf_freq_encode");
     if (n == 0) return 0;
     freq_encode_kernel<<<nerf::blocks_for(n * dim, 256), 256, 0, (cudaStream_t)stream>>>(x, n, dim, n_freq, out);
@@ -254,6 +255,7 @@ extern "C" int nerf_freq_encode(const float* x, long n, int dim, int n_freq, flo
 extern "C" size_t nerf_packed_model_bytes(void) { return nerf::kPackedBytes; }
 
 extern "C" int nerf_pack_model(const float* const* host_params, void* packed_out, void* stream) {
+    nerf::DeviceGuard device_guard(packed_out);
     if (!host_params || !packed_out) return nerf::arg_error("nerf_pack_model");
     ParamPtrs p;
     for (int i = 0; i < 12; ++i) {
@@ -272,6 +274,7 @@ extern "C" int nerf_pack_model(const float* const* host_params, void* packed_out
 extern "C" size_t nerf_packed_model_bwd_bytes(void) { return nerf::kBwdPackedBytes; }
 
 extern "C" int nerf_pack_model_bwd(const float* const* host_params, void* packed_out, void* stream) {
+    nerf::DeviceGuard device_guard(packed_out);
     if (!host_params || !packed_out) return nerf::arg_error("nerf_pack_model_bwd");
     ParamPtrs p;
     for (int i = 0; i < 12; ++i) {
@@ -289,6 +292,7 @@ extern "C" int nerf_pack_model_bwd(const float* const* host_params, void* packed
 
 extern "C" int nerf_pack_models_train(int n_models, const float* const* host_params, void* const* packed_out,
                                       void* const* packed_bwd_out, void* stream) {
+    nerf::DeviceGuard device_guard((n_models > 0 && packed_out ? packed_out[0] : nullptr));
     if (n_models < 1 || n_models > 2 || !host_params || !packed_out || !packed_bwd_out)
         return nerf::arg_error("nerf_pack_models_train");
     PackAll A;
@@ -308,6 +312,7 @@ extern "C" int nerf_pack_models_train(int n_models, const float* const* host_par
 
 extern "C" int nerf_viewdir_term(const void* packed, const float* dirs, int dir_stride, int embedded,
                                  long count, float* out, void* stream) {
+    nerf::DeviceGuard device_guard(out);
     if (count < 0 || (count > 0 && (!packed || !dirs || !out))) return nerf::arg_error("nerf_viewdir_term");
     if (count == 0) return 0;
     const float* tail = (const float*)((const uint8_t*)packed + kWeightBytes);

@@ -235,6 +235,7 @@ int fill_scalars(AdamScalars& s, float lr, float beta1, float beta2, float eps, 
 extern "C" int nerf_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                               float* const* exp_avg_sq, const long* sizes, float lr, float beta1, float beta2,
                               float eps, long step, float grad_scale, void* stream) {
+    nerf::DeviceGuard device_guard((n_tensors > 0 && params ? params[0] : nullptr));
     if (n_tensors < 0 || (n_tensors > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !sizes)))
         return nerf::arg_error("nerf_adam_step");
     AdamScalars s;
@@ -259,6 +260,7 @@ extern "C" int nerf_adam_step(int n_tensors, float* const* params, const float* 
 extern "C" int nerf_adam_step_blob(const float* grad_blob, float* const* params, float* const* exp_avg,
                                    float* const* exp_avg_sq, float lr, float beta1, float beta2, float eps,
                                    long step, float grad_scale, void* stream) {
+    nerf::DeviceGuard device_guard(grad_blob);
     if (!grad_blob || !params || !exp_avg || !exp_avg_sq) return nerf::arg_error("nerf_adam_step_blob");
     AdamScalars s;
     int rc = fill_scalars(s, lr, beta1, beta2, eps, step, grad_scale);
@@ -275,6 +277,7 @@ extern "C" int nerf_adam_step_blob(const float* grad_blob, float* const* params,
 extern "C" int nerf_adam_step_blob_peers(const float* const* peer_blobs, int world, float* const* params,
                                          float* const* exp_avg, float* const* exp_avg_sq, float lr, float beta1,
                                          float beta2, float eps, long step, float grad_scale, void* stream) {
+    nerf::DeviceGuard device_guard((params ? params[0] : nullptr));
     if (!peer_blobs || world < 1 || world > kMaxPeers || !params || !exp_avg || !exp_avg_sq)
         return nerf::arg_error("nerf_adam_step_blob_peers");
     AdamScalars s;
@@ -299,6 +302,7 @@ extern "C" int nerf_train_rays(int H, int W, float focal, float cw, float ch, co
                                unsigned long long seed, int crop_r0, int crop_c0, int crop_h, int crop_w, long n,
                                int ndc, float near, float far, const float* image, float* rays_out,
                                float* target_out, int* pix_out, void* stream) {
+    nerf::DeviceGuard device_guard(rays_out);
     if (H <= 0 || W <= 0 || !pose || n < 0 || (n > 0 && !rays_out)) return nerf::arg_error("nerf_train_rays");
     if (n == 0) return 0;
     int half_bits = 1;

@@ -10,6 +10,7 @@
 // The kernels are HBM-write bound (44 B/ray); one thread per ray, rays_out written as 11
 // consecutive floats per thread (consecutive threads -> consecutive 44 B records).
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace {
 
@@ -145,6 +146,29 @@ __global__ void sample_coarse_kernel(const float* __restrict__ rays, long n, int
     z_out[idx] = z;
 }
 
+// The same with the jitter drawn in place: one thread per (ray, group of four samples).
+__global__ void sample_coarse_rng_kernel(const float* __restrict__ rays, long n, int S, unsigned long long seed,
+                                         long ray0, float* __restrict__ z_out) {
+    const int groups = (S + 3) / 4;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * groups) return;
+    const long ray = idx / groups;
+    const int g = (int)(idx % groups);
+    const float near = __ldg(rays + NERF_RAY_STRIDE * ray + 6), far = __ldg(rays + NERF_RAY_STRIDE * ray + 7);
+    const float step = __fdiv_rn(1.f, (float)(S - 1));
+    const float4 t = nerf::uniform4(nerf::draw_group(seed, NERF_RNG_STREAM_T_RAND, ray0 + ray, g));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = g * 4 + j;
+        if (i >= S) break;
+        const float z = coarse_z(i, S, step, near, far);
+        float lo = z, hi = z;
+        if (i > 0) lo = __fmul_rn(.5f, __fadd_rn(z, coarse_z(i - 1, S, step, near, far)));
+        if (i < S - 1) hi = __fmul_rn(.5f, __fadd_rn(coarse_z(i + 1, S, step, near, far), z));
+        z_out[ray * S + i] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), nerf::pick4(t, j)));
+    }
+}
+
 // to_byte / cont_to_byte8_im (model.py:134, utils.py:57): (255 * clip(x, 0, 1)).astype(uint8);
 // numpy multiplies in fp32 and astype truncates toward zero.  4 values per thread.
 __global__ void to_byte_kernel(const float* __restrict__ x, long n, uint8_t* __restrict__ out) {
@@ -166,6 +190,7 @@ __global__ void to_byte_kernel(const float* __restrict__ x, long n, uint8_t* __r
 }  // namespace
 
 extern "C" int nerf_to_byte(const float* x, long n, unsigned char* out, void* stream) {
+    nerf::DeviceGuard device_guard(out);
     if (n < 0 || (n > 0 && (!x || !out))) return nerf::arg_error("nerf_to_byte");
     if (n == 0) return 0;
     to_byte_kernel<<<nerf::blocks_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, n, out);
@@ -174,6 +199,7 @@ extern "C" int nerf_to_byte(const float* x, long n, unsigned char* out, void* st
 
 extern "C" int nerf_compute_rays(int H, int W, float focal, const float* pose, int row0, int row1,
                                  float* origins_out, float* dirs_out, void* stream) {
+    nerf::DeviceGuard device_guard(dirs_out);
     if (H <= 0 || W <= 0 || !pose || !dirs_out || row0 < 0 || row1 > H || row0 > row1)
         return nerf::arg_error("nerf_compute_rays");
     long n = (long)(row1 - row0) * W;
@@ -185,6 +211,7 @@ extern "C" int nerf_compute_rays(int H, int W, float focal, const float* pose, i
 
 extern "C" int nerf_get_ndc(float cw, float ch, float near_plane, const float* o, const float* d,
                             long n, float* o_out, float* d_out, void* stream) {
+    nerf::DeviceGuard device_guard(o_out);
     if (n < 0 || (n > 0 && (!o || !d || !o_out || !d_out))) return nerf::arg_error("nerf_get_ndc");
     if (n == 0) return 0;
     get_ndc_kernel<<<nerf::blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(cw, ch, near_plane, o, d,
@@ -195,6 +222,7 @@ extern "C" int nerf_get_ndc(float cw, float ch, float near_plane, const float* o
 extern "C" int nerf_pack_rays(int H, int W, float focal, float cw, float ch, const float* pose,
                               int row0, int row1, const float* rays_o, const float* rays_d, long n,
                               int ndc, float near, float far, float* rays_out, void* stream) {
+    nerf::DeviceGuard device_guard(rays_out);
     if (pose) {
         if (H <= 0 || W <= 0 || row0 < 0 || row1 > H || row0 > row1) return nerf::arg_error("nerf_pack_rays rows");
         n = (long)(row1 - row0) * W;
@@ -209,8 +237,19 @@ extern "C" int nerf_pack_rays(int H, int W, float focal, float cw, float ch, con
     return nerf::check_launch("nerf_pack_rays");
 }
 
+extern "C" int nerf_sample_coarse_rng(const float* rays, long n, int S, unsigned long long seed, long ray0,
+                                      float* z_out, void* stream) {
+    nerf::DeviceGuard device_guard(z_out);
+    if (n < 0 || S < 2 || (n > 0 && (!rays || !z_out))) return nerf::arg_error("nerf_sample_coarse_rng");
+    if (n == 0) return 0;
+    sample_coarse_rng_kernel<<<nerf::blocks_for(n * ((S + 3) / 4), 256), 256, 0, (cudaStream_t)stream>>>(rays, n, S, seed,
+                                                                                                     ray0, z_out);
+    return nerf::check_launch("nerf_sample_coarse_rng");
+}
+
 extern "C" int nerf_sample_coarse(const float* rays, long n, int S, const float* t_rand,
                                   float* z_out, void* stream) {
+    nerf::DeviceGuard device_guard(z_out);
     if (n < 0 || S < 2 || (n > 0 && (!rays || !z_out))) return nerf::arg_error("nerf_sample_coarse");
     if (n == 0) return 0;
     sample_coarse_kernel<<<nerf::blocks_for(n * S, 256), 256, 0, (cudaStream_t)stream>>>(rays, n, S, t_rand,

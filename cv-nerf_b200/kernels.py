@@ -5,6 +5,7 @@ PyTorch's job here, nothing else) and launches on the tensor's current stream.  
 file computes anything on the host.
 """
 import ctypes
+import dataclasses
 
 import numpy as np
 import torch
@@ -94,10 +95,44 @@ def pack_rays(height, width, focal, *, pose=None, row0=0, row1=None, rays_o=None
     return out
 
 
-def sample_coarse(rays, n_samples, t_rand=None):
+RNG_T_RAND, RNG_U, RNG_NOISE_C, RNG_NOISE_F = 0, 1, 2, 3      # NERF_RNG_STREAM_* of include/nerf_b200.h
+
+
+@dataclasses.dataclass(frozen=True)
+class Rng:
+    """Key of the in-kernel draws of one render_rays call: Philox seed and the global index of the
+    batch's first ray (so that chunked / row-sharded calls draw what the whole call would)."""
+    seed: int
+    ray0: int = 0
+
+    def shifted(self, rays):
+        return Rng(self.seed, self.ray0 + int(rays))
+
+    @property
+    def key(self):
+        return self.seed & 0xFFFFFFFFFFFFFFFF
+
+
+def rng_fill(kind, rng, stream_id, n, cols, device):
+    """The numbers the *_rng kernels draw for rows [rng.ray0, rng.ray0+n) of a stream, as a tensor
+    (kind 'uniform' | 'normal')."""
+    lib = _lib.load()
+    out = torch.empty((n, cols), dtype=torch.float32, device=device)
+    check(lib.nerf_rng_fill(0 if kind == "uniform" else 1, rng.key, stream_id, rng.ray0, n, cols, ptr(out),
+                            torch.cuda.current_stream(out.device).cuda_stream), "nerf_rng_fill")
+    return out
+
+
+def sample_coarse(rays, n_samples, t_rand=None, rng=None):
+    """Coarse depths; stratified jitter from the tensor ``t_rand`` or, with ``rng``, drawn in place."""
     lib = _lib.load()
     n = rays.shape[0]
     z = torch.empty((n, n_samples), dtype=torch.float32, device=rays.device)
+    if rng is not None:
+        assert t_rand is None
+        check(lib.nerf_sample_coarse_rng(ptr(rays), n, n_samples, rng.key, rng.ray0, ptr(z), stream_of(rays)),
+              "nerf_sample_coarse_rng")
+        return z
     if t_rand is not None:
         t_rand = f32c(t_rand, rays.device)
         assert t_rand.shape == z.shape
@@ -114,14 +149,28 @@ def _dir_arg(dirs):
     return dirs, dirs.data_ptr(), 3
 
 
+@dataclasses.dataclass(frozen=True)
+class RngNoise:
+    """Density noise drawn inside the compositing kernels: scale * N(0,1) from (rng, stream)."""
+    scale: float
+    rng: Rng
+    stream: int
+
+
 def composite_fwd(raw, z, dirs, noise=None, white_bkg=False, want_weights=True):
+    """noise: None, a [n,S] tensor (already scaled) or an RngNoise."""
     lib = _lib.load()
     raw, z = f32c(raw), f32c(z)
     n, s = z.shape
     keep, dptr, dstride = _dir_arg(dirs)
-    noise = None if noise is None else f32c(noise, raw.device)
     rgb = torch.empty((n, 3), dtype=torch.float32, device=raw.device)
     w = torch.empty((n, s), dtype=torch.float32, device=raw.device) if want_weights else None
+    if isinstance(noise, RngNoise):
+        check(lib.nerf_composite_fwd_rng(ptr(raw), ptr(z), dptr, dstride, float(noise.scale), noise.rng.key, noise.stream,
+                                         noise.rng.ray0, n, s, int(bool(white_bkg)), ptr(rgb), ptr(w), stream_of(raw)),
+              "nerf_composite_fwd_rng")
+        return rgb, w
+    noise = None if noise is None else f32c(noise, raw.device)
     check(lib.nerf_composite_fwd(ptr(raw), ptr(z), dptr, dstride, ptr(noise), n, s, int(bool(white_bkg)),
                                  ptr(rgb), ptr(w), stream_of(raw)), "nerf_composite_fwd")
     return rgb, w
@@ -132,10 +181,15 @@ def composite_bwd(raw, z, dirs, noise, white_bkg, grad_rgb, grad_w=None):
     raw, z = f32c(raw), f32c(z)
     n, s = z.shape
     keep, dptr, dstride = _dir_arg(dirs)
-    noise = None if noise is None else f32c(noise, raw.device)
     grad_rgb = f32c(grad_rgb)
     grad_w = None if grad_w is None else f32c(grad_w)
     grad_raw = torch.empty_like(raw)
+    if isinstance(noise, RngNoise):
+        check(lib.nerf_composite_bwd_rng(ptr(raw), ptr(z), dptr, dstride, float(noise.scale), noise.rng.key, noise.stream,
+                                         noise.rng.ray0, n, s, int(bool(white_bkg)), ptr(grad_rgb), ptr(grad_w),
+                                         ptr(grad_raw), stream_of(raw)), "nerf_composite_bwd_rng")
+        return grad_raw
+    noise = None if noise is None else f32c(noise, raw.device)
     check(lib.nerf_composite_bwd(ptr(raw), ptr(z), dptr, dstride, ptr(noise), n, s, int(bool(white_bkg)),
                                  ptr(grad_rgb), ptr(grad_w), ptr(grad_raw), stream_of(raw)),
           "nerf_composite_bwd")
@@ -172,10 +226,19 @@ def sample_pdf(bins, weights, u):
     return out
 
 
-def resample_merge(z_c, w_c, u):
+def resample_merge(z_c, w_c, u=None, rng=None, n_fine=None):
+    """main.py:248-251.  Uniforms from the tensor ``u`` [n,m] or, with ``rng``, drawn in place
+    (``n_fine`` = m)."""
     lib = _lib.load()
-    z_c, w_c, u = f32c(z_c), f32c(w_c), f32c(u)
+    z_c, w_c = f32c(z_c), f32c(w_c)
     n, s = z_c.shape
+    if rng is not None:
+        assert u is None and n_fine is not None
+        z_f = torch.empty((n, s + n_fine), dtype=torch.float32, device=z_c.device)
+        check(lib.nerf_resample_merge_rng(ptr(z_c), ptr(w_c), rng.key, rng.ray0, n, s, int(n_fine), ptr(z_f),
+                                          stream_of(z_c)), "nerf_resample_merge_rng")
+        return z_f
+    u = f32c(u, z_c.device)
     m = u.shape[-1]
     z_f = torch.empty((n, s + m), dtype=torch.float32, device=z_c.device)
     check(lib.nerf_resample_merge(ptr(z_c), ptr(w_c), ptr(u), n, s, m, ptr(z_f), stream_of(z_c)),

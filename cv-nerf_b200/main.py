@@ -7,9 +7,11 @@ process_volume_info (174-204), render_rays (207-261), decayed_learning_rate (276
 reader for the ``configs/*.txt`` flag files (config_parser, 410-457).
 
 All arithmetic runs in libnerf_b200.so.  Random draws (stratified jitter, density noise, the
-inverse-CDF uniforms -- SURVEY.md App. A.7) come from torch's device generator unless a
-``RenderDraws`` is passed through the keyword-only ``draws`` argument (parity tests inject the
-numbers the oracle consumed).
+inverse-CDF uniforms -- SURVEY.md App. A.7) are made INSIDE the consuming kernels from a Philox
+counter keyed by (seed, global ray index, sample) -- the seed comes from torch's CPU generator, so
+``torch.manual_seed`` makes a run reproducible and no [n,S] tensor of random numbers is ever written
+to HBM -- unless a ``RenderDraws`` is passed through the keyword-only ``draws`` argument (parity
+tests inject the numbers the oracle consumed).
 """
 import dataclasses
 import os
@@ -44,6 +46,12 @@ class RenderDraws:
         return RenderDraws(cut(self.t_rand), cut(self.noise_c), cut(self.u), cut(self.noise_f))
 
 
+def fresh_rng(ray0=0):
+    """A new key for one render call's in-kernel draws, taken from torch's CPU generator (no device
+    synchronisation; reproducible under torch.manual_seed)."""
+    return K.Rng(int(torch.randint(0, 1 << 62, (1,), dtype=torch.int64).item()), int(ray0))
+
+
 def compute_rays(h, w, f, pose):
     """Pinhole rays of an h x w image -> (origins [h,w,3] stride-0 view, dirs [h,w,3])."""
     pose = torch.as_tensor(pose)
@@ -60,8 +68,8 @@ def process_volume_info(raw_rgba, t_samples, r_dirs, noise=0.0, bkg=False, *, no
         raise NerfB200Error("process_volume_info expects 2-D t_samples [n,S] (as the reference does, main.py:194)")
     nz = None
     if noise > 0.:
-        nz = noise_draw if noise_draw is not None else torch.randn(t_samples.shape, device=raw_rgba.device)
-        nz = nz.to(raw_rgba.device) * noise
+        nz = (noise_draw.to(raw_rgba.device) * noise if noise_draw is not None
+              else K.RngNoise(float(noise), fresh_rng(), K.RNG_NOISE_C))
     return _composite(raw_rgba, f32c(t_samples), r_dirs, nz, bool(bkg))
 
 
@@ -72,11 +80,13 @@ def _field(model, rays, z):
 
 
 def render_rays(ray_batch, coarse_model, q_fn=None, n_coarse_samples=64, perturb=0.0, n_fine_samples=0,
-                fine_model=None, white_bkg=False, noise=0.0, *, draws=None, extras=False, maps=False):
+                fine_model=None, white_bkg=False, noise=0.0, *, draws=None, rng=None, extras=False, maps=False):
     """[n,11] rays -> {'rgb_map': [n,3], 'rgb_c': [n,3]} (main.py:207-261).
 
     ``q_fn`` is accepted and ignored: when the models are cv_nerf_b200 ``Model`` instances the
-    encode+MLP closure the reference builds (main.py:138-141) is what the fused kernel does."""
+    encode+MLP closure the reference builds (main.py:138-141) is what the fused kernel does.
+    ``draws`` injects random numbers; whatever it leaves out is drawn in-kernel from ``rng``
+    (a kernels.Rng; default: a fresh key from torch's CPU generator)."""
     if not isinstance(coarse_model, Model) or (fine_model is not None and not isinstance(fine_model, Model)):
         raise NerfB200Error("render_rays needs cv_nerf_b200.model.Model networks; there is no fallback path")
     if ray_batch.shape[-1] != K.RAY_STRIDE:
@@ -86,28 +96,35 @@ def render_rays(ray_batch, coarse_model, q_fn=None, n_coarse_samples=64, perturb
         raise NerfB200Error("render_rays needs CUDA tensors; there is no CPU fallback")
     n, dev = rays.shape[0], rays.device
     draws = draws or RenderDraws()
+    rng = rng or fresh_rng()
     on_dev = lambda t: None if t is None else f32c(t, dev)
 
-    t_rand = None
-    if perturb > 0.:
-        t_rand = on_dev(draws.t_rand) if draws.t_rand is not None else torch.rand((n, n_coarse_samples), device=dev)
-    z_c = K.sample_coarse(rays, n_coarse_samples, t_rand)
+    if not perturb > 0.:
+        z_c = K.sample_coarse(rays, n_coarse_samples)
+    elif draws.t_rand is not None:
+        z_c = K.sample_coarse(rays, n_coarse_samples, on_dev(draws.t_rand))
+    else:
+        z_c = K.sample_coarse(rays, n_coarse_samples, rng=rng)
 
-    def noise_for(shape, injected):
+    def noise_for(injected, stream):
         if not noise > 0.:
             return None
-        base = on_dev(injected) if injected is not None else torch.randn(shape, device=dev)
-        return base * noise
+        return on_dev(injected) * noise if injected is not None else K.RngNoise(float(noise), rng, stream)
 
+    want_all = extras or maps
     raw_c = _field(coarse_model, rays, z_c)
-    rgb_c, w_c = _composite(raw_c, z_c, rays, noise_for(z_c.shape, draws.noise_c), bool(white_bkg))
+    rgb_c, w_c = _composite(raw_c, z_c, rays, noise_for(draws.noise_c, K.RNG_NOISE_C), bool(white_bkg))
 
-    u = on_dev(draws.u) if draws.u is not None else torch.rand((n, n_fine_samples), device=dev)
-    z_f = K.resample_merge(z_c, w_c.detach(), u)
+    if draws.u is not None:
+        z_f = K.resample_merge(z_c, w_c.detach(), on_dev(draws.u))
+    else:
+        z_f = K.resample_merge(z_c, w_c.detach(), rng=rng, n_fine=n_fine_samples)
 
     run = coarse_model if fine_model is None else fine_model
     raw_f = _field(run, rays, z_f)
-    rgb_f, w_f = _composite(raw_f, z_f, rays, noise_for(z_f.shape, draws.noise_f), bool(white_bkg))
+    # the fine pass's weights are only materialised when somebody reads them (0.49 GB per 800x800 frame)
+    rgb_f, w_f = _composite(raw_f, z_f, rays, noise_for(draws.noise_f, K.RNG_NOISE_F), bool(white_bkg),
+                            want_weights=want_all)
 
     out = {'rgb_map': rgb_f, 'rgb_c': rgb_c}
     if maps:
@@ -119,7 +136,7 @@ def render_rays(ray_batch, coarse_model, q_fn=None, n_coarse_samples=64, perturb
     return out
 
 
-def batch_rays(rays_flat, chunk=32768, *, draws=None, **kwargs):
+def batch_rays(rays_flat, chunk=32768, *, draws=None, rng=None, **kwargs):
     """Chunked render_rays (main.py:90-99).  ``chunk`` exists in the reference to bound the
     [chunk*S,90] encoding tensor; the inference path has no such tensor (about 6 KB of raw/depth
     scratch per ray), so without autograd chunks are merged up to MAX_RAYS_PER_LAUNCH rays per
@@ -129,9 +146,10 @@ def batch_rays(rays_flat, chunk=32768, *, draws=None, **kwargs):
     chunk = max(int(chunk), 1)
     step = chunk if torch.is_grad_enabled() else max(chunk, MAX_RAYS_PER_LAUNCH)
     res = {}
+    rng = rng or fresh_rng()
     for i in range(0, rays_flat.shape[0], step):
         d = None if draws is None else draws.rows(i, i + step)
-        ret = render_rays(rays_flat[i:i + step], draws=d, **kwargs)
+        ret = render_rays(rays_flat[i:i + step], draws=d, rng=rng.shifted(i), **kwargs)
         for k in ret:
             res.setdefault(k, []).append(ret[k])
     return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in res.items()}
@@ -142,11 +160,13 @@ to8b = to_byte              # the name main() calls in the reference (main.py:40
 
 
 def render(height, width, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1.,
-           *, rows=None, draws=None, **kwargs):
+           *, rows=None, draws=None, rng=None, **kwargs):
     """Full front end (main.py:49-87): returns ``[rgb_map, {'rgb_c': ...}]`` shaped like the
     ray batch (``[H,W,3]`` for ``c2w``).  ``rows=(r0,r1)`` restricts a ``c2w`` render to image
-    rows [r0,r1) (used to shard a frame across GPUs)."""
+    rows [r0,r1) (used to shard a frame across GPUs; the in-kernel draws are keyed by the global
+    ray index, so the shards of a frame rendered with the same ``rng`` seed equal the whole frame)."""
     height, width = int(height), int(width)
+    first_ray = 0
     if c2w is not None:
         c2w = torch.as_tensor(c2w)
         if not c2w.is_cuda:
@@ -154,13 +174,15 @@ def render(height, width, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True,
         r0, r1 = (0, height) if rows is None else rows
         packed = K.pack_rays(height, width, focal, pose=c2w.float(), row0=r0, row1=r1, ndc=ndc, near=near, far=far)
         lead = [r1 - r0, width]
+        first_ray = r0 * width
     else:
         rays_o, rays_d = rays
         if not rays_d.is_cuda:
             raise NerfB200Error("render needs CUDA ray tensors; there is no CPU fallback")
         packed = K.pack_rays(height, width, focal, rays_o=rays_o, rays_d=rays_d, ndc=ndc, near=near, far=far)
         lead = list(rays_d.shape[:-1])
-    all_ret = batchify_rays(packed, chunk, draws=draws, **kwargs)
+    rng = fresh_rng(first_ray) if rng is None else rng.shifted(first_ray)
+    all_ret = batchify_rays(packed, chunk, draws=draws, rng=rng, **kwargs)
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], lead + list(all_ret[k].shape[1:]))
     k_extract = ['rgb_map']

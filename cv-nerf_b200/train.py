@@ -90,14 +90,12 @@ class TrainStep:
             self.rank = torch.distributed.get_rank(process_group)
         # Data-parallel ranks must draw DIFFERENT ray batches (rays are sharded; identical batches
         # would make N GPUs do the work of one): the rank is folded into the pixel-permutation key and
-        # into the generator that draws the stratified jitter / resampling uniforms / density noise.
+        # into the Philox key of the stratified jitter / resampling uniforms / density noise.
         self.seed, self.it = rank_seed(seed, self.rank), 0
         dev = next(coarse_model.parameters()).device
         if dev.type != "cuda":
             raise NerfB200Error("TrainStep needs the models on a CUDA device; there is no CPU fallback")
         self.dev = dev
-        self.gen = torch.Generator(device=dev)
-        self.gen.manual_seed(self.seed)
         g = K.grad_blob_floats()
         self.blob = torch.zeros((2, g), dtype=torch.float32, device=dev)          # [coarse, fine]
         # Data parallel: put the blobs into symmetric (peer-mapped) memory so that the fused
@@ -143,24 +141,30 @@ class TrainStep:
         if n > self.n_rays:
             raise NerfB200Error(f"TrainStep was sized for {self.n_rays} rays per step, got {n}")
         dev = self.dev
-        pick = lambda t, shape, fn: (t.to(dev).float().contiguous() if t is not None
-                                     else fn(shape, device=dev, generator=self.gen))
-        t_rand = None
-        if self.perturb > 0.:
-            t_rand = pick(draws.t_rand if draws else None, (n, self.s_c), torch.rand)
-        z_c = K.sample_coarse(rays, self.s_c, t_rand)
+        # Random draws: injected tensors (parity tests) or, by default, drawn inside the consuming
+        # kernels from the Philox key (this rank's seed; rays of iteration `it` are numbered from
+        # it * n_rays), so no torch.rand / torch.randn launch and no [n,S] tensor in HBM.
+        rng = K.Rng(self.seed, self.it * self.n_rays)
+        inj = lambda t: None if t is None else t.to(dev).float().contiguous()
+        d_t, d_u = inj(draws.t_rand if draws else None), inj(draws.u if draws else None)
+        if not self.perturb > 0.:
+            z_c = K.sample_coarse(rays, self.s_c)
+        elif d_t is not None:
+            z_c = K.sample_coarse(rays, self.s_c, d_t)
+        else:
+            z_c = K.sample_coarse(rays, self.s_c, rng=rng)
         noise_c = noise_f = None
         if self.noise > 0.:
-            noise_c = pick(draws.noise_c if draws else None, (n, self.s_c), torch.randn) * self.noise
-            noise_f = pick(draws.noise_f if draws else None, (n, self.s_f), torch.randn) * self.noise
-        u = pick(draws.u if draws else None, (n, self.n_fine), torch.rand)
+            d_nc, d_nf = inj(draws.noise_c if draws else None), inj(draws.noise_f if draws else None)
+            noise_c = d_nc * self.noise if d_nc is not None else K.RngNoise(float(self.noise), rng, K.RNG_NOISE_C)
+            noise_f = d_nf * self.noise if d_nf is not None else K.RngNoise(float(self.noise), rng, K.RNG_NOISE_F)
 
         pk_c, pk_f = self.coarse.packed(), self.fine.packed()
         rows_c, rows_f = n * self.s_c, n * self.s_f
         vt_c = K.viewdir_term(pk_c, rays)
         raw_c = K.mlp_fwd(pk_c, K.IN_RAYS, rays, z_c, rows_c, self.s_c, vt_c, self.s_c, act_save=self.act_c)
         rgb_c, w_c = K.composite_fwd(raw_c.view(n, self.s_c, 4), z_c, rays, noise_c, self.white_bkg)
-        z_f = K.resample_merge(z_c, w_c, u)
+        z_f = K.resample_merge(z_c, w_c, d_u) if d_u is not None else K.resample_merge(z_c, w_c, rng=rng, n_fine=self.n_fine)
         vt_f = K.viewdir_term(pk_f, rays)
         raw_f = K.mlp_fwd(pk_f, K.IN_RAYS, rays, z_f, rows_f, self.s_f, vt_f, self.s_f, act_save=self.act_f)
         rgb_f, _ = K.composite_fwd(raw_f.view(n, self.s_f, 4), z_f, rays, noise_f, self.white_bkg, want_weights=False)

@@ -99,6 +99,42 @@ int nerf_sample_pdf(const float* bins, const float* weights, const float* u, lon
 int nerf_resample_merge(const float* z_c, const float* w_c, const float* u, long n, int S, int m,
                         float* z_f, void* stream);
 
+/* ---------------------------------------------------------------- in-kernel random draws
+ * The reference draws torch.rand / torch.randn tensors for the stratified jitter (main.py:233), the
+ * density noise (main.py:188) and the inverse-CDF uniforms (utils.py:23, drawn even at test time).
+ * The entry points above take those tensors from the caller (parity runs inject the numbers the
+ * oracle consumed).  The *_rng variants draw them inside the consuming kernel from Philox4x32-10
+ * keyed by (seed; ray0 + ray, value index / 4, stream), so no [n,S] tensor of random numbers ever
+ * touches HBM and a row-sharded render (ray0 = first ray of the shard) draws the same numbers as the
+ * unsharded one.  csrc/rng.cuh states the mapping; nerf_rng_fill writes the same numbers out. */
+#define NERF_RNG_STREAM_T_RAND 0  /* uniforms [n,S_c]: stratified jitter              */
+#define NERF_RNG_STREAM_U 1       /* uniforms [n,m]:   inverse-CDF resampling          */
+#define NERF_RNG_STREAM_NOISE_C 2 /* normals  [n,S_c]: density noise, coarse pass      */
+#define NERF_RNG_STREAM_NOISE_F 3 /* normals  [n,S_c+m]: density noise, fine pass      */
+
+/* nerf_sample_coarse with t_rand drawn in place (perturb > 0, main.py:227-234). */
+int nerf_sample_coarse_rng(const float* rays, long n, int S, unsigned long long seed, long ray0,
+                           float* z_out, void* stream);
+
+/* nerf_resample_merge with u drawn in place (utils.py:23). */
+int nerf_resample_merge_rng(const float* z_c, const float* w_c, unsigned long long seed, long ray0,
+                            long n, int S, int m, float* z_f, void* stream);
+
+/* nerf_composite_fwd / _bwd with noise = noise_scale * N(0,1) drawn in place (main.py:186-189);
+ * rng_stream is NERF_RNG_STREAM_NOISE_C or _F.  Forward and backward regenerate the same values. */
+int nerf_composite_fwd_rng(const float* raw, const float* z, const float* dirs, int dir_stride,
+                           float noise_scale, unsigned long long seed, int rng_stream, long ray0,
+                           long n, int S, int white_bkg, float* rgb_out, float* weights_out,
+                           void* stream);
+int nerf_composite_bwd_rng(const float* raw, const float* z, const float* dirs, int dir_stride,
+                           float noise_scale, unsigned long long seed, int rng_stream, long ray0,
+                           long n, int S, int white_bkg, const float* grad_rgb,
+                           const float* grad_weights, float* grad_raw, void* stream);
+
+/* out [n,cols] = the draws of rows ray0..ray0+n-1 of a stream; kind 0: uniforms, 1: normals. */
+int nerf_rng_fill(int kind, unsigned long long seed, int rng_stream, long ray0, long n, int cols,
+                  float* out, void* stream);
+
 /* ---------------------------------------------------------------- K2: the field network */
 
 /* Bytes of the packed parameter blob of one Model (BF16 UMMA-layout weight stages + fp32 tail). */

@@ -53,13 +53,16 @@ def _reference_chain(p, pts, dirs_per_row, grad_raw):
         {k: v.grad for k, v in q.items()}
 
 
-def _emulated_chain(p, pe, acts, pe_dir, grad_raw):
+def _emulated_chain(p, pe, acts, pe_dir, grad_raw, mask_acts=None):
     """The kernels' arithmetic restated in fp64: BF16 operands (saved activations, BF16-rounded dZ,
-    BF16 weights), exact accumulation, ReLU masks taken from the SAVED activations.
+    BF16 weights), exact accumulation, ReLU masks taken from the SAVED activations -- or, with
+    ``mask_acts``, from another forward's activations (the fp32 reference's: isolates the rounding
+    error of the contractions from the ReLU-mask flips of a BF16 forward).
     Returns (dz dict, param grads dict)."""
     W = lambda n: bf16(p[n + ".weight"]).double()
     g = grad_raw.double()
-    a = {k: v.double() for k, v in acts.items()}
+    vals = {k: v.double() for k, v in acts.items()}
+    a = vals if mask_acts is None else {k: v.double() for k, v in mask_acts.items()}
     dz, r = {}, {}
     r16 = lambda t: bf16(t.float()).double()
     dz[10] = r16((g[:, :3] @ p["l11.weight"].double()) * (a[10] > 0))
@@ -70,19 +73,28 @@ def _emulated_chain(p, pe, acts, pe_dir, grad_raw):
     dz[5] = r16((dz[6] @ W("l6")[:, 63:]) * (a[5] > 0))
     for i in (4, 3, 2, 1):
         dz[i] = r16((dz[i + 1] @ W(f"l{i + 1}")) * (a[i] > 0))
-    x_in = {1: pe.double()[:, :63], 6: torch.cat([pe.double()[:, :63], a[5]], -1), 10: a[9]}
+    x_in = {1: pe.double()[:, :63], 6: torch.cat([pe.double()[:, :63], vals[5]], -1), 10: vals[9]}
     for i in range(1, 10):
-        x = x_in.get(i, a.get(i - 1))
+        x = x_in.get(i, vals.get(i - 1))
         r[f"l{i}.weight"] = dz[i].T @ x
         r[f"l{i}.bias"] = dz[i].sum(0)
     dv = dz[10]
-    r["l10.weight"] = torch.cat([dv.T @ a[9], dv.T @ pe_dir.double()], -1)
+    r["l10.weight"] = torch.cat([dv.T @ vals[9], dv.T @ pe_dir.double()], -1)
     r["l10.bias"] = dv.sum(0)
-    r["l_alpha.weight"] = (g[:, 3:4] * a[8]).sum(0, keepdim=True)
+    r["l_alpha.weight"] = (g[:, 3:4] * vals[8]).sum(0, keepdim=True)
     r["l_alpha.bias"] = g[:, 3].sum().reshape(1)
-    r["l11.weight"] = g[:, :3].T @ a[10]
+    r["l11.weight"] = g[:, :3].T @ vals[10]
     r["l11.bias"] = g[:, :3].sum(0)
     return dz, r
+
+
+def _fp32_bar(layer):
+    """rel-L2 bound of a BF16-forward gradient against the fp32 reference, by depth of the tensor in
+    the backward chain.  A ReLU mask that differs between the two forwards moves that element by its
+    full size, so the error is ~sqrt(fraction of masks flipped) per layer (measured 4e-4 -> 0.02 at
+    dZ10) and accumulates towards l1: measured on B200 0.020 (dZ10) ... 0.119 (dZ1), 0.133 (l1.bias)
+    (profiles/r02_grad_parity.txt); the bounds are the measured worst cases plus about a quarter."""
+    return {10: 0.030, 9: 0.030, 8: 0.060, 7: 0.080, 6: 0.095, 5: 0.105, 4: 0.115, 3: 0.130, 2: 0.145, 1: 0.155}[layer]
 
 
 @pytest.mark.parametrize("rows,S", [(96, 8), (1000, 8), (3 * 128 * 4, 64)])
@@ -121,6 +133,12 @@ def test_field_backward_stages(rows, S):
     assert (saved[10] - acts[10]).abs().max() <= 2e-2 * max(1.0, acts[10].abs().max().item())
     pe_dir = O.freq_encode(dirs.repeat_interleave(S, 0), 4)
     dz_emu, g_emu = _emulated_chain(p, pe, saved, pe_dir, grad_raw)
+    # the same BF16 arithmetic with the fp32 forward's ReLU masks: what is left against the fp32
+    # reference is the rounding of the contractions alone
+    dz_fm, g_fm = _emulated_chain(p, pe, saved, pe_dir, grad_raw, mask_acts=acts)
+    flipped = {i: ((saved[i] > 0) != (acts[i] > 0)).float().mean().item() for i in (1, 2, 3, 4, 5, 6, 7, 8, 10)}
+    print("fraction of ReLU masks that differ between the BF16 and the fp32 forward:", flipped)
+    record("relu_mask_flips", dict(rows=rows, **{f"l{i}": v for i, v in flipped.items()}))
 
     # 2. dZ chain
     dz = K.mlp_bwd_dz(model.packed_bwd(), grad_raw.to(DEV), act, rows)
@@ -139,8 +157,11 @@ def test_field_backward_stages(rows, S):
         print(f"dZ{i} vs emulation", se, "vs fp32 reference", st)
         record("grad_stage", dict(rows=rows, tensor=f"dZ{i}", emu_rel_l2=se["rel_l2"], emu_cos=se["cos"],
                                   fp32_rel_l2=st["rel_l2"], fp32_cos=st["cos"]))
-        assert se["rel_l2"] <= 1e-2 and se["cos"] >= 0.9999, (i, se)
-        assert st["rel_l2"] <= 0.15 and st["cos"] >= 0.99, (i, st)
+        sm = grad_stats(dz_fm[i], dz_ref[i])
+        record("grad_stage_fp32_masks", dict(rows=rows, tensor=f"dZ{i}", rel_l2=sm["rel_l2"], cos=sm["cos"]))
+        assert se["rel_l2"] <= 2e-3 and se["cos"] >= 0.99999, (i, se)          # measured <= 5.7e-4
+        assert sm["rel_l2"] <= 3e-2, (i, sm)                                     # rounding alone
+        assert st["rel_l2"] <= _fp32_bar(i) and st["cos"] >= 0.99, (i, st)
 
     # 3. parameter gradients
     blob = torch.zeros(K.grad_blob_floats(), device=DEV)
@@ -155,8 +176,14 @@ def test_field_backward_stages(rows, S):
         print(name, "vs emulation", se, "vs fp32 reference", st)
         record("grad_stage", dict(rows=rows, tensor=name, emu_rel_l2=se["rel_l2"], emu_cos=se["cos"],
                                   fp32_rel_l2=st["rel_l2"], fp32_cos=st["cos"]))
-        assert se["rel_l2"] <= 1e-2 and se["cos"] >= 0.9999, (name, se)
-        assert st["rel_l2"] <= 0.15 and st["cos"] >= 0.99, (name, st)
+        sm = grad_stats(g_fm[name], g_ref[name])
+        record("grad_stage_fp32_masks", dict(rows=rows, tensor=name, rel_l2=sm["rel_l2"], cos=sm["cos"]))
+        layer = {"l_alpha": 9, "l10": 10, "l11": 11}.get(name.split(".")[0]) or int(name.split(".")[0][1:])
+        assert se["rel_l2"] <= 2e-3 and se["cos"] >= 0.99999, (name, se)
+        assert sm["rel_l2"] <= 3e-2, (name, sm)
+        # parameter gradients are sums of dZ over the rows (biases: plain sums), the flips do not
+        # average out the same way: measured up to 1.37x the dZ figure of the layer
+        assert st["rel_l2"] <= _fp32_bar(min(layer, 10)) * 1.4 and st["cos"] >= 0.99, (name, st)
     # accumulate mode adds
     K.grad_unpack(blob, grads, accumulate=True)
     torch.cuda.synchronize()
@@ -256,6 +283,12 @@ def test_train_step_gradients_match_reference_fixture(name):
     assert abs(loss.item() - ref_loss.item()) <= 1e-3 * max(1., ref_loss.item()), (loss.item(), ref_loss.item())
 
     bad, worst_norm, worst_cos = [], 0., 1.
+    all_got = torch.cat([prm.grad.detach().cpu().reshape(-1) for net in (coarse, fine) for _, prm in net.named_parameters()])
+    all_ref = torch.cat([q[k].grad.reshape(-1) for net, q in ((coarse, cq), (fine, fq)) for k, _ in net.named_parameters()])
+    whole = grad_stats(all_got, all_ref)
+    print(name, "whole gradient vector (1 191 688 values) vs the fp32 reference:", whole)
+    record("grad_e2e_whole", dict(fixture=name, rel_l2=whole["rel_l2"], cos=whole["cos"], rays=int(keep.sum()), n_flip=n_flip))
+    assert whole["rel_l2"] <= 0.08 and whole["cos"] >= 0.997, whole
     for tag, net, q in (("coarse", coarse, cq), ("fine", fine, fq)):
         for k, prm in net.named_parameters():
             st = grad_stats(prm.grad.detach().cpu(), q[k].grad)
@@ -265,10 +298,11 @@ def test_train_step_gradients_match_reference_fixture(name):
             record("grad_e2e", dict(fixture=name, net=tag, tensor=k, norm_rel_err=rel_norm, rel_l2=st["rel_l2"],
                                     cos=st["cos"], n_flip=n_flip))
             worst_norm, worst_cos = max(worst_norm, rel_norm), min(worst_cos, st["cos"])
-            # BF16 contractions + ReLU masks of a BF16 forward on <= 96 rays: norm within 5 %,
-            # direction cos >= 0.98 per tensor (the kernels' own arithmetic is pinned to 1e-2 rel-L2,
-            # measured 6e-4, by test_field_backward_stages)
-            if rel_norm > 5e-2 or st["cos"] < 0.98:
+            # BF16 contractions + ReLU masks of a BF16 forward on <= 96 rays, per tensor: norm within
+            # 3 % (measured <= 2.0 %), cos >= 0.985 (measured >= 0.9886), rel-L2 <= 0.18 (measured
+            # <= 0.153 at fine l1.weight, the end of the chain); the kernels' own arithmetic is pinned to
+            # 2e-3 rel-L2 (measured 6e-4) by test_field_backward_stages
+            if rel_norm > 3e-2 or st["cos"] < 0.985 or st["rel_l2"] > 0.18:
                 bad.append((tag, k, rel_norm, st))
             if n_flip == 0:
                 gn = float(g[f"gnorm/{tag}.{k}"])

@@ -104,37 +104,35 @@ def test_skull_spiral_frames_parity(frame):
 
 
 def test_sharpened_weights_parity():
-    """Parity is not a property of smooth random-init weights only: train both networks for 300
-    steps on a high-frequency synthetic target (stripes of 3-pixel period, four views), then render
-    a full 400x400 view with the trained weights and check a pixel subset against the oracle running
-    the SAME trained weights in fp32."""
-    from cv_nerf_b200.model import Model
+    """Parity is not a property of smooth random-init weights only: fit both networks for 300 steps
+    to a target with sharp edges (a 0/1 checkerboard of 40-pixel squares with a different colour
+    phase per channel, one view), then render that 400x400 view with the trained weights and check a
+    pixel subset against the oracle running the SAME trained weights in fp32."""
     from cv_nerf_b200.train import TrainStep
     torch.manual_seed(7)
     h = w = 400
     f = 555.5555155968841
     cp, fp, coarse, fine = _nets(5, 0.5, 10.0)
     ii, jj = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
-    images = torch.stack([torch.stack([0.5 + 0.5 * torch.sin(2.1 * (ii + k * jj) + c) for c in (0., 2., 4.)], -1)
-                          for k in (0., 1., -1., 2.)]).float().to(DEV)
-    poses = [O.lego_pose(a, -30., 4.)[:3, :4].to(DEV) for a in (-180., -90., 0., 90.)]
+    image = torch.stack([(((ii + s) // 40 + (jj + 2 * s) // 40) % 2).float() for s in (0, 13, 26)], -1).to(DEV)
+    pose = O.lego_pose(-180., -30., 4.)[:3, :4]
     ts = TrainStep(coarse, fine, height=h, width=w, focal=f, n_rays=4096, perturb=1., noise=0., white_bkg=True,
-                   ndc=False, near=2., far=6., lr=5e-4, lr_decay=250, seed=3)
-    first = last = None
-    for it in range(300):
-        loss = ts.step(images[it % 4], poses[it % 4])
-        if it == 0:
-            first = loss.item()
-    last = loss.item()
+                   ndc=False, near=2., far=6., lr=1e-3, lr_decay=250, seed=3)
+    pose_dev = pose.to(DEV)
+    losses = [ts.step(image, pose_dev).clone() for _ in range(300)]      # step() returns its own loss buffer
+    first, last = torch.stack(losses[:5]).mean().item(), torch.stack(losses[-5:]).mean().item()
     print("sharpening: loss", first, "->", last)
-    assert last < first
+    assert last < 0.6 * first, "the fit did not sharpen the field"
     trained = []
     for net, p0 in ((coarse, cp), (fine, fp)):
         sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
-        moved = max((sd[k] - p0[k]).abs().max().item() for k in p0)
-        assert moved > 1e-3, "training did not move the weights"
+        assert max((sd[k] - p0[k]).abs().max().item() for k in p0) > 1e-2, "training did not move the weights"
         trained.append(sd)
     wmax = max(v.abs().max().item() for sd in trained for v in sd.values())
-    record("sharpened_weights", dict(loss_first=first, loss_last=last, steps=300, weight_absmax=wmax))
-    _frame_vs_oracle("lego400_trained", h, w, f, O.lego_pose(-180., -30., 4.)[:3, :4], trained[0], trained[1],
-                     coarse, fine, ndc=False, near=2., far=6., white_bkg=True, n_check=2048, seed=13)
+    out = _frame_vs_oracle("lego400_trained", h, w, f, pose, trained[0], trained[1], coarse, fine, ndc=False, near=2.,
+                           far=6., white_bkg=True, n_check=2048, seed=13)
+    got, want, _ = out["rgb_map"]
+    spread = want.std().item()
+    record("sharpened_weights", dict(loss_first=first, loss_last=last, steps=300, weight_absmax=wmax,
+                                     rendered_rgb_std=spread))
+    assert spread > 0.1, "the trained scene renders flat: the parity check would be vacuous"

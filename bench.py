@@ -13,12 +13,15 @@ all-gathered so each step ends with the whole frame on every rank.
 Printed JSON (rank 0): `value` = rays/s with inputs resident in HBM; `e2e` = the same through the
 public render() call with the pose coming from pinned host memory and the frame read back to
 pinned host memory inside the timed region; `roofline` = the field-network kernel against the
-measured BF16 tensor peak; `cpu_baseline` = the CPU port of the reference's path (oracle/) on a
-bounded sample of the same frame.
+measured BF16 tensor peak; `cpu_baseline` = the reference's CPU path on a bounded sample of the same
+frame; `train` = BASELINE.json configs[3] (4096-ray data-parallel train step) with its own HBM
+roofline; `configs` = the fern (configs[2]) and skull-video (configs[4]) shapes.
 
-`--impl reference` times the reference's algorithm on the host CPUs (the oracle port: the
-reference is Python and /root/reference does not exist on the GPU box) on bounded samples of the
-same frame.
+`--impl reference` times the reference's own `main.render` on the host CPUs, all host threads, on
+bounded samples of the same frame: the reference is pure Python, /root/reference does not exist on
+the GPU box, so its modules are byte-compiled in the build container into oracle/_ref/
+(oracle/build_ref.py; git-ignored, travels with the snapshot) -- kind "reference"; if that directory
+is absent the oracle port (pinned to the reference's outputs by tests/) is timed -- kind "port".
 """
 import argparse
 import json
@@ -105,29 +108,63 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so
+    torch.get_num_threads() is 1 there; the CPU arm must not inherit that."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
 def cpu_reference_rays_per_s(n_rays, steps, warmup):
-    """The reference's algorithm (oracle port, torch-CPU fp32, all host threads) on `n_rays`
-    rays of the benchmark frame per step -> (rays/s, ms_per_step, threads)."""
+    """The reference's CPU path on `n_rays` rays of the benchmark frame per step, fp32, all host
+    threads -> (rays/s, ms_per_step, threads, kind).  kind "reference": the reference's own main.render
+    run from oracle/_ref (its modules byte-compiled in the build container by oracle/build_ref.py);
+    kind "port": the oracle restatement (tests pin it to the reference's outputs) when oracle/_ref did
+    not travel."""
+    from oracle import build_ref
     from oracle import nerf_oracle as O
+    threads = host_threads()
     torch.manual_seed(0)
-    coarse, fine = O.init_field_params(0)
     pose_list = poses(40, O.lego_pose)
-    threads = torch.get_num_threads()
-    times = []
-    with torch.no_grad():
-        for it in range(warmup + steps):
-            pose = pose_list[it % len(pose_list)]
+    idx = torch.arange(n_rays) * ((H * W) // n_rays)             # bounded, strided sample of the frame
+    if build_ref.available():
+        from types import SimpleNamespace
+        ref = build_ref.load()
+        cfg = SimpleNamespace(netchunk=65536, lr=5e-4, perturb=0., n_fine_samples=N_FINE, n_coarse_samples=N_COARSE,
+                              white_bkg=True, noise=0., dtype="blender", no_ndc=False)
+        _, kw_test, _, _, _ = ref.create_model(cfg)              # torch.manual_seed(0) default init, main.py:127-167
+        kw_test.update(near=NEAR, far=FAR)
+
+        def one(pose):
+            o, d = ref.compute_rays(H, W, FOCAL, pose)
+            rays = torch.stack([o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx]], 0)
+            t0 = time.perf_counter()
+            ref.render(H, W, FOCAL, chunk=32768, rays=rays, **kw_test)          # main.py:49-87
+            return time.perf_counter() - t0
+        kind = "reference"
+    else:
+        coarse, fine = O.init_field_params(0)
+
+        def one(pose):
             o, d = O.ray_grid(H, W, FOCAL, pose)
-            idx = torch.arange(n_rays) * ((H * W) // n_rays)     # bounded, strided sample of the frame
             rays = (o.reshape(-1, 3)[idx], d.reshape(-1, 3)[idx])
             t0 = time.perf_counter()
             O.render_image(H, W, FOCAL, coarse, fine, rays=rays, ndc=False, near=NEAR, far=FAR,
                            n_coarse=N_COARSE, n_fine=N_FINE, white_bkg=True)
-            dt = time.perf_counter() - t0
+            return time.perf_counter() - t0
+        kind = "port"
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            dt = one(pose_list[it % len(pose_list)])
             if it >= warmup:
                 times.append(dt)
     total = sum(times)
-    return n_rays * len(times) / total, 1e3 * total / len(times), threads
+    return n_rays * len(times) / total, 1e3 * total / len(times), threads, kind
 
 
 def run_reference(args):
@@ -135,14 +172,14 @@ def run_reference(args):
     if rank != 0:
         return
     n_rays = args.ref_rays
-    rps, ms, threads = cpu_reference_rays_per_s(n_rays, args.steps, max(args.warmup, 1))
-    sample = f"{n_rays} rays per step, strided over the 800x800 frame, full 64+128 pipeline"
+    rps, ms, threads, kind = cpu_reference_rays_per_s(n_rays, args.steps, max(args.warmup, 1))
+    sample = f"{n_rays} rays per step, strided over the {H}x{W} frame, full 64+128 pipeline, fp32, {threads} threads"
     line = {
         "impl": "reference", "metric": "rendered rays/sec (64+128 samples)", "value": rps, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -176,9 +213,9 @@ def run_ours(args):
     pose_dev = pose_host.to(dev)
 
     # contiguous row blocks per rank (rays are independent: no exchange inside the render)
-    bounds = [H * r // world for r in range(world + 1)]
+    from cv_nerf_b200 import parallel as P
+    bounds = P.row_bounds(H, world)                   # blocks differ by at most one row (ragged allowed)
     r0, r1 = bounds[rank], bounds[rank + 1]
-    assert all(b - a == H // world for a, b in zip(bounds[:-1], bounds[1:])), "H must divide by the GPU count"
     frame = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
     host_out = torch.empty((r1 - r0, W, 3), dtype=torch.float32).pin_memory()
     pose_slot = torch.empty((3, 4), dtype=torch.float32, device=dev)
@@ -186,7 +223,7 @@ def run_ours(args):
     def step_device(i):
         rgb, _ = M.render(H, W, FOCAL, c2w=pose_dev[i % 40], rows=(r0, r1), **kw_test)
         if world > 1:
-            dist.all_gather_into_tensor(frame.view(-1), rgb.reshape(-1))
+            P.all_gather_rows(rgb, H)                 # the whole frame on every rank
         return rgb
 
     def step_e2e(i):
@@ -232,6 +269,10 @@ def run_ours(args):
     if not args.no_train:
         train = bench_train_step(args, dev, world, rank)
 
+    extra = None
+    if not args.no_extra_configs:
+        extra = bench_extra_configs(dev, world, rank)
+
     peaks, peak_kind = measured_peaks()
     n_rays = H * W
     rays_per_s = n_rays * args.steps / (total_ms * 1e-3)
@@ -245,14 +286,15 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_cpu = args.cpu_rays
-        rps, ms, threads = cpu_reference_rays_per_s(n_cpu, 1, 1)
-        cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+        rps, ms, threads, kind = cpu_reference_rays_per_s(n_cpu, 1, 1)
+        cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": kind,
                "sample": f"{n_cpu} rays of the same frame (strided), 1 warm-up + 1 timed pass, torch-CPU fp32"}
     line = {
         "metric": "rendered rays/sec (64+128 samples)", "value": rays_per_s, "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_step": n_rays, "sharding": f"{world} x {H // world} image rows",
+        "config": {"workload": WORKLOAD, "rays_per_step": n_rays, "sharding": f"{world} row blocks of {min(b - a for a, b in zip(bounds[:-1], bounds[1:]))}..{max(b - a for a, b in zip(bounds[:-1], bounds[1:]))} image rows",
+                   "random_draws": "in-kernel Philox (resampling uniforms; no torch.rand launch, no u tensor in HBM)",
                    "l2": "per-step intermediates (1.97 GB raw + 0.49 GB depths) exceed the 126 MB L2; no flush needed",
                    "weights": "torch.manual_seed(0) default nn.Linear init"},
         "e2e": {"value": e2e_rays_per_s, "unit": "rays/s", "h2d_bytes_per_step": 48 * world,
@@ -264,7 +306,9 @@ def run_ours(args):
                      # 19.2 M-row launch of this kernel (profiles/r01_fwd_variants_ncu.txt) = 20.4 B/row, against
                      # ~23 B/row algorithmic (depth in, raw out, rays/view term per ray): no re-reads
                      "traffic": NCU_DRAM_BYTES_PER_ROW * kern_rows / max(len(kern), 1),
-                     "traffic_unit": "bytes per launch (ncu dram__bytes_read+write per row x rows per launch)",
+                     "traffic_unit": "bytes per launch",
+                     "traffic_source": "ncu --set full capture of round 1 (profiles/r01_fwd_variants_ncu.txt: dram__bytes_read.sum "
+                                       "+ dram__bytes_write.sum = 20.4 B per row) x rows per launch of this run; not re-measured here",
                      "kernel": "mlp_fwd_kernel",
                      "peak_kind": f"{peak_kind} bf16_tflops_sustained",
                      "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
@@ -276,6 +320,8 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     if train is not None:
         line["train"] = train
+    if extra is not None:
+        line["configs"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -334,7 +380,21 @@ def bench_train_step(args, dev, world, rank):
         stages = time_train_stages(ts, images[0], pose_dev[0])
     peaks, _ = measured_peaks()
     tflops = n_rays * TRAIN_FLOP_PER_RAY / (ms_step * 1e-3) / 1e12
-    return {"metric": "train step ms (4096 rays per GPU, fwd+bwd+allreduce+Adam)", "ms_per_step": ms_step,
+    # HBM roofline of the step: the training kernels are HBM-bound by design --
+    # the forward writes the activation records, the dZ chain writes the dZ records, the dW kernel reads
+    # both.  Algorithmic bytes = every record written once and read once (+ raw / grad_raw, 32 B/row).
+    rows = n_rays * (N_COARSE + N_COARSE + N_FINE)
+    rec_bytes = sum(K.act_bytes(n_rays * s_) + K.dz_bytes(n_rays * s_) for s_ in (N_COARSE, N_COARSE + N_FINE))
+    hbm_bytes = 2 * rec_bytes + 32 * rows
+    hbm_gbs = hbm_bytes / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": hbm_gbs, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                "frac": hbm_gbs / float(peaks["hbm_gbs"]), "traffic": None,
+                "bytes_per_step": hbm_bytes, "bytes_per_row": hbm_bytes / rows,
+                "what": "activation + dZ tile records written once and read once per step, whole step time "
+                        "(forward, compositing, loss, dZ chains, dW, Adam, re-pack); write-only HBM measures "
+                        "3.9 TB/s on this part, so a step that writes half of its bytes cannot reach 1.0",
+                "tensor_frac_of_sustained_bf16_peak": tflops / float(peaks["bf16_tflops_sustained"])}
+    return {"roofline": roofline,"metric": "train step ms (4096 rays per GPU, fwd+bwd+allreduce+Adam)", "ms_per_step": ms_step,
             "rays_per_step_per_gpu": n_rays, "rays_per_s_all_gpus": n_rays * world / (ms_step * 1e-3),
             "steps": steps, "warmup": warmup, "tflops_per_gpu": tflops,
             "frac_of_sustained_bf16_peak": tflops / float(peaks["bf16_tflops_sustained"]),
@@ -344,6 +404,77 @@ def bench_train_step(args, dev, world, rank):
                               "fused into Adam: peer loads over NVLink from symmetric memory" if ts.symm is not None
                               else "nccl all_reduce"),
             "stages_ms": stages}
+
+
+def bench_extra_configs(dev, world, rank):
+    """BASELINE.json configs[2] and configs[4] on the same GPUs (max over ranks, CUDA events):
+      fern 378x504 NDC: one frame (row-sharded like the headline) and a train step with the
+      configs/fern.txt flags (perturb 1, noise 1);
+      skull 504x378 NDC: the reference's 120 spiral poses (tests/golden/skull_spiral.npz, derived with
+      its own pose math) through render_full, frame-parallel over the ranks, uint8 frames to the host.
+    Fern poses are not in the reference tree: the fern shape is rendered from a
+    recentred skull training pose."""
+    import torch.distributed as dist
+    from cv_nerf_b200 import main as M
+    from cv_nerf_b200 import parallel as P
+    from cv_nerf_b200.model import Model
+    from cv_nerf_b200.train import TrainStep
+    path = os.path.join(ROOT, "tests", "golden", "skull_spiral.npz")
+    if not os.path.exists(path):
+        return {"unavailable": "tests/golden/skull_spiral.npz missing"}
+    g = np.load(path)
+    torch.manual_seed(0)
+    coarse, fine = Model().to(dev), Model().to(dev)
+    kw = dict(coarse_model=coarse, fine_model=fine, n_coarse_samples=N_COARSE, n_fine_samples=N_FINE, white_bkg=False,
+              ndc=True, near=0., far=1., perturb=False, noise=0.)
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / reps
+
+    out = {}
+    h, w, f = 378, 504, np.float32(407.5657)
+    pose = torch.from_numpy(g["train_poses"][3][:3, :4]).float().to(dev)
+    b = P.row_bounds(h, world)
+
+    def fern_frame():
+        with torch.no_grad():
+            rgb, _ = M.render(h, w, f, c2w=pose, rows=(b[rank], b[rank + 1]), **kw)
+            P.all_gather_rows(rgb, h)
+    ms = timed(fern_frame, 10)
+    out["fern_render"] = {"workload": "fern 378x504 NDC frame, 64+128 samples, rows sharded over the GPUs",
+                          "value": h * w / (ms * 1e-3), "unit": "rays/s", "ms_per_frame": ms, "n_gpus": world}
+    ts = TrainStep(coarse, fine, height=h, width=w, focal=f, n_rays=4096, perturb=1., noise=1., white_bkg=False, ndc=True,
+                   near=0., far=1., lr=5e-4, lr_decay=250, seed=77)
+    image = torch.rand(h, w, 3, device=dev)
+    ms = timed(lambda: ts.step(image, pose), 20, warm=3)
+    out["fern_train"] = {"workload": "fern train step (configs/fern.txt: perturb 1, noise 1), 4096 rays per GPU, data parallel",
+                         "ms_per_step": ms, "rays_per_s_all_gpus": 4096 * world / (ms * 1e-3), "n_gpus": world}
+    del ts
+    h, w, f = int(g["hwf"][0]), int(g["hwf"][1]), np.float32(g["hwf"][2])
+    spiral = [torch.from_numpy(p_).float().to(dev) for p_ in g["render_poses"]]
+    kw_v = dict(kw)
+    sec = timed(lambda: M.render_full(spiral, [h, w, f], 32768, kw_v, as_bytes=True, verbose=False), 1, warm=0) * 1e-3
+    out["skull_video"] = {"workload": "skull 504x378 NDC, the reference's 120-frame spiral, frame-parallel over the GPUs, "
+                                      "uint8 frames to pinned host memory (D2H inside the timed region)",
+                          "value": len(spiral) * h * w / sec, "unit": "rays/s", "frames_per_s": len(spiral) / sec,
+                          "seconds": sec, "n_gpus": world}
+    return out
 
 
 def time_train_stages(ts, image, pose):
@@ -403,6 +534,7 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step measurement")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the fern / skull-video measurements")
     ap.add_argument("--train-rays", type=int, default=4096, help="rays per GPU and train step (BASELINE configs[3])")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--size", type=int, default=800, help="frame height=width (profiling runs only; 800 is the benchmark)")

@@ -53,6 +53,13 @@ _SIGNATURES = {
                                               ctypes.c_int, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     "nerf_rng_fill": (ctypes.c_int, [ctypes.c_int, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_long, ctypes.c_long,
                                      ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "nerf_render_scratch_bytes": (ctypes.c_size_t, [ctypes.c_long, ctypes.c_int, ctypes.c_int]),
+    "nerf_render_fused": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_float_p, ctypes.c_int,
+                                         ctypes.c_int, c_float_p, ctypes.c_long, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                         ctypes.c_ulonglong, ctypes.c_long, ctypes.c_void_p, c_float_p, c_float_p,
+                                         ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
     "nerf_packed_model_bytes": (ctypes.c_size_t, []),
     "nerf_pack_model": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p]),
     "nerf_viewdir_term": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_long,

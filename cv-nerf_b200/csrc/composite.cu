@@ -300,6 +300,23 @@ __device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins,
     return (b1 - b0) * ((u - c0) / span) + b0;
 }
 
+// The same for the resample+merge kernel: B <= 127 entries, the cdf padded with +inf up to 128, so
+// the search is seven fixed steps without a loop (first index with cdf[idx] > u, searchsorted
+// right=True).  Arithmetic identical to invert_cdf.
+__device__ __forceinline__ float invert_cdf_padded(const float* cdf, const float* bins, int B, float u) {
+    int idx = 0;
+#pragma unroll
+    for (int step = 64; step > 0; step >>= 1)
+        if (cdf[idx + step - 1] <= u) idx += step;
+    idx = min(idx, B);
+    const int lower = max(idx - 1, 0), upper = min(idx, B - 1);
+    const float c0 = cdf[lower], c1 = cdf[upper];
+    const float b0 = bins[lower], b1 = bins[upper];
+    float span = c1 - c0;
+    if (span < PDF_EPS) span = 1.f;
+    return (b1 - b0) * ((u - c0) / span) + b0;
+}
+
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
                   const float* __restrict__ u, long n, int B, int m, float* __restrict__ out) {
@@ -380,6 +397,7 @@ resample_merge_kernel(const float* __restrict__ z_c, const float* __restrict__ w
     float* bins = s_bins[wib];
     for (int i = lane; i < B; i += 32) bins[i] = .5f * (__ldg(zr + i + 1) + __ldg(zr + i));   // main.py:248
     build_cdf(w_c + ray * S + 1, S - 2, cdf, lane);                                            // weights[..., 1:-1]
+    for (int i = B + lane; i < 128; i += 32) cdf[i] = __int_as_float(0x7f800000);              // +inf padding
     // second half of the final bitonic sequence: element 128 + t holds coarse rank 127 - t
     uint32_t key[8];
 #pragma unroll
@@ -403,7 +421,7 @@ resample_merge_kernel(const float* __restrict__ z_c, const float* __restrict__ w
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        key[j] = lane * 4 + j < m ? order_key(invert_cdf(cdf, bins, B, nerf::pick4(uu, j))) : 0xffffffffu;
+        key[j] = lane * 4 + j < m ? order_key(invert_cdf_padded(cdf, bins, B, nerf::pick4(uu, j))) : 0xffffffffu;
     uint32_t (&samp)[4] = reinterpret_cast<uint32_t (&)[4]>(key[0]);
     uint32_t (&coarse)[4] = reinterpret_cast<uint32_t (&)[4]>(key[4]);
     warp_bitonic_sort<4, false>(samp, lane);

@@ -246,6 +246,43 @@ def resample_merge(z_c, w_c, u=None, rng=None, n_fine=None):
     return z_f
 
 
+def render_fused(coarse, fine, *, height, width, focal, pose=None, rows=None, rays=None, ndc=True, near=0., far=1.,
+                 n_coarse=64, n_fine=128, perturb=0., noise=0., white_bkg=False, rng=None):
+    """The whole render_rays chain (and, with ``pose``, the ray generation of image rows ``rows``) in
+    one C call: (rgb [n,3], rgb_c [n,3]).  coarse / fine: model.Model.  Inference only."""
+    lib = _lib.load()
+    cw, ch = _ndc_consts(height, width, focal)
+    if pose is not None:
+        pose = f32c(pose[:3, :4])
+        r0, r1 = (0, height) if rows is None else rows
+        n, dev, rays_ptr = (r1 - r0) * width, pose.device, None
+    else:
+        rays = f32c(rays)
+        r0 = r1 = 0
+        n, dev, rays_ptr = rays.shape[0], rays.device, ptr(rays)
+    rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    rgb_c = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    if n == 0:
+        return rgb, rgb_c
+    scratch = torch.empty(int(lib.nerf_render_scratch_bytes(n, n_coarse, n_fine)), dtype=torch.uint8, device=dev)
+    pk_c, ht_c, pk_f, ht_f = coarse.packed(), coarse.host_tail(), fine.packed(), fine.host_tail()
+    events = None
+    if STATS.timed is not None:
+        # CUDA events around the two field-kernel launches, recorded by the C entry on the launch stream
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        for e in evs:
+            e.record(torch.cuda.current_stream(dev))      # creates the handle; re-recorded inside the call
+        events = (ctypes.c_void_p * 4)(*[e.cuda_event for e in evs])
+        STATS.timed.append((evs[0], evs[1], n * n_coarse))
+        STATS.timed.append((evs[2], evs[3], n * (n_coarse + n_fine)))
+    check(lib.nerf_render_fused(pk_c.data_ptr(), ht_c.data_ptr(), pk_f.data_ptr(), ht_f.data_ptr(), height, width,
+                                _f32(focal), cw, ch, ptr(pose), r0, r1, rays_ptr, n, int(bool(ndc)), _f32(near), _f32(far),
+                                n_coarse, n_fine, float(perturb), float(noise), int(bool(white_bkg)), rng.key, rng.ray0,
+                                scratch.data_ptr(), ptr(rgb), ptr(rgb_c), events, torch.cuda.current_stream(dev).cuda_stream),
+          "nerf_render_fused", launches=8 + (1 if pose is not None else 0))
+    return rgb, rgb_c
+
+
 def packed_model_bytes():
     return int(_lib.load().nerf_packed_model_bytes())
 

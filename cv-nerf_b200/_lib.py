@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnerf_b200.so")
+LIB_PATH = os.environ.get("NERF_B200_LIB") or os.path.join(_HERE, "libnerf_b200.so")
 
 c_float_p = ctypes.c_void_p  # device pointers travel as integers
 _lib = None
@@ -75,7 +75,9 @@ _SIGNATURES = {
     "nerf_mlp_fwd_host_tail": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p,
                                               ctypes.c_int, ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int,
                                               c_float_p, ctypes.c_void_p]),
-    "nerf_mlp_fwd_use_pairs": (ctypes.c_int, [ctypes.c_int]),
+    "nerf_mlp_fwd_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int,
+                                          ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p,
+                                          ctypes.c_int, c_float_p, ctypes.c_void_p]),
     "nerf_packed_model_bwd_bytes": (ctypes.c_size_t, []),
     "nerf_pack_model_bwd": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p]),
     "nerf_pack_models_train": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
@@ -109,11 +111,10 @@ _SIGNATURES = {
                                        ctypes.c_void_p]),
 }
 
-# debug / test-only symbols that are exported but not part of the public header
-_DEBUG_SIGNATURES = {
-    "nerf_mlp_fwd_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int,
-                                          ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p,
-                                          ctypes.c_int, c_float_p, ctypes.c_void_p]),
+# symbols of the experiments build only (make -C cv-nerf_b200/csrc experiments; NERF_B200_LIB selects the
+# library): the round-1 design alternatives of the field kernel and their cycle-counter entry
+_EXPERIMENT_SIGNATURES = {
+    "nerf_mlp_fwd_use_pairs": (ctypes.c_int, [ctypes.c_int]),
     "nerf_mlp_fwd_stats": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_long, ctypes.c_int,
                                           c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
@@ -127,6 +128,11 @@ def public_symbols():
     return sorted(_SIGNATURES)
 
 
+def has_experiments():
+    """True when the loaded library is the experiments build (libnerf_b200_exp.so)."""
+    return hasattr(load(), "nerf_mlp_fwd_use_pairs")
+
+
 def load():
     """Load libnerf_b200.so (once) and attach prototypes.  Raises if it is not built."""
     global _lib
@@ -137,8 +143,12 @@ def load():
             f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU fallback "
             "(run `python -c 'import __graft_entry__ as g; g.build()'`)")
     lib = ctypes.CDLL(LIB_PATH)
-    for table in (_SIGNATURES, _DEBUG_SIGNATURES):
-        for name, (res, args) in table.items():
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    for name, (res, args) in _EXPERIMENT_SIGNATURES.items():
+        if hasattr(lib, name):
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args

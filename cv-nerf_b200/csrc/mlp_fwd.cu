@@ -938,6 +938,11 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
     }
 }
 
+#ifdef NERF_B200_EXPERIMENTS
+// The kernels from here to the matching #endif are the round-1 design alternatives that LOST against
+// mlp_fwd_kernel (DESIGN.md section 4.1 has the measurements).  They are kept as evidence and for A/B
+// timing, and are compiled only into the experiments build (`make experiments` ->
+// libnerf_b200_exp.so); the shipped library contains the production kernels only.
 // ---------------------------------------------------------------------------- TS kernel
 // Inference variant whose activations never touch shared memory: the epilogue writes the BF16
 // activations of a layer straight into TENSOR MEMORY (tcgen05.st) and the next layer's MMA reads its
@@ -1841,6 +1846,8 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P, const __grid_constant__
     }
 }
 
+#endif  // NERF_B200_EXPERIMENTS
+
 using FwdKernel = void (*)(const FwdParams);   // (__grid_constant__ does not change the type)
 
 // variant 0 = production; 1 = probe (production config + debug outputs);
@@ -1849,14 +1856,15 @@ FwdKernel fwd_variant(int v) {
     switch (v) {
         case 0: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>>;                    // PE in the A tile, three weight slots
         case 1: return mlp_fwd_kernel<true, Cfg<kRing, false>>;
+        case 8: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>, true>;   // training: saves activations (PE in the A tile, three slots)
+        case 9: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>, false, true>;      // inference with the host tail (production)
+#ifdef NERF_B200_EXPERIMENTS
         case 2: return mlp_fwd_kernel<true, Cfg<1, false>>;
         case 3: return mlp_fwd_kernel<true, Cfg<3, true>>;
         case 4: return mlp_fwd_kernel<true, Cfg<kRing, false, 1>>;
         case 5: return mlp_fwd_kernel<true, Cfg<kRing, false, 2>>;
         case 6: return mlp_fwd_kernel<true, Cfg<kRing, false, 4>>;
         case 7: return mlp_fwd_kernel<true, Cfg<kRing, false, 7>>;
-        case 8: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>, true>;   // training: saves activations (PE in the A tile, three slots)
-        case 9: return mlp_fwd_kernel<false, Cfg<3, false, 0, true>, false, true>;      // inference with the host tail (production)
         case 10: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true, true>;   // + 16-warp epilogue crew
         case 11: return mlp_fwd_kernel<true, Cfg<kRing, false, 8>>;
         case 12: return mlp_fwd_kernel<false, Cfg<kRing, false>, true>;       // training forward, round-1 layout: PE tiles + two slots (A/B)
@@ -1866,19 +1874,29 @@ FwdKernel fwd_variant(int v) {
         case 16: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;            // host tail, round-1 layout: PE tiles + two weight slots (A/B)
         case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
         case 18: return mlp_fwd_kernel<false, Cfg<3, false, 2048, true>, false, true>;    // production + sampled wait profile (trace_out[0..50) slot waits, [64..84) A waits, [100] pairs)
+#endif
         default: return nullptr;
     }
 }
 
 int launch_fwd(const FwdParams& P, int variant, void* stream) {
-    static int sm_count = 0;
-    static bool configured[19] = {};
+    // per device (a process may hold tensors on several GPUs; the entry points switch to the buffers'
+    // device): SM count, and the opt-in shared-memory size, which is a per-device function attribute
+    constexpr int kMaxDevices = 64;
+    static int sm_counts[kMaxDevices] = {};
+    static bool configured_dev[kMaxDevices][19] = {};
     FwdKernel k = fwd_variant(variant);
     if (!k) return nerf::arg_error("nerf_mlp_fwd: variant");
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        nerf::set_last_error("nerf_mlp_fwd setup: %s", e0 != cudaSuccess ? cudaGetErrorString(e0) : "device index");
+        return e0 != cudaSuccess ? (int)e0 : NERF_ERR_UNSUPPORTED;
+    }
+    int& sm_count = sm_counts[dev];
+    bool* configured = configured_dev[dev];
     if (sm_count == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) {
             sm_count = 0;
             nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
@@ -1900,6 +1918,7 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
     return nerf::check_launch("nerf_mlp_fwd");
 }
 
+#ifdef NERF_B200_EXPERIMENTS
 // measured on B200 (profiles/r01_fwd_variants_ncu.txt): 0 is the fastest of the three
 int g_use_pairs = 0;
 
@@ -2031,6 +2050,8 @@ int launch_fwd_pair(const FwdParams& P, void* stream, int mode = 0) {
     return nerf::check_launch("nerf_mlp_fwd (CTA pairs)");
 }
 
+#endif  // NERF_B200_EXPERIMENTS
+
 int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0, const float* in1,
                 int in_stride, long M, int S, const float* vterm, int vterm_div, float* raw_out) {
     if (M < 0 || vterm_div < 1) return nerf::arg_error("nerf_mlp_fwd");
@@ -2061,8 +2082,11 @@ extern "C" int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, c
     if (M == 0) return 0;
     if (act_save && ((uintptr_t)act_save & 15)) return nerf::arg_error("nerf_mlp_fwd: act_save must be 16-byte aligned");
     P.act_save = (uint8_t*)act_save;
+#ifdef NERF_B200_EXPERIMENTS
     static const bool old_layout = getenv("NERF_B200_EXP_SAVE_OLD_LAYOUT") != nullptr;   // A/B timing only
-    return launch_fwd(P, act_save ? (old_layout ? 12 : 8) : 0, stream);
+    if (act_save && old_layout) return launch_fwd(P, 12, stream);
+#endif
+    return launch_fwd(P, act_save ? 8 : 0, stream);
 }
 
 extern "C" size_t nerf_model_host_tail_bytes(void) { return sizeof(ConstTail); }
@@ -2092,14 +2116,19 @@ extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail,
     if (rc) return rc;
     if (M == 0) return 0;
     memcpy(&P.ct, host_tail, sizeof(ConstTail));
+#ifndef NERF_B200_EXPERIMENTS
+    return launch_fwd(P, 9, stream);
+#else
     if (g_use_pairs == 3) return launch_fwd_tr(P, stream);
     if (g_use_pairs == 4) return launch_fwd_ts(P, stream);
     if (g_use_pairs == 5) return launch_fwd_pair(P, stream, 1);
     if (g_use_pairs == 6) return launch_fwd_pair(P, stream, 2);
     if (g_use_pairs == 7) return launch_fwd_pair(P, stream, 3);
     return g_use_pairs == 1 ? launch_fwd_pair(P, stream) : launch_fwd(P, g_use_pairs == 2 ? 10 : 9, stream);
+#endif
 }
 
+#ifdef NERF_B200_EXPERIMENTS
 // Kernel behind nerf_mlp_fwd_host_tail: 0 (default) single CTA per SM; 1 CTA pairs (tcgen05
 // cta_group::2, half the weight bytes staged and read per SM); 2 single CTA with one 16-warp epilogue
 // crew.  All give the same results; the switch exists for A/B timing and tests.
@@ -2109,7 +2138,9 @@ extern "C" int nerf_mlp_fwd_use_pairs(int enable) {
     return old;
 }
 
-// Debug entry (tests only): additionally dumps the FP32 post-activation output of MMA layer
+#endif  // NERF_B200_EXPERIMENTS
+
+// Test-support entry: additionally dumps the FP32 post-activation output of MMA layer
 // `probe_layer` (0 = l1 ... 8 = l9, 9 = l10; 256 floats per row, l10 uses the first 128).
 extern "C" int nerf_mlp_fwd_probe(const void* packed, int in_mode, const float* in0, const float* in1,
                                   int in_stride, long M, int S, const float* vterm, int vterm_div,
@@ -2123,6 +2154,7 @@ extern "C" int nerf_mlp_fwd_probe(const void* packed, int in_mode, const float* 
     return launch_fwd(P, 1, stream);
 }
 
+#ifdef NERF_B200_EXPERIMENTS
 // Debug entry (tools/gpu_diag.py): run a pipeline variant and collect per-CTA cycle counters
 // (stats_out [148][8] int64).  Variants other than 1 exist to time the pipeline only.
 extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const float* z, long M, int S,
@@ -2165,6 +2197,8 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
     }
     return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }
+
+#endif  // NERF_B200_EXPERIMENTS
 
 extern "C" size_t nerf_mlp_act_bytes(long M) {
     return M <= 0 ? 0 : (size_t)((M + kTileM - 1) / kTileM) * nerf::kActTileBytes;

@@ -200,18 +200,13 @@ int nerf_model_host_tail(const void* packed, void* host_tail_out, void* stream);
 int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail, int in_mode, const float* in0,
                            const float* in1, int in_stride, long M, int S, const float* vterm,
                            int vterm_div, float* raw_out, void* stream);
-/* Kernel variant behind nerf_mlp_fwd_host_tail (A/B timing and tests; -1 only queries; returns the
- * previous setting):
- *   0 (default) one CTA per SM, PE block inside the A tile, three 32 KB weight slots
- *   1 CTA pairs (tcgen05 cta_group::2, clusters of 2: each CTA stages half of every weight chunk)
- *   2 one CTA per SM with a single 16-warp epilogue crew
- *   3 mixed orientation (transposed trunk)       4 TS form (activations in tensor memory)
- *   5 CTA pairs + 16-warp crew                    6 / 7 as 1 / 5 with tensor-map weight copies that
- *                                                 complete on the leader CTA's barrier
- * All compute the same contraction.  0 and 2 sum l6's PE chunk after its h5 chunks, the others before
- * them: bit-identical inside each family, equal up to a BF16 rounding boundary of h6 across them
- * (tests/test_gpu_kernels.py::test_field_kernel_variants_agree). */
-int nerf_mlp_fwd_use_pairs(int enable);
+/* Test support: nerf_mlp_fwd that additionally writes the FP32 post-activation output of tensor-core
+ * layer `probe_layer` (0 = l1 ... 8 = l9, 9 = l10) to probe_out [M,256] (l10 fills the first 128
+ * columns).  The layer-by-layer parity tests compare it with a CPU emulation of the kernel's rounding
+ * points (tests/test_gpu_kernels.py::test_field_embedded_mode_layers). */
+int nerf_mlp_fwd_probe(const void* packed, int in_mode, const float* in0, const float* in1,
+                       int in_stride, long M, int S, const float* vterm, int vterm_div,
+                       float* raw_out, int probe_layer, float* probe_out, void* stream);
 
 /* ---------------------------------------------------------------- training: backward of the field
  * Replaces autograd through Model.forward for loss.backward(), main.py:385.  Three stages:

@@ -65,6 +65,9 @@ def load():
         loaded[name] = mod
     ref_main = loaded["main"]
     ref_main.batchify_rays = ref_main.batch_rays
+    # main.py:15 picks "cuda" when a GPU is visible; this is the CPU baseline, so its models stay on the
+    # host like its inputs (on the GPU box the module would otherwise mix devices)
+    ref_main.device = torch.device("cpu")
     torch.autograd.set_detect_anomaly(False)      # main.py:16 switches it on at import; irrelevant to a no_grad render
     return ref_main
 

@@ -297,6 +297,14 @@ def test_field_kernel_variants_agree(rows, S):
     saved_raw = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, act_save=act)
     assert torch.equal(probe_raw, base), (probe_raw - base).abs().max().item()
     assert torch.equal(saved_raw, base), (saved_raw - base).abs().max().item()
+    single = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)
+    assert torch.equal(single, base), (single - base).abs().max().item()
+    from cv_nerf_b200 import _lib
+    if not _lib.has_experiments():
+        # the shipped library holds the production kernels only (four builds of mlp_fwd_kernel: device
+        # tail, host tail, activation-saving, probe -- all compared above); the round-1 design alternatives
+        # live in the experiments build: NERF_B200_LIB=cv-nerf_b200/libnerf_b200_exp.so pytest ...
+        return
     old = K.use_pairs(0)
     try:
         single = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, S, vt, S, host_tail=ht)

@@ -28,7 +28,7 @@ def _nets(seed, sigma_bias=1.0, sigma_gain=5.0):
 
 
 def _frame_vs_oracle(tag, h, w, f, pose, cp, fp, coarse, fine, *, ndc, near, far, white_bkg, n_check, seed,
-                     max_flip_frac=0.05, rgb_tol=RGB_TOL, frac_over_1e2=0.0, emulate=False):
+                     max_flip_frac=0.05, rgb_tol=RGB_TOL, rgb_tol_fine=None, frac_over_1e2=0.0, emulate=False):
     """Full frame on the GPU, `n_check` random pixels of it on the CPU oracle; returns the stats.
     ``emulate``: additionally restate the kernel's BF16 rounding points on the CPU (helpers.emulate_field)
     for the checked rays' coarse samples and require the GPU to match THAT tightly -- separates "this
@@ -62,7 +62,7 @@ def _frame_vs_oracle(tag, h, w, f, pose, cp, fp, coarse, fine, *, ndc, near, far
         st["raw_absmax_ref"] = ref[raw_key].abs().max().item()
         print(tag, key, st)
         record("frame_parity", dict(case=tag, output=key, frame=f"{h}x{w}", checked=n_check, **st))
-        assert st["max_noflip"] <= rgb_tol, (tag, key, st)
+        assert st["max_noflip"] <= (rgb_tol_fine if key == "rgb_map" and rgb_tol_fine else rgb_tol), (tag, key, st)
         assert st["n_gt_1e-2"] - st["n_flip"] <= frac_over_1e2 * n_check, (tag, key, st)
         assert st["n_flip"] <= max(2, int(n_check * max_flip_frac)), (tag, key, st)
         out[key] = (got, ref[key], st)
@@ -81,7 +81,21 @@ def _frame_vs_oracle(tag, h, w, f, pose, cp, fp, coarse, fine, *, ndc, near, far
               "raw_rel_l2_vs_emulation": ((raw_got - raw_emu).norm() / raw_emu.norm()).item(),
               "rgb_c_max_abs_vs_emulation": (got_c - rgb_emu).abs().max().item(),
               "rgb_c_emulation_vs_fp32_max_abs": (rgb_emu - ref["rgb_c"]).abs().max().item()}
-        print(tag, "coarse pass vs the CPU emulation of BF16 tensor-core math:", st)
+        # fine pass on the GPU's own fine depths (the resampling amplifies the coarse differences: a sample
+        # lands on the other side of a density edge), so that only the field's arithmetic is compared
+        z_f = ex["z_f"].reshape(h * w, -1)[di].cpu()
+        s_f = z_f.shape[1]
+        pts_f = rays[:, None, 0:3] + rays[:, None, 3:6] * z_f[:, :, None]
+        vt_f = vterm_reference(fp, rays[:, 8:11])[:, None].expand(n_check, s_f, 128).reshape(-1, 128)
+        raw_f_emu = emulate_field(fp, O.freq_encode(pts_f.reshape(-1, 3), 10), vt_f).reshape(n_check, s_f, 4)
+        raw_f_fp32 = O.query_field(fp, pts_f, rays[:, 8:11])
+        rgb_f_emu, _ = O.composite(raw_f_emu, z_f, rays[:, 3:6], None, white_bkg)
+        rgb_f_fp32, _ = O.composite(raw_f_fp32, z_f, rays[:, 3:6], None, white_bkg)
+        got_f = rgb.reshape(-1, 3)[di].cpu()
+        st.update({"rgb_f_max_abs_vs_emulation_same_depths": (got_f - rgb_f_emu).abs().max().item(),
+                   "rgb_f_max_abs_vs_fp32_same_depths": (got_f - rgb_f_fp32).abs().max().item(),
+                   "rgb_f_frac_gt_1e-2_vs_fp32_same_depths": ((got_f - rgb_f_fp32).abs().amax(-1) > 1e-2).float().mean().item()})
+        print(tag, "vs the CPU emulation of BF16 tensor-core math:", st)
         record("frame_vs_bf16_emulation", dict(case=tag, **st))
         out["emulation"] = st
     # north_star's PSNR criterion against a synthetic target correlated with the image
@@ -154,14 +168,19 @@ def test_sharpened_weights_parity():
     # A sharp field (|sigma| up to ~130 here) amplifies the BF16 rounding of the activations: SURVEY.md
     # App. C measured max-abs 3.6e-2 (excluding flips) for a BF16 EMULATION OF THE REFERENCE on a sharp
     # density head, i.e. the north_star's 1e-2 is not attainable by BF16 MLP math on such weights.  So:
-    # (1) <= 5e-2 for every non-flip ray and <= 1e-2 for at least 95 % of them against the fp32 oracle,
-    # (2) PSNR delta <= 0.1 dB (north_star's second criterion; asserted inside), and
-    # (3) the GPU agrees with the CPU emulation of BF16 tensor-core math to 2e-3 -- what is left against
-    #     fp32 is the number format, not the kernel.
+    # (1) against the fp32 oracle: <= 1e-2 for at least 95 % of the non-flip rays; <= 5e-2 for every
+    #     coarse pixel (measured 2.5e-2..3.0e-2); the fine pass additionally moves its samples (inverse-CDF
+    #     resampling of slightly different coarse weights puts a sample on the other side of a density
+    #     edge): measured 0.12 on the worst of 2048 pixels, bounded at 0.25;
+    # (2) PSNR delta <= 0.1 dB (north_star's second criterion; asserted inside);
+    # (3) the GPU agrees with the CPU emulation of BF16 tensor-core math to 2e-3 in both passes (the fine
+    #     pass on the GPU's own depths) -- what is left against fp32 is the number format, not the kernel.
     out = _frame_vs_oracle("lego400_trained", h, w, f, pose, trained[0], trained[1], coarse, fine, ndc=False, near=2.,
-                           far=6., white_bkg=True, n_check=2048, seed=13, rgb_tol=5e-2, frac_over_1e2=0.05, emulate=True)
+                           far=6., white_bkg=True, n_check=2048, seed=13, rgb_tol=5e-2, rgb_tol_fine=0.25,
+                           frac_over_1e2=0.05, emulate=True)
     emu = out["emulation"]
     assert emu["rgb_c_max_abs_vs_emulation"] <= 2e-3, emu
+    assert emu["rgb_f_max_abs_vs_emulation_same_depths"] <= 2e-3, emu
     assert emu["raw_rel_l2_vs_emulation"] <= 1e-3, emu
     got, want, _ = out["rgb_map"]
     spread = want.std().item()

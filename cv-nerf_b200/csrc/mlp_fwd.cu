@@ -337,6 +337,64 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tacc, int c0_rt, uint32
     if (MODE == 1) sigma += sig2.x + sig2.y;
 }
 
+// The same arithmetic with 32-column TMEM loads (inference, biases in the kernel parameters): four
+// tcgen05.ld.x32 per thread and layer instead of eight .x16, each in flight while the previous 32 columns
+// are processed.  tcgen05.wait::ld waits for every outstanding load of the thread, so the depth of the
+// pipeline is one load whatever its width; wider loads halve the number of exposed load latencies, which
+// is what the sub-tile's accumulator -> A-operand chain consists of (the instructions themselves need
+// ~400 issue cycles of the ~1950 the epilogue takes).  Bit-identical results.
+template <int MODE, int C0>
+__device__ __forceinline__ void epilogue_hidden_w32(uint32_t tacc, uint32_t row_addr, uint32_t swz, float& sigma,
+                                                    const ConstTail& ct, int l) {
+    uint32_t v[2][32];
+    float2 sig2 = make_float2(0.f, 0.f);
+    umma::tmem_ld32(tacc + C0, v[0]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        umma::tmem_wait_ld();
+        if (g + 1 < 4) umma::tmem_ld32(tacc + C0 + 32 * (g + 1), v[(g + 1) & 1]);
+        const uint32_t(&cur)[32] = v[g & 1];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int c = C0 + g * 32 + hh * 16;
+            float2 h[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 bl = *reinterpret_cast<const float4*>(ct.bias + l * kHidden + c + q * 4);
+                h[2 * q] = __fadd2_rn(make_float2(__uint_as_float(cur[hh * 16 + q * 4 + 0]), __uint_as_float(cur[hh * 16 + q * 4 + 1])),
+                                      make_float2(bl.x, bl.y));
+                h[2 * q + 1] = __fadd2_rn(make_float2(__uint_as_float(cur[hh * 16 + q * 4 + 2]), __uint_as_float(cur[hh * 16 + q * 4 + 3])),
+                                          make_float2(bl.z, bl.w));
+            }
+            if (MODE == 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w = *reinterpret_cast<const float4*>(ct.walpha + c + q * 4);
+                    h[2 * q].x = fmaxf(h[2 * q].x, 0.f); h[2 * q].y = fmaxf(h[2 * q].y, 0.f);
+                    h[2 * q + 1].x = fmaxf(h[2 * q + 1].x, 0.f); h[2 * q + 1].y = fmaxf(h[2 * q + 1].y, 0.f);
+                    sig2 = __ffma2_rn(make_float2(w.x, w.y), h[2 * q], sig2);
+                    sig2 = __ffma2_rn(make_float2(w.z, w.w), h[2 * q + 1], sig2);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t o0, o1, o2, o3;
+                if (MODE == 0) {
+                    o0 = pack_relu_bf16x2(h[q * 4 + 0].x, h[q * 4 + 0].y); o1 = pack_relu_bf16x2(h[q * 4 + 1].x, h[q * 4 + 1].y);
+                    o2 = pack_relu_bf16x2(h[q * 4 + 2].x, h[q * 4 + 2].y); o3 = pack_relu_bf16x2(h[q * 4 + 3].x, h[q * 4 + 3].y);
+                } else {
+                    o0 = pack_bf16x2(h[q * 4 + 0].x, h[q * 4 + 0].y); o1 = pack_bf16x2(h[q * 4 + 1].x, h[q * 4 + 1].y);
+                    o2 = pack_bf16x2(h[q * 4 + 2].x, h[q * 4 + 2].y); o3 = pack_bf16x2(h[q * 4 + 3].x, h[q * 4 + 3].y);
+                }
+                const int cc = c + q * 8;
+                const int blk = cc >> 6, c16 = (cc & 63) >> 3;
+                umma::st_shared_v4(row_addr + blk * 16384 + ((uint32_t)(c16 << 4) ^ swz), o0, o1, o2, o3);
+            }
+        }
+    }
+    if (MODE == 1) sigma += sig2.x + sig2.y;
+}
+
 // CT epilogue of hidden layer l (0..8) with the layer index turned into a template constant.
 template <int NIT, int EXP = 0, int C0 = -1>
 __device__ __forceinline__ void epilogue_hidden_ct(int l, uint32_t tacc, int c0, uint32_t row_addr, uint32_t swz,
@@ -354,6 +412,13 @@ __device__ __forceinline__ void epilogue_hidden_ct(int l, uint32_t tacc, int c0,
             default: epilogue_hidden<2, false, EXP, true, NIT, 8, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 8); break;
 #undef NERF_CT_LAYER
         }
+        return;
+    }
+    if ((EXP & 16384) && NIT == 8 && C0 >= 0) {     // EXP bit14: 32-column TMEM loads
+        constexpr int C = C0 >= 0 ? C0 : 0;
+        if (l < 7) epilogue_hidden_w32<0, C>(tacc, row_addr, swz, sigma, ct, (int)__reduce_max_sync(0xffffffffu, (unsigned)l));
+        else if (l == 7) epilogue_hidden_w32<1, C>(tacc, row_addr, swz, sigma, ct, 7);
+        else epilogue_hidden_w32<2, C>(tacc, row_addr, swz, sigma, ct, 8);
         return;
     }
     // (the warp-wide reduction hands the compiler a value it knows to be uniform: REDUX writes a uniform register)
@@ -437,8 +502,7 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
 // The MMA -> epilogue -> MMA chain of a sub-tile is latency-bound on the epilogue; with twice the
 // warps on it the next layer's operand is ready in about half the time and the tensor core idles less.
 template <bool PROBE, class CFG, bool SAVE = false, bool CT = false, bool WIDE = false>
-__global__ void __launch_bounds__(CFG::two_producers ? kThreadsFwd2 : kThreads, 1)
-mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
+__device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
     static_assert(!WIDE || (CT && !SAVE && !PROBE), "WIDE is an inference-only variant");
     constexpr bool kPEA = CFG::pea;
     static_assert(!kPEA || (!WIDE && !PROBE), "PEA is implemented for the 8-warp epilogue groups");
@@ -840,8 +904,8 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
                 if (l < 9) {
                     const int c0 = half * 128;
                     if (CT && !PROBE) {
-                        if (half == 0) epilogue_hidden_ct<8, CFG::exp & (7 | 64 | 8192), 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
-                        else epilogue_hidden_ct<8, CFG::exp & (7 | 64 | 8192), 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
+                        if (half == 0) epilogue_hidden_ct<8, CFG::exp & (7 | 64 | 8192 | 16384), 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
+                        else epilogue_hidden_ct<8, CFG::exp & (7 | 64 | 8192 | 16384), 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
                     } else if (l == 7) {
                         epilogue_hidden<1, PROBE, CFG::exp, CT, 8, -1, SAVE>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row, P.ct, l, mw);
                     } else if (l == 8) {
@@ -936,6 +1000,20 @@ mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
         umma::tc_fence_after();
         umma::tmem_dealloc(tmem_base, 512);
     }
+}
+
+template <bool PROBE, class CFG, bool SAVE = false, bool CT = false, bool WIDE = false>
+__global__ void __launch_bounds__(CFG::two_producers ? kThreadsFwd2 : kThreads, 1)
+mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
+    mlp_fwd_body<PROBE, CFG, SAVE, CT, WIDE>(P);
+}
+
+// The same body with a 112-register budget (576 threads x 112 = 64 512 of the SM's 65 536 registers;
+// with __launch_bounds__(576, 1) ptxas stops at 96): room for the 2 x 32-register accumulator buffers
+// of the 32-column epilogue.
+template <bool PROBE, class CFG, bool SAVE = false, bool CT = false, bool WIDE = false>
+__global__ void __maxnreg__(112) mlp_fwd_kernel_r112(const __grid_constant__ FwdParams P) {
+    mlp_fwd_body<PROBE, CFG, SAVE, CT, WIDE>(P);
 }
 
 #ifdef NERF_B200_EXPERIMENTS
@@ -1874,6 +1952,9 @@ FwdKernel fwd_variant(int v) {
         case 16: return mlp_fwd_kernel<false, Cfg<kRing, false>, false, true>;            // host tail, round-1 layout: PE tiles + two weight slots (A/B)
         case 17: return mlp_fwd_kernel<false, Cfg<kRing, false, 128>, false, true>;       // host tail, whole-warp MMA issuer with elect.sync (A/B)
         case 18: return mlp_fwd_kernel<false, Cfg<3, false, 2048, true>, false, true>;    // production + sampled wait profile (trace_out[0..50) slot waits, [64..84) A waits, [100] pairs)
+        case 19: return mlp_fwd_kernel<false, Cfg<3, false, 16384, true>, false, true>;   // production with 32-column TMEM loads in the hidden epilogue (A/B)
+        case 20: return mlp_fwd_kernel_r112<false, Cfg<3, false, 16384, true>, false, true>;   // ... and a 112-register budget
+        case 21: return mlp_fwd_kernel_r112<false, Cfg<3, false, 0, true>, false, true>;       // production with a 112-register budget (A/B)
 #endif
         default: return nullptr;
     }
@@ -1884,7 +1965,7 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
     // device): SM count, and the opt-in shared-memory size, which is a per-device function attribute
     constexpr int kMaxDevices = 64;
     static int sm_counts[kMaxDevices] = {};
-    static bool configured_dev[kMaxDevices][19] = {};
+    static bool configured_dev[kMaxDevices][24] = {};
     FwdKernel k = fwd_variant(variant);
     if (!k) return nerf::arg_error("nerf_mlp_fwd: variant");
     int dev = 0;
@@ -2191,7 +2272,7 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
         if (e != cudaSuccess) return (int)e;
         return launch_fwd_ts(P, stream);
     }
-    if (variant == 9 || variant == 10 || (variant >= 13 && variant <= 18)) {   // host-tail kernels
+    if (variant == 9 || variant == 10 || (variant >= 13 && variant <= 23)) {   // host-tail kernels
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
     }

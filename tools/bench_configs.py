@@ -65,11 +65,19 @@ def timed(fn, reps):
 # ---- configs[2]: fern shape, NDC, single frame + train step -----------------------------------
 H, W, F = 378, 504, np.float32(407.5657)
 fern_pose = torch.from_numpy(g["train_poses"][3]).to(dev)
-if rank == 0:
+from cv_nerf_b200 import parallel as P  # noqa: E402
+bounds = P.row_bounds(H, world)
+
+
+def fern_frame():
     with torch.no_grad():
-        sec = timed(lambda: M.render(H, W, F, c2w=fern_pose, **kw), 5)
-    emit(config="fern 378x504 NDC render, 64+128 samples", metric="rendered rays/sec", value=H * W / sec, unit="rays/s",
-         ms_per_frame=sec * 1e3, n_gpus=1)
+        rgb, _ = M.render(H, W, F, c2w=fern_pose, rows=(bounds[rank], bounds[rank + 1]), **kw)
+        P.all_gather_rows(rgb, H)
+
+
+sec = timed(fern_frame, 5)
+emit(config="fern 378x504 NDC render, 64+128 samples, rows sharded over the GPUs", metric="rendered rays/sec",
+     value=H * W / sec, unit="rays/s", ms_per_frame=sec * 1e3, n_gpus=world)
 ts = TrainStep(coarse, fine, height=H, width=W, focal=F, n_rays=4096, perturb=1., noise=1., white_bkg=False, ndc=True,
                near=0., far=1., lr=5e-4, lr_decay=250, seed=rank)
 image = torch.rand(H, W, 3, device=dev)

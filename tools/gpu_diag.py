@@ -124,21 +124,35 @@ def ab(variants, rounds=6):
     raw = torch.empty(n_rays * S, 4, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
     tot = {v: 0. for v in variants}
+    cyc = {v: 0. for v in variants}
+    first = None
+    stats = torch.zeros(148, 8, dtype=torch.int64, device=DEV)
     for rnd in range(rounds + 1):
         for v in variants:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(3):
+                # variants >= 9 write only their total cycle count per CTA into the counter block
                 rc = lib.nerf_mlp_fwd_stats(packed.data_ptr(), rays.data_ptr(), z.data_ptr(), n_rays * S, S,
-                                            vt.data_ptr(), raw.data_ptr(), v, 0, st)
+                                            vt.data_ptr(), raw.data_ptr(), v, stats.data_ptr() if v >= 9 else 0, st)
                 assert rc == 0, lib.nerf_b200_last_error()
             e1.record()
             torch.cuda.synchronize()
-            if rnd > 0:
+            if rnd == 0:
+                if first is None:
+                    first = raw.clone()
+                else:
+                    print(f"variant {v}: max |raw - raw(variant {variants[0]})| = {(raw - first).abs().max().item():.3e}"
+                          f"  bit-identical: {bool(torch.equal(raw, first))}")
+            else:
                 tot[v] += e0.elapsed_time(e1) / 3
+                if v >= 9:
+                    rows = stats[stats[:, 5] > 0, 5].double()
+                    cyc[v] += rows.mean().item() if rows.numel() else 0.
     for v in variants:
         ms = tot[v] / rounds
-        print(f"variant {v}: {ms:.3f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s (mean of {rounds} interleaved rounds)")
+        print(f"variant {v}: {ms:.3f} ms  {n_rays * S * 1186816 / ms / 1e9:.0f} TFLOP/s  cycles/CTA {cyc[v] / rounds:.4e} "
+              f"(mean of {rounds} interleaved rounds)")
 
 
 def pipeline_stats(variants=(9, 15, 16, 14)):

@@ -511,11 +511,11 @@ def time_train_stages(ts, image, pose):
     mark("composite+loss+bwd")
     K.mlp_bwd_dz(ts.fine.packed_bwd(), graw_f, ts.act_f, n * ts.s_f, dz=ts.dz)
     mark("dz_fine")
-    K.mlp_bwd_params(ts.act_f, ts.dz, graw_f, n * ts.s_f, rays, ts.s_f, False, ts.blob[1])
+    K.mlp_bwd_params(ts.act_f, ts.dz, graw_f, n * ts.s_f, rays, ts.s_f, False, ts.blob[1], params=ts.params[1])
     mark("dw_fine(+heads,view)")
     K.mlp_bwd_dz(ts.coarse.packed_bwd(), graw_c, ts.act_c, n * ts.s_c, dz=ts.dz)
     mark("dz_coarse")
-    K.mlp_bwd_params(ts.act_c, ts.dz, graw_c, n * ts.s_c, rays, ts.s_c, False, ts.blob[0])
+    K.mlp_bwd_params(ts.act_c, ts.dz, graw_c, n * ts.s_c, rays, ts.s_c, False, ts.blob[0], params=ts.params[0])
     mark("dw_coarse(+heads,view)")
     ts.apply_gradients(allreduce=False)     # this split runs on rank 0 only: no collectives here
     ts.coarse.packed(); ts.fine.packed(); ts.coarse.packed_bwd(); ts.fine.packed_bwd()

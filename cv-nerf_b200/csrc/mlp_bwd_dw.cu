@@ -36,7 +36,7 @@ constexpr int kDrainWarps = 8;
 constexpr int kThreads = 64 + kDrainWarps * 32;          // 320
 constexpr uint32_t kOffBar = kRing * kSlotBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 256;
-constexpr int kNumJobsLayers = 11;
+constexpr int kNumJobsLayers = 10;     // l1, l2..l5, l6 (PE), l6 (h5), l7, l8, l10' (l9 folded: G = dZ10^T h8)
 
 struct LayerJob {
     uint32_t a_off;      // byte offset of the dZ image inside a dZ tile record
@@ -250,7 +250,8 @@ extern "C" int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, flo
     DwParams P;
     P.act = (const uint8_t*)act_save; P.dz = (const uint8_t*)dz; P.grad = grad_blob;
     P.n_tiles = (M + kTileRows - 1) / kTileRows;
-    // layer table: l1, l2..l5, l6 (PE columns), l6 (h5 columns), l7, l8, l9, l10
+    // layer table: l1, l2..l5, l6 (PE columns), l6 (h5 columns), l7, l8, and the folded l10': G = dZ10^T . h8
+    // into the scratch region of the blob (nerf_mlp_bwd_unfold turns it into the gradients of l9 and l10)
     int k = 0;
     auto add = [&](size_t a_off, int a_blocks, size_t b_off, int b_blocks, int out_off, int pitch, int bias_off) {
         LayerJob& j = P.jobs[k++];
@@ -261,8 +262,8 @@ extern "C" int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, flo
     for (int l = 2; l <= 5; ++l) add(dz_hidden(l), 4, act_hidden(l - 1), 4, grad_w_square(l), 256, kG_B + (l - 1) * 256);
     add(dz_hidden(6), 4, kActPE, 1, kG_W6, 320, -1);
     add(dz_hidden(6), 4, act_hidden(5), 4, kG_W6 + 64, 320, kG_B + 5 * 256);
-    for (int l = 7; l <= 9; ++l) add(dz_hidden(l), 4, act_hidden(l - 1), 4, grad_w_square(l), 256, kG_B + (l - 1) * 256);
-    add(kDz10, 2, act_hidden(9), 4, kG_W10, 288, -1);
+    for (int l = 7; l <= 8; ++l) add(dz_hidden(l), 4, act_hidden(l - 1), 4, grad_w_square(l), 256, kG_B + (l - 1) * 256);
+    add(kDz10, 2, act_hidden(8), 4, kG_Fold, 256, -1);
     // split the SMs over the layers in proportion to their traffic, at most one CTA per tile
     const long cap = P.n_tiles;
     int total = kNumJobsLayers;

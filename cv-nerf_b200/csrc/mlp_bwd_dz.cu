@@ -4,8 +4,9 @@
 // loop calls loss.backward() (/root/reference/main.py:385), restricted to the activations: for
 // each 128-sample tile
 //     dZ10 = (grad_rgb . W11) * [h10 > 0]                        CUDA cores, FP32
-//     dZ9  = dZ10 . W10[:, :256]                                  (l9 has no activation)
-//     dZ8  = (dZ9 . W9 + grad_sigma * w_alpha) * [h8 > 0]
+//     dZ8  = (dZ10 . W' + grad_sigma * w_alpha) * [h8 > 0]       W' = W10[:, :256] . W9: l9 has no
+//                                                                 activation and is folded into l10
+//                                                                 (mlp_layout.h), so there is no dZ9
 //     dZi  = (dZ(i+1) . W(i+1)) * [hi > 0]            i = 7..1    (l6 contributes its h5 columns)
 // as BF16 tensor-core contractions against the transposed weights (mlp_bwd_layout.h) with FP32
 // accumulation in tensor memory.  Every dZ tile is dumped to HBM as a tile image (one bulk copy
@@ -291,17 +292,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dz_kernel(const DzParams 
             umma::named_bar_sync(group_bar, kGroupThreads);
 #pragma unroll 1
             for (int j = 0; j < kBwdLayers; ++j) {
-                const int i = 9 - j;               // this epilogue produces dZ_i
+                const int i = 8 - j;               // this epilogue produces dZ_i
                 const int c0 = half * 128;
                 // one 16-byte load per thread and layer, issued before the accumulator wait
                 uint4 mk = make_uint4(0, 0, 0, 0);
-                if (j > 0 && tile_ok) mk = __ldg(reinterpret_cast<const uint4*>(act_tile + act_mask_slot(i - 1, row, half)));
+                if (tile_ok) mk = __ldg(reinterpret_cast<const uint4*>(act_tile + act_mask_slot(i - 1, row, half)));
                 umma::mbar_wait(bar_acc_full + 8 * g, n_full & 1);
                 ++n_full;
                 umma::tc_fence_after();
-                if (j == 0) {
-                    epilogue_dz<false, false>(tacc, c0, a_row_addr, swz, mk, 0.f, walpha_addr);
-                } else if (j == 1) {
+                if (j == 0) {          // dZ8: the sigma head's gradient joins here
                     epilogue_dz<true, true>(tacc, c0, a_row_addr, swz, mk, graw.w, walpha_addr);
                 } else {
                     epilogue_dz<true, false>(tacc, c0, a_row_addr, swz, mk, 0.f, walpha_addr);

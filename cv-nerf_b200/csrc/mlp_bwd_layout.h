@@ -20,10 +20,10 @@ constexpr size_t kBlockBytes = (size_t)kTileRows * 64 * 2;   // one [128][64] bl
 
 // ---- activation record of one tile (written by nerf_mlp_fwd with act_save) -------------------
 constexpr size_t kActPE = 0;                                  // PE10(point), 1 block (column 63 = 0)
-__host__ __device__ constexpr size_t act_hidden(int i) {      // i = 1..8: h_i (post-ReLU); 9: l9 output
+__host__ __device__ constexpr size_t act_hidden(int i) {      // i = 1..8: h_i (post-ReLU)
     return kBlockBytes + (size_t)(i - 1) * 4 * kBlockBytes;
 }
-constexpr size_t kActH10 = kBlockBytes + 9 * 4 * kBlockBytes; // h10 (post-ReLU), 2 blocks
+constexpr size_t kActH10 = kBlockBytes + 8 * 4 * kBlockBytes; // h10 (post-ReLU), 2 blocks
 // ReLU masks of h1..h8 and h10 as bits, for the dZ chain (which then never re-reads the BF16
 // activations): [9 layers][128 rows][2 column halves] x 16 bytes.  The thread that owns (row, half)
 // in the forward epilogue writes one uint4 per layer: word p covers its 16-column iterations 2p and
@@ -33,7 +33,7 @@ constexpr size_t kActH10 = kBlockBytes + 9 * 4 * kBlockBytes; // h10 (post-ReLU)
 constexpr size_t kActMasks = kActH10 + 2 * kBlockBytes;
 constexpr int kMaskLayers = 9;                                // index 0..7: h1..h8, 8: h10
 constexpr size_t kActMaskBytes = (size_t)kMaskLayers * kTileRows * 2 * 16;   // 36864
-constexpr size_t kActTileBytes = kActMasks + kActMaskBytes;   // 675840
+constexpr size_t kActTileBytes = kActMasks + kActMaskBytes;   // 610304
 __host__ __device__ constexpr size_t act_mask_slot(int layer, int row, int half) {
     return kActMasks + ((size_t)(layer * kTileRows + row) * 2 + half) * 16;
 }
@@ -42,19 +42,19 @@ __host__ __device__ constexpr uint32_t relu_mask_bits(int parity, int j) {
 }
 
 // ---- dZ record of one tile (written by nerf_mlp_bwd_dz) ---------------------------------------
-// dZ_i = dL/d(pre-activation of layer i): i = 1..8 trunk, 9 = l9 (no activation), 10 = l10.
+// dZ_i = dL/d(pre-activation of layer i): i = 1..8 trunk, 10 = l10 (l9 is folded into l10: no dZ9).
 __host__ __device__ constexpr size_t dz_hidden(int i) { return (size_t)(i - 1) * 4 * kBlockBytes; }
-constexpr size_t kDz10 = 9 * 4 * kBlockBytes;                 // 2 blocks
-constexpr size_t kDzTileBytes = kDz10 + 2 * kBlockBytes;      // 622592
+constexpr size_t kDz10 = 8 * 4 * kBlockBytes;                 // 2 blocks
+constexpr size_t kDzTileBytes = kDz10 + 2 * kBlockBytes;      // 557056
 
 // ---- transposed weights for the dZ chain (nerf_pack_model_bwd) --------------------------------
 // Stage = [128 rows n = input feature][64 columns k = output feature] of W^T, K-major swizzled.
-// Consumption order: l10[:, :256]^T (2 K chunks), then l9, l8, l7, l6[:, 63:], l5, l4, l3, l2
-// (4 K chunks each); every chunk has two 128-row halves, chunk-major / half-minor.
-constexpr int kBwdLayers = 9;
+// Consumption order: (l10[:, :256] . l9)^T (the folded W', 2 K chunks), then l8, l7, l6[:, 63:],
+// l5, l4, l3, l2 (4 K chunks each); every chunk has two 128-row halves, chunk-major / half-minor.
+constexpr int kBwdLayers = 8;
 __host__ __device__ constexpr int bwd_chunks(int j) { return j == 0 ? 2 : 4; }
 __host__ __device__ constexpr int bwd_first_stage(int j) { return j == 0 ? 0 : 4 + (j - 1) * 8; }
-constexpr int kBwdStages = 4 + 8 * 8;                         // 68
+constexpr int kBwdStages = 4 + 7 * 8;                         // 60
 constexpr size_t kBwdWeightBytes = (size_t)kBwdStages * kStageBytes;
 // fp32 tail: l_alpha.weight [256], l11.weight [3][128]
 constexpr int kBwdTailWAlpha = 0;
@@ -77,7 +77,10 @@ constexpr int kG_B = kG_W11 + 3 * 128;                        // [9][256] b1..b9
 constexpr int kG_BAlpha = kG_B + 9 * 256;                     // [4]
 constexpr int kG_B10 = kG_BAlpha + 4;                         // [128]
 constexpr int kG_B11 = kG_B10 + 128;                          // [4]
-constexpr int kGradFloats = kG_B11 + 4;
+// scratch behind the parameter gradients: G = dZ10^T . h8 [128][256], from which nerf_mlp_bwd_unfold
+// forms the gradients of l9 and of l10's first 256 columns (the optimizer never reads this region)
+constexpr int kG_Fold = kG_B11 + 4;                           // [128][256]
+constexpr int kGradFloats = kG_Fold + 128 * 256;
 static_assert(grad_w_square(2) == 256 * 64 && grad_w_square(5) + 65536 == kG_W6, "grad layout");
 static_assert(grad_w_square(7) == kG_W6 + 256 * 320 && grad_w_square(9) + 65536 == kG_W10, "grad layout");
 

@@ -3,6 +3,8 @@
 //   nerf_mlp_bwd_heads    dW/db of l_alpha (256 -> 1) and l11 (128 -> 3): 640 MAC per sample
 //   nerf_viewdir_term_bwd dW of l10's 27 view-direction columns and db of l10, through the per-ray
 //                         sum of dZ10 (the transpose of the hoisting nerf_viewdir_term does)
+//   nerf_mlp_bwd_unfold   gradients of l9 and of l10's first 256 columns from G = dZ10^T h8 (l9 is
+//                         folded into l10 in the forward and in the dZ chain, mlp_layout.h)
 //   nerf_grad_unpack      padded gradient blob -> the 24 .grad tensors of Model.parameters()
 //   nerf_mse_loss_grad    mean((rgb - target)^2) and its gradient (/root/reference/main.py:380-383)
 #include <cuda_bf16.h>
@@ -182,6 +184,43 @@ __global__ void __launch_bounds__(128) viewdir_term_bwd_kernel(const uint8_t* __
     atomicAdd(grad + kG_B10 + j, accb);
 }
 
+// ------------------------------------------------------------------ unfold (l9 folded into l10)
+// feat = W9 h8 + b9 feeds l10 without an activation (model.py:100-104), so with G = sum_rows dz10 (x) h8
+// (accumulated by the dW kernel into the blob's scratch region) and db10 = sum_rows dz10:
+//     dW10[:, :256] = G W9^T + db10 (x) b9          dW9 = W10a^T G          db9 = W10a^T db10
+// FP32 on CUDA cores, 16.8 M multiply-adds per network and step.  One thread per output element; every
+// element has a single writer, which ADDS to the blob like the other gradient kernels.
+__global__ void __launch_bounds__(256) unfold_kernel(float* __restrict__ grad, const float* __restrict__ w9,
+                                                     const float* __restrict__ b9, const float* __restrict__ w10) {
+    const float* G = grad + kG_Fold;
+    const float* db10 = grad + kG_B10;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t < 128 * 256) {                                     // dW10[o][i], o < 128, i < 256
+        const int o = t >> 8, i = t & 255;
+        const float4* g4 = reinterpret_cast<const float4*>(G + o * 256);
+        const float4* w4 = reinterpret_cast<const float4*>(w9 + (size_t)i * 256);
+        float acc = db10[o] * __ldg(b9 + i);
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) {
+            const float4 g = g4[k], w = __ldg(w4 + k);
+            acc = fmaf(g.x, w.x, acc); acc = fmaf(g.y, w.y, acc); acc = fmaf(g.z, w.z, acc); acc = fmaf(g.w, w.w, acc);
+        }
+        grad[kG_W10 + o * 288 + i] += acc;
+    } else if (t < 128 * 256 + 256 * 256) {                  // dW9[i][k], i, k < 256
+        const int u = t - 128 * 256;
+        const int i = u >> 8, k = u & 255;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int o = 0; o < 128; ++o) acc = fmaf(__ldg(w10 + (size_t)o * 283 + i), G[o * 256 + k], acc);
+        grad[grad_w_square(9) + i * 256 + k] += acc;
+    } else if (t < 128 * 256 + 256 * 256 + 256) {            // db9[i]
+        const int i = t - (128 * 256 + 256 * 256);
+        float acc = 0.f;
+        for (int o = 0; o < 128; ++o) acc = fmaf(__ldg(w10 + (size_t)o * 283 + i), db10[o], acc);
+        grad[kG_B + 8 * 256 + i] += acc;
+    }
+}
+
 // ------------------------------------------------------------------ blob -> .grad tensors
 struct UnpackPtrs {
     float* p[NERF_N_PARAM_TENSORS];
@@ -272,6 +311,15 @@ extern "C" int nerf_viewdir_term_bwd(const void* dz, const float* dirs, int dir_
     viewdir_term_bwd_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)dz, dirs, dir_stride,
                                                                              embedded, M, vterm_div, count, grad_blob);
     return nerf::check_launch("nerf_viewdir_term_bwd");
+}
+
+extern "C" int nerf_mlp_bwd_unfold(float* grad_blob, const float* l9_weight, const float* l9_bias,
+                                   const float* l10_weight, void* stream) {
+    nerf::DeviceGuard device_guard(grad_blob);
+    if (!grad_blob || !l9_weight || !l9_bias || !l10_weight) return nerf::arg_error("nerf_mlp_bwd_unfold");
+    constexpr int kItems = 128 * 256 + 256 * 256 + 256;
+    unfold_kernel<<<(kItems + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grad_blob, l9_weight, l9_bias, l10_weight);
+    return nerf::check_launch("nerf_mlp_bwd_unfold");
 }
 
 extern "C" int nerf_grad_unpack(const float* grad_blob, float* const* host_grads, int accumulate, void* stream) {

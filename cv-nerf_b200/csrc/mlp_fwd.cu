@@ -3,7 +3,8 @@
 // Replaces net_forward + FreqEmbedding.embed + Model.forward
 // (/root/reference/model.py:9-31, 77-131) and the point construction of render_rays
 // (/root/reference/main.py:238,252): sample position -> positional encoding -> 8x256 trunk with
-// the skip at l6 -> sigma head, l9, l10 (+ hoisted view term), l11 -> raw[rgb(3), sigma].
+// the skip at l6 -> sigma head, l9 folded into l10 (mlp_layout.h; + hoisted view term), l11 ->
+// raw[rgb(3), sigma].
 // Per-sample activations never leave the SM: BF16 activations live in shared memory, FP32
 // accumulators in tensor memory.
 //
@@ -408,8 +409,8 @@ __device__ __forceinline__ void epilogue_hidden_ct(int l, uint32_t tacc, int c0,
 #define NERF_CT_LAYER(LL, MODE) \
             case LL: epilogue_hidden<MODE, false, EXP, true, NIT, LL, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, LL); break;
             NERF_CT_LAYER(0, 0) NERF_CT_LAYER(1, 0) NERF_CT_LAYER(2, 0) NERF_CT_LAYER(3, 0) NERF_CT_LAYER(4, 0)
-            NERF_CT_LAYER(5, 0) NERF_CT_LAYER(6, 0) NERF_CT_LAYER(7, 1)
-            default: epilogue_hidden<2, false, EXP, true, NIT, 8, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 8); break;
+            NERF_CT_LAYER(5, 0) NERF_CT_LAYER(6, 0)
+            default: epilogue_hidden<1, false, EXP, true, NIT, 7, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 7); break;
 #undef NERF_CT_LAYER
         }
         return;
@@ -417,15 +418,13 @@ __device__ __forceinline__ void epilogue_hidden_ct(int l, uint32_t tacc, int c0,
     if ((EXP & 16384) && NIT == 8 && C0 >= 0) {     // EXP bit14: 32-column TMEM loads
         constexpr int C = C0 >= 0 ? C0 : 0;
         if (l < 7) epilogue_hidden_w32<0, C>(tacc, row_addr, swz, sigma, ct, (int)__reduce_max_sync(0xffffffffu, (unsigned)l));
-        else if (l == 7) epilogue_hidden_w32<1, C>(tacc, row_addr, swz, sigma, ct, 7);
-        else epilogue_hidden_w32<2, C>(tacc, row_addr, swz, sigma, ct, 8);
+        else epilogue_hidden_w32<1, C>(tacc, row_addr, swz, sigma, ct, 7);
         return;
     }
     // (the warp-wide reduction hands the compiler a value it knows to be uniform: REDUX writes a uniform register)
     if (l < 7) epilogue_hidden<0, false, EXP, true, NIT, -1, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct,
                                                                           (int)__reduce_max_sync(0xffffffffu, (unsigned)l));
-    else if (l == 7) epilogue_hidden<1, false, EXP, true, NIT, 7, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 7);
-    else epilogue_hidden<2, false, EXP, true, NIT, 8, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 8);
+    else epilogue_hidden<1, false, EXP, true, NIT, 7, false, C0>(tacc, c0, row_addr, swz, 0, nullptr, sigma, nullptr, ct, 7);
 }
 
 // l10 (+ hoisted view term, ReLU) and l11 in FP32 over this thread's 64 columns [c0, c0+64):
@@ -767,7 +766,7 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                     umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full[g] & 1);
                     ++n_full[g];
                     umma::tc_fence_after();
-                    if (l < 9) {
+                    if (l < kNumMmaLayers - 1) {
                         float sg = 0.f;
                         switch (cg) {
                             case 0: epilogue_hidden_ct<4, 0, 0>(l, tacc, 0, a_row_addr, swz, sg, P.ct); break;
@@ -883,7 +882,7 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
 #pragma unroll 1
             for (int l = 0; l < kNumMmaLayers; ++l) {
                 long long t0 = PROBE ? clock64() : 0;
-                if (!SAVE && l == 9 && pair + gridDim.x < n_pairs) {
+                if (!SAVE && l == kNumMmaLayers - 1 && pair + gridDim.x < n_pairs) {
                     const long nxt = ((pair + gridDim.x) * 2 + g) * kTileM + row;
                     if (half == 0) input_encode<0>(P, nxt < P.M ? nxt : P.M - 1, pe_regs);
                     else input_encode<1>(P, nxt < P.M ? nxt : P.M - 1, pe_regs);
@@ -901,19 +900,17 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                     if (gtid == 0) umma::bulk_wait_read0();
                     umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
                 }
-                if (l < 9) {
+                if (l < kNumMmaLayers - 1) {
                     const int c0 = half * 128;
                     if (CT && !PROBE) {
                         if (half == 0) epilogue_hidden_ct<8, CFG::exp & (7 | 64 | 8192 | 16384), 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
                         else epilogue_hidden_ct<8, CFG::exp & (7 | 64 | 8192 | 16384), 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
-                    } else if (l == 7) {
+                    } else if (l == 7) {       // l8: its FP32 accumulator also feeds the sigma head (l_alpha)
                         epilogue_hidden<1, PROBE, CFG::exp, CT, 8, -1, SAVE>(tacc, c0, a_row_addr, swz, bias_addr, tail + kTailWAlpha, sigma, probe_row, P.ct, l, mw);
-                    } else if (l == 8) {
-                        epilogue_hidden<2, PROBE, CFG::exp, CT>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row, P.ct, l);
                     } else {
                         epilogue_hidden<0, PROBE, CFG::exp, CT, 8, -1, SAVE>(tacc, c0, a_row_addr, swz, bias_addr, nullptr, sigma, probe_row, P.ct, l, mw);
                     }
-                    if (SAVE && l != 8 && mask_tile)
+                    if (SAVE && mask_tile)
                         *reinterpret_cast<uint4*>(mask_tile + act_mask_slot(l, row, half)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
                     umma::fence_proxy_async_smem();
                     umma::tc_fence_before();
@@ -922,10 +919,10 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                     // stage the next hidden layer's bias (after l9 comes l1 of the next tile); both
                     // barriers fall into the time the group would wait for the tensor core anyway
                     float bnext = 0.f;
-                    if (kStageBias) bnext = __ldg(tail + kTailBias + (l == 8 ? 0 : l + 1) * kHidden + gtid);
+                    if (kStageBias) bnext = __ldg(tail + kTailBias + (l == 7 ? 0 : l + 1) * kHidden + gtid);
                     if (kGroupSync) umma::named_bar_sync(group_bar, kEpiWarpsPerGroup * 32);
                     if (SAVE && gtid == 0) {
-                        // activation record: h_{l+1} (l9's output for l == 8) straight from the A tile;
+                        // activation record: h_{l+1} straight from the A tile;
                         // the copy must have read the tile before the next epilogue overwrites it
                         if (act_tile) {
                             umma::bulk_s2g(act_tile + act_hidden(l + 1), sbase + kOffA + g * 65536, 65536);
@@ -1016,915 +1013,12 @@ __global__ void __maxnreg__(112) mlp_fwd_kernel_r112(const __grid_constant__ Fwd
     mlp_fwd_body<PROBE, CFG, SAVE, CT, WIDE>(P);
 }
 
-#ifdef NERF_B200_EXPERIMENTS
-// The kernels from here to the matching #endif are the round-1 design alternatives that LOST against
-// mlp_fwd_kernel (DESIGN.md section 4.1 has the measurements).  They are kept as evidence and for A/B
-// timing, and are compiled only into the experiments build (`make experiments` ->
-// libnerf_b200_exp.so); the shipped library contains the production kernels only.
-// ---------------------------------------------------------------------------- TS kernel
-// Inference variant whose activations never touch shared memory: the epilogue writes the BF16
-// activations of a layer straight into TENSOR MEMORY (tcgen05.st) and the next layer's MMA reads its
-// A operand from there (tcgen05.mma "TS" form).  Measured on B200 (tools/probes/mma_rate_probe.cu):
-// an M=128 x N=256 x K=16 BF16 MMA issues every 166 cycles in the SS form (both operands from shared
-// memory) and every 137 cycles in the TS form (= 7650 FLOP/cycle/SM, the tensor peak); N=128 MMAs are
-// slower per column in either form (102 / 88 cycles).  The TS form also takes the 64 KB of epilogue
-// stores and the 64 KB of A-operand reads per tile and layer off the shared-memory pipe.
-//
-// Tensor memory (512 columns) is two regions of 256 columns, R0 and R1.  Layer l accumulates into
-// R[l & 1] (N = 256 FP32 columns) from the A operand in R[(l - 1) & 1].  The epilogue converts the
-// accumulator IN PLACE: the thread that owns row r and column group cg reads the 16 FP32 columns
-// [64 j + 16 cg, +16) of K chunk j and writes the 16 BF16 features back as 8 packed columns at
-// [64 j + 16 cg, +8) -- columns only this thread has read -- which is exactly the K = 16 slice
-// (j, kk = cg) the next layer's MMA addresses.  The region the next layer accumulates into held this
-// layer's A operand, which is dead once this layer's MMAs have completed.
-//
-// One 128-row tile per CTA is in flight, so MMA and epilogue overlap INSIDE the tile, by K chunk:
-// the 16-warp epilogue crew (four threads per row) finishes chunk 0 of layer l first and signals it;
-// the MMA warp starts layer l+1 on chunk 0 while the crew converts chunks 1..3.  The tensor core idles
-// only from the last MMA of a layer to the first converted chunk.
-//   warp 0      producer: 32 KB weight slots ([256 out][64 in], all N) through a 5-slot ring
-//   warp 1      MMA issuer
-//   warps 2-17  epilogue crew: warp = (TMEM lane quadrant, column group cg)
-// The PE tile (A operand of l1 and of l6's first K chunk) stays in shared memory (SS form) and is
-// double-buffered across tiles; sigma / rgb heads as in the other variants (FP32, CUDA cores).
-constexpr int kTsRing = 5;
-constexpr uint32_t kTsOffPE = 0;                               // 2 x [128][64] bf16
-constexpr uint32_t kTsOffXchg = 2 * 16384;                     // [128 rows][4] float4
-constexpr uint32_t kTsOffW = kTsOffXchg + 128 * 4 * 16;        // ring x 32 KB (1 KB aligned: 40960)
-constexpr uint32_t kTsOffBar = kTsOffW + kTsRing * kSlotBytes;
-constexpr uint32_t kTsSmemBytes = kTsOffBar + 512;
-static_assert(kTsOffW % 1024 == 0 && kTsSmemBytes <= 232448, "TS kernel shared memory");
-
-// Epilogue of hidden layer L for this thread (row, column group cg): per K chunk j, 16 accumulator
-// columns + bias -> activation -> BF16 -> 8 packed columns in place, then the chunk is signalled.
-// treg: tensor-memory address of (this warp's lane quadrant, first column of the layer's region).
-template <int MODE, int L>
-__device__ __forceinline__ void epilogue_ts(uint32_t treg, int cg, uint32_t bar_a, float& sigma, const ConstTail& ct) {
-    uint32_t v[2][16];
-    umma::tmem_ld16(treg + cg * 16, v[0]);
-    float2 sig2 = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        umma::tmem_wait_ld();
-        if (j + 1 < 4) umma::tmem_ld16(treg + (j + 1) * 64 + cg * 16, v[(j + 1) & 1]);
-        const uint32_t(&cur)[16] = v[j & 1];
-        const float* bl = ct.bias + L * kHidden + j * 64 + cg * 16;
-        uint32_t o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float2 h = __fadd2_rn(make_float2(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1])),
-                                  make_float2(bl[2 * e], bl[2 * e + 1]));
-            if (MODE == 1) {
-                h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f);
-                const float* wa = ct.walpha + j * 64 + cg * 16 + 2 * e;
-                sig2 = __ffma2_rn(make_float2(wa[0], wa[1]), h, sig2);
-            }
-            o[e] = MODE == 0 ? pack_relu_bf16x2(h.x, h.y) : pack_bf16x2(h.x, h.y);
-        }
-        umma::tmem_st8(treg + j * 64 + cg * 16, o);
-        umma::tmem_wait_st();
-        umma::tc_fence_before();
-        // one arrival per warp: 512 per-thread arrivals on one mbarrier serialise on the shared-memory
-        // atomic unit (4 chunks x 9 layers per tile) and were the critical path of the first version
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) umma::mbar_arrive(bar_a + 8 * j);
-    }
-    if (MODE == 1) sigma += sig2.x + sig2.y;
-}
-
-__device__ __forceinline__ void epilogue_ts_layer(int l, uint32_t treg, int cg, uint32_t bar_a, float& sigma,
-                                                  const ConstTail& ct) {
-    switch (l) {
-#define NERF_TS_LAYER(LL, MODE) case LL: epilogue_ts<MODE, LL>(treg, cg, bar_a, sigma, ct); break;
-        NERF_TS_LAYER(0, 0) NERF_TS_LAYER(1, 0) NERF_TS_LAYER(2, 0) NERF_TS_LAYER(3, 0) NERF_TS_LAYER(4, 0)
-        NERF_TS_LAYER(5, 0) NERF_TS_LAYER(6, 0) NERF_TS_LAYER(7, 1)
-        default: epilogue_ts<2, 8>(treg, cg, bar_a, sigma, ct); break;
-#undef NERF_TS_LAYER
-    }
-}
-
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_ts_kernel(const __grid_constant__ FwdParams P) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t sbase = umma::smem_u32(smem);
-    if ((sbase & 1023u) != 0) __trap();
-    const uint32_t bar_w_full = sbase + kTsOffBar;                 // [kTsRing]
-    const uint32_t bar_w_empty = bar_w_full + 8 * kTsRing;         // [kTsRing]
-    const uint32_t bar_pe_ready = bar_w_empty + 8 * kTsRing;       // [2]  PE tile buffer written
-    const uint32_t bar_a = bar_pe_ready + 16;                      // [4]  K chunk j of the next A operand converted
-    const uint32_t bar_acc = bar_a + 32;                           // [2]  layer l accumulated (by layer parity)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kTsOffBar + 8 * (2 * kTsRing + 8));
-    static_assert(8 * (2 * kTsRing + 8) + 4 <= 512, "barrier region");
-    constexpr uint32_t kCrew = 2 * kEpiWarpsPerGroup * 32;         // 512 epilogue threads
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long n_tiles = (P.M + kTileM - 1) / kTileM;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kTsRing; ++s) {
-            umma::mbar_init(bar_w_full + 8 * s, 1);
-            umma::mbar_init(bar_w_empty + 8 * s, 1);
-        }
-        umma::mbar_init(bar_pe_ready, kCrew);
-        umma::mbar_init(bar_pe_ready + 8, kCrew);
-        for (int j = 0; j < 4; ++j) umma::mbar_init(bar_a + 8 * j, kCrew / 32);
-        umma::mbar_init(bar_acc, 1);
-        umma::mbar_init(bar_acc + 8, 1);
-        umma::fence_barrier_init();
-    }
-    if (warp == 1) {
-        umma::tmem_alloc(umma::smem_u32(tmem_slot), 512);
-        umma::tmem_relinquish();
-    }
-    umma::tc_fence_before();
-    __syncthreads();
-    umma::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================== producer =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int first = layer_first_stage(l), chunks = layer_chunks(l);
-                    const uint32_t bytes = layer_halves(l) * kStageBytes;
-                    for (int j = 0; j < chunks; ++j, ++it) {
-                        const uint32_t slot = it % kTsRing, ph = (it / kTsRing) & 1;
-                        umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
-                        umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
-                        umma::bulk_g2s(sbase + kTsOffW + slot * kSlotBytes,
-                                       P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes,
-                                       bar_w_full + 8 * slot);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t it = 0, n_a = 0;
-            long n = 0;
-            const bool stats = P.stats_out != nullptr;
-            long long tw_a = 0, tw_w = 0, tw_pe = 0, tw_x = 0, tw_i = 0;
-            uint32_t n_accm[2] = {0, 0};
-            const long long t_begin = stats ? clock64() : 0;
-            for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-                const uint32_t pe_tile = sbase + kTsOffPE + (uint32_t)(n & 1) * 16384;
-                for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int chunks = layer_chunks(l);
-                    const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
-                    const uint32_t a_in = tmem_base + (uint32_t)((l - 1) & 1) * 256;   // hidden input (l >= 1)
-                    const uint32_t d_addr = tmem_base + (uint32_t)(l & 1) * 256;
-                    if (l == 0) {
-                        // R0 was last read by the previous tile's l10 MMAs (same pipe, in order) and
-                        // converted by its l9 epilogue, which those MMAs waited for
-                        const long long t0 = stats ? clock64() : 0;
-                        umma::mbar_wait(bar_pe_ready + 8 * (uint32_t)(n & 1), (uint32_t)(n >> 1) & 1);
-                        if (stats) tw_pe += clock64() - t0;
-                        umma::tc_fence_after();
-                    }
-                    for (int j = 0; j < chunks; ++j) {
-                        const bool x_is_pe = l == 0 || (l == 5 && j == 0);
-                        const int jj = l == 5 ? j - 1 : j;              // K chunk of the hidden input
-                        if (!x_is_pe) {
-                            const long long t0 = stats ? clock64() : 0;
-                            umma::mbar_wait(bar_a + 8 * (uint32_t)jj, n_a & 1);
-                            if (stats) tw_a += clock64() - t0;
-                            umma::tc_fence_after();
-                        }
-                        const uint32_t slot = it % kTsRing, ph = (it / kTsRing) & 1;
-                        ++it;
-                        const long long t1 = stats ? clock64() : 0;
-                        umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                        if (stats) tw_w += clock64() - t1;
-                        umma::tc_fence_after();
-                        const uint32_t w_addr = sbase + kTsOffW + slot * kSlotBytes;
-                        const long long t3 = stats ? clock64() : 0;
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
-                            const uint64_t b_desc = umma::smem_desc_sw128(w_addr + kk * 32);
-                            if (x_is_pe) umma::mma_bf16_ss(d_addr, umma::smem_desc_sw128(pe_tile + kk * 32), b_desc, idesc, acc);
-                            else umma::mma_bf16_ts(d_addr, a_in + (uint32_t)(jj * 64 + kk * 16), b_desc, idesc, acc);
-                        }
-                        umma::mma_commit(bar_w_empty + 8 * slot);
-                        if (stats) tw_i += clock64() - t3;
-                    }
-                    umma::mma_commit(bar_acc + 8 * (uint32_t)(l & 1));
-                    if (stats) {   // time to drain the MMA queue (diagnostic runs only)
-                        const long long t2 = clock64();
-                        umma::mbar_wait(bar_acc + 8 * (uint32_t)(l & 1), n_accm[l & 1] & 1);
-                        ++n_accm[l & 1];
-                        tw_x += clock64() - t2;
-                    }
-                    if (l >= 1) ++n_a;
-                }
-            }
-            if (stats) {   // [1] wait A chunk, [2] wait weights, [6] wait PE, [5] total, [3] crew wait acc, [4] crew busy
-                long long* o = P.stats_out + (long)blockIdx.x * 8;
-                o[1] = tw_a; o[2] = tw_w; o[6] = tw_pe; o[5] = clock64() - t_begin; o[0] = tw_x; o[7] = tw_i;
-            }
-        }
-    } else {
-        // ===================== epilogue crew (16 warps) =====================
-        const int cg = (warp - 2) >> 2;           // column group: 16 of the 64 columns of every K chunk
-        const int quad = warp & 3;                // TMEM lane quadrant
-        const int row = quad * 32 + lane;
-        const uint32_t quad_bar = 1 + quad;       // the four warps sharing rows
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-        float4* xchg = reinterpret_cast<float4*>(smem + kTsOffXchg) + row * 4;
-        uint32_t n_acc[2] = {0, 0};
-        const bool stats = P.stats_out != nullptr && warp == 2;
-        long long tw_acc = 0, t_epi = 0;
-        auto pe_stage = [&](long tile, long n) {
-            const long grow_raw = tile * kTileM + row;
-            const long grow = grow_raw < P.M ? grow_raw : P.M - 1;
-            uint8_t* pe_tile = smem + kTsOffPE + (n & 1) * 16384;
-            if (cg == 0) input_stage<0>(P, grow, pe_tile, row);
-            else if (cg == 1) input_stage<1>(P, grow, pe_tile, row);
-            umma::fence_proxy_async_smem();
-            umma::mbar_arrive(bar_pe_ready + 8 * (uint32_t)(n & 1));
-        };
-        if ((long)blockIdx.x < n_tiles) pe_stage(blockIdx.x, 0);
-        long n = 0;
-        for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-            float sigma = 0.f;
-#pragma unroll 1
-            for (int l = 0; l < 9; ++l) {
-                const long long t0 = stats ? clock64() : 0;
-                umma::mbar_wait_warp(bar_acc + 8 * (uint32_t)(l & 1), n_acc[l & 1] & 1);
-                const long long t1 = stats ? clock64() : 0;
-                ++n_acc[l & 1];
-                umma::tc_fence_after();
-                epilogue_ts_layer(l, lane_base + (uint32_t)(l & 1) * 256, cg, bar_a, sigma, P.ct);
-                if (stats) { tw_acc += t1 - t0; t_epi += clock64() - t1; }
-                // the other PE buffer was last read by the previous tile's l6: encode the next tile
-                if (l == 0 && tile + gridDim.x < n_tiles) pe_stage(tile + gridDim.x, n + 1);
-            }
-            {   // l10 + l11: R1[0,128) holds the 128 pre-activations
-                umma::mbar_wait_warp(bar_acc + 8, n_acc[1] & 1);
-                ++n_acc[1];
-                umma::tc_fence_after();
-                const long grow_raw = tile * kTileM + row;
-                const bool valid = grow_raw < P.M;
-                const long grow = valid ? grow_raw : P.M - 1;
-                float rgb[3];
-                const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                epilogue_rgb<false, false, true, 2>(lane_base + 256, cg * 32, vt, nullptr, rgb, nullptr, 0, 0, P.ct);
-                // R1 is next written by the following tile's l2, which waits for this crew's l1 epilogue
-                if (cg > 0) xchg[cg] = make_float4(rgb[0], rgb[1], rgb[2], sigma);
-                umma::named_bar_sync(quad_bar, 128);
-                if (cg == 0 && valid) {
-                    const float4 p1 = xchg[1], p2 = xchg[2], p3 = xchg[3];
-                    float4 o;
-                    o.x = rgb[0] + p1.x + p2.x + p3.x + P.ct.b11[0];
-                    o.y = rgb[1] + p1.y + p2.y + p3.y + P.ct.b11[1];
-                    o.z = rgb[2] + p1.z + p2.z + p3.z + P.ct.b11[2];
-                    o.w = sigma + p1.w + p2.w + p3.w + P.ct.balpha[0];
-                    reinterpret_cast<float4*>(P.raw_out)[grow] = o;
-                }
-                umma::named_bar_sync(quad_bar, 128);      // the next tile's partials reuse the slots
-            }
-        }
-        if (stats && lane == 0) {
-            long long* o = P.stats_out + (long)blockIdx.x * 8;
-            o[3] = tw_acc; o[4] = t_epi;
-        }
-    }
-    umma::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        umma::tc_fence_after();
-        umma::tmem_dealloc(tmem_base, 512);
-    }
-}
-
-// ---------------------------------------------------------------------------- mixed-orientation kernel
-// Inference variant that runs most layers TRANSPOSED: D^T[feature][sample] = W . H^T, i.e. the
-// weight stage is the A operand (M = 128 output features, two M blocks) and the activation tile the
-// B operand (N = 128 samples).  An epilogue thread then owns ONE output feature and 128 samples, so
-// the bias is a single register (no per-column bias traffic at all: the row-per-thread epilogue
-// needs 128 different biases per thread and layer, delivered through LDS or LDC -- the dominant
-// stall of the other variants), and it writes H^T[feature][sample] rows, which tcgen05 reads back
-// as an MN-major operand.  Layers whose epilogue needs a whole sample per thread (l8: FP32 sigma
-// head over the 256 features; l10: view term + FP32 rgb head) stay in the normal orientation; the
-// stored tile of either orientation feeds either kind of MMA just by flipping the operand-major
-// bits of the instruction descriptor.  The weight blob, the producer and the ring are unchanged.
-//   layer         l1 l2 l3 l4 l5 l6 l7 | l8 | l9 | l10
-//   orientation    T  T  T  T  T  T  T |  N |  T |  N
-__host__ __device__ constexpr bool layer_transposed(int l) { return l != 7 && l != 9; }
-
-// Transposed epilogue: this thread's feature row f, 128 samples: acc + bias -> (ReLU) -> BF16 ->
-// H^T tile ([2 blocks of 64 samples][256 feature rows][128 B], swizzled by row like every tile).
-template <bool RELU>
-__device__ __forceinline__ void epilogue_hidden_t(uint32_t tacc, uint32_t tile_addr, int f, float bias) {
-    const uint32_t row_addr = tile_addr + (uint32_t)f * 128;
-    const uint32_t swz = (uint32_t)(f & 7) << 4;
-    const float2 b2 = make_float2(bias, bias);
-    uint32_t v[2][16];
-    umma::tmem_ld16(tacc, v[0]);
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int s0 = it * 16;
-        umma::tmem_wait_ld();
-        if (it + 1 < 8) umma::tmem_ld16(tacc + s0 + 16, v[(it + 1) & 1]);
-        const uint32_t(&cur)[16] = v[it & 1];
-        uint32_t o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float2 h = __fadd2_rn(make_float2(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1])), b2);
-            o[e] = RELU ? pack_relu_bf16x2(h.x, h.y) : pack_bf16x2(h.x, h.y);
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int s = s0 + q * 8;
-            const int blk = s >> 6, c16 = (s & 63) >> 3;
-            umma::st_shared_v4(row_addr + blk * 32768 + ((uint32_t)(c16 << 4) ^ swz), o[q * 4 + 0], o[q * 4 + 1],
-                               o[q * 4 + 2], o[q * 4 + 3]);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tr_kernel(const __grid_constant__ FwdParams P) {
-    constexpr int kRingT = kRing;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t sbase = umma::smem_u32(smem);
-    if ((sbase & 1023u) != 0) __trap();
-    const uint32_t bar_w_full = sbase + kOffBar;
-    const uint32_t bar_w_empty = bar_w_full + 8 * kMaxRing;
-    const uint32_t bar_a_ready = bar_w_empty + 8 * kMaxRing;
-    const uint32_t bar_acc_full = bar_a_ready + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kMaxRing + 4));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long n_tiles = (P.M + kTileM - 1) / kTileM;
-    const long n_pairs = (n_tiles + 1) / 2;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kRingT; ++s) {
-            umma::mbar_init(bar_w_full + 8 * s, 1);
-            umma::mbar_init(bar_w_empty + 8 * s, 1);
-        }
-        for (int g = 0; g < 2; ++g) {
-            umma::mbar_init(bar_a_ready + 8 * g, kEpiWarpsPerGroup * 32);
-            umma::mbar_init(bar_acc_full + 8 * g, 1);
-        }
-        umma::fence_barrier_init();
-    }
-    if (warp == 1) {
-        umma::tmem_alloc(umma::smem_u32(tmem_slot), 512);
-        umma::tmem_relinquish();
-    }
-    umma::tc_fence_before();
-    __syncthreads();
-    umma::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================== producer (same stream of 32 KB slots as mlp_fwd_kernel) =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int first = layer_first_stage(l), chunks = layer_chunks(l);
-                    const uint32_t bytes = layer_halves(l) * kStageBytes;
-                    for (int g = 0; g < 2; ++g) {
-                        for (int j = 0; j < chunks; ++j, ++it) {
-                            const uint32_t slot = it % kRingT, ph = (it / kRingT) & 1;
-                            umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
-                            umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
-                            umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
-                                           P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes,
-                                           bar_w_full + 8 * slot);
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t it = 0, n_ready[2] = {0, 0};
-            for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-                for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int chunks = layer_chunks(l);
-                    const bool out_t = layer_transposed(l);
-                    const bool in_t = l > 0 && layer_transposed(l - 1);   // layout of the hidden input tile
-                    const int n_cols = layer_halves(l) == 2 ? 256 : 128;  // normal orientation: N
-                    for (int g = 0; g < 2; ++g) {
-                        umma::mbar_wait(bar_a_ready + 8 * g, n_ready[g] & 1);
-                        ++n_ready[g];
-                        umma::tc_fence_after();
-                        const uint32_t d_base = tmem_base + g * 256;
-                        const uint32_t a_tile = sbase + kOffA + g * 65536;
-                        const uint32_t pe_tile = sbase + kOffPE + g * 16384;
-                        for (int j = 0; j < chunks; ++j) {
-                            const bool x_is_pe = l == 0 || (l == 5 && j == 0);
-                            const int jj = l == 5 ? j - 1 : j;            // chunk of the hidden tile
-                            const bool x_mn = !x_is_pe && in_t;
-                            const uint32_t slot = it % kRingT, ph = (it / kRingT) & 1;
-                            ++it;
-                            umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                            umma::tc_fence_after();
-                            const uint32_t w_addr = sbase + kOffW + slot * kSlotBytes;
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                // activations of K step kk of this chunk: [sample][feature] image (K-major)
-                                // or [feature][sample] image (MN-major), whichever the previous layer wrote
-                                uint64_t x_desc;
-                                if (x_is_pe) x_desc = umma::smem_desc_sw128(pe_tile + kk * 32);
-                                else if (in_t) x_desc = umma::smem_desc_sw128_mn(a_tile + (uint32_t)(jj * 64 + kk * 16) * 128, 32768);
-                                else x_desc = umma::smem_desc_sw128(a_tile + jj * 16384 + kk * 32);
-                                const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
-                                if (out_t) {
-                                    // D^T[mb] (+)= W[mb] . X^T: weights are A (two 128-row halves), N = 128 samples
-                                    const uint32_t idesc = umma::instr_desc_bf16_ex(128, 128, false, x_mn);
-                                    umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(w_addr + kk * 32), x_desc, idesc, acc);
-                                    umma::mma_bf16_ss(d_base + 128, umma::smem_desc_sw128(w_addr + kStageBytes + kk * 32),
-                                                      x_desc, idesc, acc);
-                                } else {
-                                    const uint32_t idesc = umma::instr_desc_bf16_ex(128, n_cols, x_mn, false);
-                                    umma::mma_bf16_ss(d_base, x_desc, umma::smem_desc_sw128(w_addr + kk * 32), idesc, acc);
-                                }
-                            }
-                            umma::mma_commit(bar_w_empty + 8 * slot);
-                        }
-                        umma::mma_commit(bar_acc_full + 8 * g);
-                    }
-                }
-            }
-        }
-    } else {
-        // ===================== epilogue groups =====================
-        const int ew = warp - 2;
-        const int g = ew >> 3;
-        const int half = (ew >> 2) & 1;          // normal layers: column half; transposed layers: M block
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;        // TMEM lane: sample (normal) or feature within the M block (transposed)
-        const uint32_t pair_bar = 1 + g * 4 + quad;
-        const uint32_t a_tile_addr = sbase + kOffA + g * 65536;
-        const uint32_t a_row_addr = a_tile_addr + row * 128;
-        const uint32_t swz = (uint32_t)(row & 7) << 4;
-        uint8_t* pe_tile = smem + kOffPE + g * 16384;
-        float4* xchg = reinterpret_cast<float4*>(pe_tile + row * 128);
-        const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
-        const float* tail = reinterpret_cast<const float*>(P.blob + kWeightBytes);
-        const int feat = half * 128 + row;       // transposed layers: this thread's output feature
-        uint32_t n_full = 0;
-        for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-            const long grow_raw = (pair * 2 + g) * kTileM + row;
-            const bool valid = grow_raw < P.M;
-            const long grow = valid ? grow_raw : P.M - 1;
-            if (half == 0) input_stage<0>(P, grow, pe_tile, row);
-            else input_stage<1>(P, grow, pe_tile, row);
-            umma::fence_proxy_async_smem();
-            umma::mbar_arrive(bar_a_ready + 8 * g);
-            float sigma = 0.f;
-#pragma unroll 1
-            for (int l = 0; l < kNumMmaLayers; ++l) {
-                // one coalesced load per thread and layer: the bias of this thread's feature
-                const float bias_f = layer_transposed(l) ? __ldg(tail + kTailBias + l * kHidden + feat) : 0.f;
-                umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
-                ++n_full;
-                umma::tc_fence_after();
-                if (l == 9) {
-                    float rgb[3];
-                    const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                    epilogue_rgb<false, false, true>(tacc, half * 64, vt, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
-                    umma::tc_fence_before();
-                    if (half == 1) *xchg = make_float4(rgb[0], rgb[1], rgb[2], sigma);
-                    umma::named_bar_sync(pair_bar, 64);
-                    if (half == 0) {
-                        const float4 o2 = *xchg;
-                        if (valid) {
-                            float4 o;
-                            o.x = rgb[0] + o2.x + P.ct.b11[0];
-                            o.y = rgb[1] + o2.y + P.ct.b11[1];
-                            o.z = rgb[2] + o2.z + P.ct.b11[2];
-                            o.w = sigma + o2.w + P.ct.balpha[0];
-                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
-                        }
-                    }
-                    umma::named_bar_sync(pair_bar, 64);
-                    continue;
-                }
-                if (l == 7) {
-                    epilogue_hidden<1, false, 0, true, 8, 7>(tacc, half * 128, a_row_addr, swz, 0, nullptr, sigma, nullptr, P.ct, 7);
-                } else if (l == 8) {
-                    epilogue_hidden_t<false>(tacc + half * 128, a_tile_addr, feat, bias_f);
-                } else {
-                    epilogue_hidden_t<true>(tacc + half * 128, a_tile_addr, feat, bias_f);
-                }
-                umma::fence_proxy_async_smem();
-                umma::tc_fence_before();
-                umma::mbar_arrive(bar_a_ready + 8 * g);
-            }
-        }
-    }
-    umma::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        umma::tc_fence_after();
-        umma::tmem_dealloc(tmem_base, 512);
-    }
-}
-
-// ---------------------------------------------------------------------------- CTA-pair kernel
-// Inference variant on tcgen05 cta_group::2: the two CTAs of a cluster (one TPC) run ONE
-// M=256 x N=256 MMA per K step over their two 128-row sub-tiles, and each CTA stages only ITS
-// half of every weight chunk (128 of the 256 output rows).  Per SM and tile-layer that halves both
-// the bytes the TMA engine writes into shared memory and the B-operand bytes the tensor core
-// reads from it -- the traffic that saturates the shared-memory pipe of the single-CTA kernel
-// (A 64 KB + B 128 KB + fill 128 KB + epilogue stores 64 KB per 2048 MMA cycles).
-//   tiles        a cluster takes four tiles at a time: CTA r, group g -> tile 4q + 2r + g
-//   warp 0       (both CTAs) producer of the CTA's own 16 KB half-chunks, ring of 4
-//   warp 1       leader: MMA issuer (tcgen05.mma.cta_group::2, commits multicast to both CTAs);
-//                peer: relays "my half-chunk has landed" to the leader's w_peer barriers
-//   warps 2-17   epilogue groups as in the single-CTA kernel; a group signals "A tile written" with
-//                one arrive (local in the leader, remote from the peer) after a group barrier
-constexpr int kPairRing = 4;
-constexpr uint32_t kPairOffBar = kOffW + kPairRing * kStageBytes;
-static_assert(kPairOffBar == kOffBar, "same footprint as the single-CTA kernel");
-
-// WIDE: one 16-warp epilogue crew (four threads per row, 64 columns each) serves the two sub-tiles of the
-// CTA alternately instead of one 8-warp group per sub-tile.  The pair MMA runs at the tensor peak
-// (128 cycles per M=256 x N=256 x K=16, tools/probes/pair_mma_rate_probe.cu), so a sub-tile's
-// MMA -> epilogue -> MMA chain must fit into about two layer times (2 x 2056 cycles); the 8-warp
-// epilogue alone takes ~3500 cycles, the crew about half of that.  Every crew warp arrives on the
-// leader's barrier itself (16 arrivals per CTA, no group barrier in the chain).
-// TMAP: the half-chunks are fetched with tensor-map copies (cp.async.bulk.tensor ... cta_group::2) whose
-// completion is counted by the LEADER's slot barrier for both CTAs, so the peer's relay thread and the
-// leader's second wait per chunk disappear from the weight path.
-struct alignas(64) PairMaps {
-    CUtensorMap stage128;     // box = one stage: [128 rows][64 bf16]
-    CUtensorMap stage64;      // box = half a stage: [64 rows][64 bf16] (l10: 64 of its 128 output rows per CTA)
-};
-
-template <bool WIDE, bool TMAP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P, const __grid_constant__ PairMaps maps) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t sbase = umma::smem_u32(smem);
-    if ((sbase & 1023u) != 0) __trap();
-    const uint32_t bar_w_full = sbase + kPairOffBar;              // [4] own half-chunk landed
-    const uint32_t bar_w_empty = bar_w_full + 8 * kPairRing;      // [4] MMAs done with the slot (multicast commit)
-    const uint32_t bar_w_peer = bar_w_empty + 8 * kPairRing;      // [4] leader only: peer's half-chunk landed
-    const uint32_t bar_a_ready = bar_w_peer + 8 * kPairRing;      // [2] leader only: both CTAs' A tiles written
-    const uint32_t bar_acc_full = bar_a_ready + 16;               // [2] accumulators complete (multicast commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kPairOffBar + 8 * (3 * kPairRing + 4));
-    static_assert(8 * (3 * kPairRing + 4) + 4 <= 256, "barrier region");
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = umma::cluster_ctarank();
-    // event trace of cluster 0 (same format and roles as mlp_fwd_kernel's; role 0 = the leader's producer)
-    const long long t_trace0 = P.trace_out ? clock64() : 0;
-    int n_ev = 0;
-    auto rec = [&](int role, long quad_no, int tag, int l, int g, int j) {
-        if (!P.trace_out || blockIdx.x != 0 || quad_no < 3 || quad_no > 4 || n_ev >= 1024) return;
-        P.trace_out[role * 1024 + n_ev++] = ((long long)tag << 56) | ((long long)l << 48) | ((long long)g << 44) |
-                                            ((long long)j << 40) | ((clock64() - t_trace0) & 0xFFFFFFFFFFll);
-    };
-    const long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const long n_tiles = (P.M + kTileM - 1) / kTileM;
-    const long n_quads = (n_tiles + 3) / 4;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kPairRing; ++s) {
-            umma::mbar_init(bar_w_full + 8 * s, 1);
-            umma::mbar_init(bar_w_empty + 8 * s, 1);
-            umma::mbar_init(bar_w_peer + 8 * s, 1);
-        }
-        for (int g = 0; g < 2; ++g) {
-            umma::mbar_init(bar_a_ready + 8 * g, (WIDE ? 2 : 1) * 2 * kEpiWarpsPerGroup);   // one arrive per warp and CTA
-            umma::mbar_init(bar_acc_full + 8 * g, 1);
-        }
-        umma::fence_barrier_init();
-    }
-    if (warp == 1) {
-        umma::tmem_alloc_pair(umma::smem_u32(tmem_slot), 512);
-        umma::tmem_relinquish_pair();
-    }
-    umma::tc_fence_before();
-    umma::cluster_sync_all();          // barriers of BOTH CTAs initialised before any remote arrive
-    umma::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================== producer: this CTA's half of every weight chunk =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            long quad_no = 0;
-            for (long quad = cluster_id; quad < n_quads; quad += n_clusters, ++quad_no) {
-                for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int first = layer_first_stage(l), chunks = layer_chunks(l), halves = layer_halves(l);
-                    // N = 256: stage (chunk, half = rank); N = 128 (l10): rows [64 rank, 64 rank + 64) of the stage
-                    const uint32_t bytes = halves == 2 ? kStageBytes : kStageBytes / 2;
-                    for (int g = 0; g < 2; ++g) {
-                        for (int j = 0; j < chunks; ++j, ++it) {
-                            const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
-                            rec(0, quad_no, 1, l, g, j);
-                            umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
-                            rec(0, quad_no, 2, l, g, j);
-                            if (TMAP) {
-                                // both halves are counted by the leader's barrier (armed by the leader)
-                                if (rank == 0) umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, 2 * bytes);
-                                const uint32_t leader_full = umma::map_to_cta(bar_w_full + 8 * slot, 0);
-                                if (halves == 2)
-                                    umma::tma_load_2d_pair(sbase + kOffW + slot * kStageBytes, &maps.stage128, 0,
-                                                           (first + j * 2 + (int)rank) * kStageRows, leader_full);
-                                else
-                                    umma::tma_load_2d_pair(sbase + kOffW + slot * kStageBytes, &maps.stage64, 0,
-                                                           (first + j) * kStageRows + (int)rank * (kStageRows / 2), leader_full);
-                                continue;
-                            }
-                            umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
-                            const uint8_t* src = halves == 2
-                                ? P.blob + (size_t)(first + j * 2 + (int)rank) * kStageBytes
-                                : P.blob + (size_t)(first + j) * kStageBytes + (size_t)rank * (kStageBytes / 2);
-                            umma::bulk_g2s(sbase + kOffW + slot * kStageBytes, src, bytes, bar_w_full + 8 * slot);
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 1 && TMAP) {
-            // nothing to relay: the peer's copies complete on the leader's barriers
-        } else if (lane == 0 && rank == 1) {
-            // ===================== peer: relay slot arrivals to the leader =====================
-            uint32_t it = 0;
-            const uint32_t leader_w_peer = umma::map_to_cta(bar_w_peer, 0);
-            for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
-                for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int chunks = layer_chunks(l);
-                    for (int gj = 0; gj < 2 * chunks; ++gj, ++it) {
-                        const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
-                        umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                        umma::mbar_arrive_remote(leader_w_peer + 8 * slot);
-                    }
-                }
-            }
-        } else if (lane == 0) {
-            // ===================== leader: MMA issuer for the pair =====================
-            if (TMAP && !P.stats_out && !P.trace_out) {
-                // lean loop (no counters, no trace): as in mlp_fwd_kernel, every instruction between the
-                // tcgen05.mma of this thread is tensor time -- and the pair MMA leaves 128 cycles per step
-                uint32_t slot = 0, ph = 0, n_ready[2] = {0, 0};
-                constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << (46 - 32)) | (2u << (61 - 32));
-                auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
-                auto desc_lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
-                const uint32_t w_lo = desc_lo(sbase + kOffW);
-                constexpr uint32_t kIdescPair256 = umma::instr_desc_bf16(256, 256);
-                constexpr uint32_t kIdescPair128 = umma::instr_desc_bf16(256, 128);
-                for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
-                    for (int l = 0; l < kNumMmaLayers; ++l) {
-                        const int chunks = layer_chunks(l);
-                        const uint32_t idesc = layer_halves(l) == 2 ? kIdescPair256 : kIdescPair128;
-                        for (int g = 0; g < 2; ++g) {
-                            umma::mbar_wait_cluster(bar_a_ready + 8 * g, n_ready[g] & 1);
-                            ++n_ready[g];
-                            umma::tc_fence_after();
-                            const uint32_t d_base = tmem_base + g * 256;
-                            const uint32_t a_tile = sbase + kOffA + g * 65536;
-                            const uint32_t pe_tile = sbase + kOffPE + g * 16384;
-                            for (int j = 0; j < chunks; ++j) {
-                                uint32_t a_addr;
-                                if (l == 0) a_addr = pe_tile;
-                                else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
-                                else a_addr = a_tile + j * 16384;
-                                umma::mbar_wait(bar_w_full + 8 * slot, ph);      // both halves' complete_tx land here
-                                const uint32_t b_lo = w_lo + slot * (kStageBytes >> 4);
-                                const uint32_t a_lo = desc_lo(a_addr);
-#pragma unroll
-                                for (int kk = 0; kk < 4; ++kk)
-                                    umma::mma_bf16_ss_pair(d_base, desc(a_lo + kk * 2), desc(b_lo + kk * 2), idesc,
-                                                           (j > 0 || kk > 0) ? 1u : 0u);
-                                umma::mma_commit_pair(bar_w_empty + 8 * slot);
-                                if (++slot == (uint32_t)kPairRing) { slot = 0; ph ^= 1; }
-                            }
-                            umma::mma_commit_pair(bar_acc_full + 8 * g);
-                        }
-                    }
-                }
-            } else {
-            uint32_t it = 0, n_ready[2] = {0, 0};
-            long long tw_a = 0, tw_w = 0, tw_p = 0;
-            const bool stats = P.stats_out != nullptr;      // the counters cost issue slots of the one thread that feeds the tensor core
-            const long long t_begin = stats ? clock64() : 0;
-            constexpr uint32_t kIdescPair256 = umma::instr_desc_bf16(256, 256);
-            constexpr uint32_t kIdescPair128 = umma::instr_desc_bf16(256, 128);
-            long quad_no = 0;
-            for (long quad = cluster_id; quad < n_quads; quad += n_clusters, ++quad_no) {
-                for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int chunks = layer_chunks(l);
-                    const uint32_t idesc = layer_halves(l) == 2 ? kIdescPair256 : kIdescPair128;
-                    for (int g = 0; g < 2; ++g) {
-                        long long t0 = stats ? clock64() : 0;
-                        rec(1, quad_no, 1, l, g, 0);
-                        umma::mbar_wait_cluster(bar_a_ready + 8 * g, n_ready[g] & 1);
-                        rec(1, quad_no, 2, l, g, 0);
-                        if (stats) tw_a += clock64() - t0;
-                        ++n_ready[g];
-                        umma::tc_fence_after();
-                        const uint32_t d_base = tmem_base + g * 256;
-                        const uint32_t a_tile = sbase + kOffA + g * 65536;
-                        const uint32_t pe_tile = sbase + kOffPE + g * 16384;
-                        for (int j = 0; j < chunks; ++j) {
-                            uint32_t a_addr;
-                            if (l == 0) a_addr = pe_tile;
-                            else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
-                            else a_addr = a_tile + j * 16384;
-                            const uint32_t slot = it % kPairRing, ph = (it / kPairRing) & 1;
-                            ++it;
-                            long long t1 = stats ? clock64() : 0;
-                            rec(1, quad_no, 3, l, g, j);
-                            if (TMAP) umma::mbar_wait_cluster(bar_w_full + 8 * slot, ph);
-                            else umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                            long long t2 = stats ? clock64() : 0;
-                            if (!TMAP) umma::mbar_wait_cluster(bar_w_peer + 8 * slot, ph);
-                            if (stats) { tw_w += t2 - t1; tw_p += clock64() - t2; }
-                            rec(1, quad_no, 4, l, g, j);
-                            umma::tc_fence_after();
-                            const uint32_t b_addr = sbase + kOffW + slot * kStageBytes;
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                umma::mma_bf16_ss_pair(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
-                                                       umma::smem_desc_sw128(b_addr + kk * 32), idesc,
-                                                       (j > 0 || kk > 0) ? 1u : 0u);
-                            }
-                            umma::mma_commit_pair(bar_w_empty + 8 * slot);
-                            rec(1, quad_no, 5, l, g, j);
-                        }
-                        umma::mma_commit_pair(bar_acc_full + 8 * g);
-                    }
-                }
-            }
-            if (stats) {
-                long long* o = P.stats_out + (long)blockIdx.x * 8;
-                o[1] = tw_a; o[2] = tw_w; o[6] = tw_p; o[5] = clock64() - t_begin;
-            }
-            }
-        }
-    } else if (WIDE) {
-        // ===================== one 16-warp epilogue crew, alternating between the sub-tiles =====================
-        const int cg = (warp - 2) >> 2;          // column group: columns [64 cg, 64 cg + 64) of a hidden layer
-        const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-        const int row = quad * 32 + lane;
-        const uint32_t quad_bar = 1 + quad;      // named barrier of the four warps sharing rows
-        const uint32_t swz = (uint32_t)(row & 7) << 4;
-        const uint32_t leader_a_ready = umma::map_to_cta(bar_a_ready, 0);
-        // this warp's part of sub-tile g's A operand (or PE tile) is written: stores fenced towards the
-        // async proxy, TMEM loads towards the tensor core, then one arrive per warp at the leader
-        auto signal_a_ready = [&](int g) {
-            umma::fence_proxy_async_smem();
-            umma::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive_remote(leader_a_ready + 8 * g);
-        };
-        auto in_stage = [&](int g, long quad_idx) {
-            const long grow_raw = (quad_idx * 4 + rank * 2 + g) * kTileM + row;
-            const long grow = grow_raw < P.M ? grow_raw : P.M - 1;
-            uint8_t* pe_tile = smem + kOffPE + g * 16384;
-            if (cg == 0) input_stage<0>(P, grow, pe_tile, row);
-            else if (cg == 1) input_stage<1>(P, grow, pe_tile, row);
-            signal_a_ready(g);
-        };
-        float sigma[2] = {0.f, 0.f};
-        uint32_t n_full[2] = {0, 0};
-        if (cluster_id < n_quads) { in_stage(0, cluster_id); in_stage(1, cluster_id); }
-        long quad_no = 0;
-        const bool tracer = warp == 2 && lane == 0;
-        for (long quad_idx = cluster_id; quad_idx < n_quads; quad_idx += n_clusters, ++quad_no) {
-#pragma unroll 1
-            for (int l = 0; l < kNumMmaLayers; ++l) {
-#pragma unroll 1
-                for (int g = 0; g < 2; ++g) {
-                    const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
-                    const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + g * 256;
-                    if (tracer) rec(2 + g, quad_no, 1, l, g, 0);
-                    umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full[g] & 1);
-                    if (tracer) rec(2 + g, quad_no, 2, l, g, 0);
-                    ++n_full[g];
-                    umma::tc_fence_after();
-                    if (l < 9) {
-                        float sg = 0.f;
-                        switch (cg) {
-                            case 0: epilogue_hidden_ct<4, 0, 0>(l, tacc, 0, a_row_addr, swz, sg, P.ct); break;
-                            case 1: epilogue_hidden_ct<4, 0, 64>(l, tacc, 64, a_row_addr, swz, sg, P.ct); break;
-                            case 2: epilogue_hidden_ct<4, 0, 128>(l, tacc, 128, a_row_addr, swz, sg, P.ct); break;
-                            default: epilogue_hidden_ct<4, 0, 192>(l, tacc, 192, a_row_addr, swz, sg, P.ct); break;
-                        }
-                        if (l == 7) sigma[g] = sg;
-                        signal_a_ready(g);
-                        if (tracer) rec(2 + g, quad_no, 3, l, g, 0);
-                    } else {
-                        const long grow_raw = (quad_idx * 4 + rank * 2 + g) * kTileM + row;
-                        const bool valid = grow_raw < P.M;
-                        const long grow = valid ? grow_raw : P.M - 1;
-                        float rgb[3];
-                        const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                        epilogue_rgb<false, false, true, 2>(tacc, cg * 32, vt, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
-                        umma::tc_fence_before();
-                        // FP32 hand-over between the four threads of a row, inside the row's own PE
-                        // line (free between l6's MMA and the next tile's encoding)
-                        float4* xchg = reinterpret_cast<float4*>(smem + kOffPE + g * 16384 + row * 128);
-                        if (cg > 0) xchg[cg - 1] = make_float4(rgb[0], rgb[1], rgb[2], sigma[g]);
-                        umma::named_bar_sync(quad_bar, 128);
-                        if (cg == 0 && valid) {
-                            const float4 p1 = xchg[0], p2 = xchg[1], p3 = xchg[2];
-                            float4 o;
-                            o.x = rgb[0] + p1.x + p2.x + p3.x + P.ct.b11[0];
-                            o.y = rgb[1] + p1.y + p2.y + p3.y + P.ct.b11[1];
-                            o.z = rgb[2] + p1.z + p2.z + p3.z + P.ct.b11[2];
-                            o.w = sigma[g] + p1.w + p2.w + p3.w + P.ct.balpha[0];
-                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
-                        }
-                        // the next tile's encoding overwrites the hand-over slots: wait for the reads
-                        umma::named_bar_sync(quad_bar, 128);
-                        if (quad_idx + n_clusters < n_quads) in_stage(g, quad_idx + n_clusters);
-                    }
-                }
-            }
-        }
-    } else {
-        // ===================== epilogue groups =====================
-        const int ew = warp - 2;
-        const int g = ew >> 3;
-        const int half = (ew >> 2) & 1;
-        const int quadrant = warp & 3;
-        const int row = quadrant * 32 + lane;
-        const uint32_t pair_bar = 1 + g * 4 + quadrant;
-        const uint32_t group_bar = 9 + g;
-        const int gtid = (ew & 7) * 32 + lane;
-        const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
-        const uint32_t swz = (uint32_t)(row & 7) << 4;
-        uint8_t* pe_tile = smem + kOffPE + g * 16384;
-        float4* xchg = reinterpret_cast<float4*>(pe_tile + row * 128);
-        const uint32_t tacc = tmem_base + ((uint32_t)(quadrant * 32) << 16) + g * 256;
-        const uint32_t leader_a_ready = umma::map_to_cta(bar_a_ready + 8 * g, 0);
-        // "this group's A tile is written": every writer has fenced its stores towards the async
-        // proxy and its TMEM loads towards the tensor core; one thread tells the leader's MMA warp
-        auto signal_a_ready = [&]() {
-            umma::fence_proxy_async_smem();
-            umma::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive_remote(leader_a_ready);
-        };
-        uint32_t n_full = 0;
-        long quad_no = 0;
-        const bool tracer = (ew & 7) == 0 && lane == 0;
-        for (long quad = cluster_id; quad < n_quads; quad += n_clusters, ++quad_no) {
-            const long grow_raw = (quad * 4 + rank * 2 + g) * kTileM + row;
-            const bool valid = grow_raw < P.M;
-            const long grow = valid ? grow_raw : P.M - 1;
-            if (half == 0) input_stage<0>(P, grow, pe_tile, row);
-            else input_stage<1>(P, grow, pe_tile, row);
-            signal_a_ready();
-            float sigma = 0.f;
-#pragma unroll 1
-            for (int l = 0; l < kNumMmaLayers; ++l) {
-                if (tracer) rec(2 + g, quad_no, 1, l, g, 0);
-                umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
-                if (tracer) rec(2 + g, quad_no, 2, l, g, 0);
-                ++n_full;
-                umma::tc_fence_after();
-                if (l < 9) {
-                    if (half == 0) epilogue_hidden_ct<8, 0, 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
-                    else epilogue_hidden_ct<8, 0, 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
-                    signal_a_ready();
-                    if (tracer) rec(2 + g, quad_no, 3, l, g, 0);
-                } else {
-                    float rgb[3];
-                    const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                    epilogue_rgb<false, false, true>(tacc, half * 64, vt, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
-                    umma::tc_fence_before();
-                    if (half == 1) *xchg = make_float4(rgb[0], rgb[1], rgb[2], sigma);
-                    umma::named_bar_sync(pair_bar, 64);
-                    if (half == 0) {
-                        const float4 o2 = *xchg;
-                        if (valid) {
-                            float4 o;
-                            o.x = rgb[0] + o2.x + P.ct.b11[0];
-                            o.y = rgb[1] + o2.y + P.ct.b11[1];
-                            o.z = rgb[2] + o2.z + P.ct.b11[2];
-                            o.w = sigma + o2.w + P.ct.balpha[0];
-                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
-                        }
-                    }
-                    umma::named_bar_sync(pair_bar, 64);
-                }
-            }
-        }
-    }
-    umma::tc_fence_before();
-    umma::cluster_sync_all();          // no CTA frees tensor memory while its partner still uses it
-    if (warp == 1) {
-        umma::tc_fence_after();
-        umma::tmem_dealloc_pair(tmem_base, 512);
-    }
-}
-
-#endif  // NERF_B200_EXPERIMENTS
+// The round-1 design alternatives of this kernel (activations in tensor memory / TS-form MMA, mixed
+// orientation, CTA pairs with tcgen05 cta_group::2, with and without tensor-map weight copies) were
+// removed from the tree in round 2, when l9 was folded into l10 (9 tensor-core layers): they lost
+// against mlp_fwd_kernel by 13..35 % and shared none of its later improvements.  Their measurements are
+// in DESIGN.md section 4.1 and profiles/r01_*.txt, their last buildable source in the commit before
+// "Fold l9 into l10".
 
 using FwdKernel = void (*)(const FwdParams);   // (__grid_constant__ does not change the type)
 
@@ -1999,140 +1093,6 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
     return nerf::check_launch("nerf_mlp_fwd");
 }
 
-#ifdef NERF_B200_EXPERIMENTS
-// measured on B200 (profiles/r01_fwd_variants_ncu.txt): 0 is the fastest of the three
-int g_use_pairs = 0;
-
-int launch_fwd_ts(const FwdParams& P, void* stream) {
-    static int sm_count = 0;
-    static bool configured = false;
-    if (sm_count == 0) {
-        sm_count = nerf_b200_sm_count();
-        if (sm_count <= 0) {
-            sm_count = 0;
-            nerf::set_last_error("nerf_mlp_fwd setup: no CUDA device");
-            return (int)cudaErrorNoDevice;
-        }
-    }
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
-        if (e != cudaSuccess) {
-            nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        configured = true;
-    }
-    const long n_tiles = (P.M + kTileM - 1) / kTileM;
-    const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
-    mlp_fwd_ts_kernel<<<grid, kThreads, kTsSmemBytes, (cudaStream_t)stream>>>(P);
-    return nerf::check_launch("nerf_mlp_fwd (TS)");
-}
-
-int launch_fwd_tr(const FwdParams& P, void* stream) {
-    static int sm_count = 0;
-    static bool configured = false;
-    if (sm_count == 0) {
-        sm_count = nerf_b200_sm_count();
-        if (sm_count <= 0) {
-            sm_count = 0;
-            nerf::set_last_error("nerf_mlp_fwd setup: no CUDA device");
-            return (int)cudaErrorNoDevice;
-        }
-    }
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) {
-            nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        configured = true;
-    }
-    const long n_pairs = ((P.M + kTileM - 1) / kTileM + 1) / 2;
-    const unsigned grid = (unsigned)(n_pairs < sm_count ? n_pairs : sm_count);
-    mlp_fwd_tr_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
-    return nerf::check_launch("nerf_mlp_fwd (mixed orientation)");
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_pair_maps(const uint8_t* blob, PairMaps& maps) {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
-            nerf::set_last_error("nerf_mlp_fwd setup: cuTensorMapEncodeTiled not available");
-            return (int)cudaErrorNotSupported;
-        }
-        encode = (EncodeTiledFn)fn;
-    }
-    // the weight stages as one [72 * 128 rows][64 bf16] array of 128-byte rows; the stage images are
-    // already swizzled, so the copy moves raw bytes (no tensor-map swizzle)
-    const cuuint64_t dims[2] = {(cuuint64_t)kStageCols, (cuuint64_t)kNumStages * kStageRows};
-    const cuuint64_t strides[1] = {(cuuint64_t)kStageCols * 2};
-    const cuuint32_t elem[2] = {1, 1};
-    for (int i = 0; i < 2; ++i) {
-        const cuuint32_t box[2] = {(cuuint32_t)kStageCols, (cuuint32_t)(i == 0 ? kStageRows : kStageRows / 2)};
-        CUresult r = encode(i == 0 ? &maps.stage128 : &maps.stage64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)blob, dims,
-                            strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            nerf::set_last_error("nerf_mlp_fwd setup: cuTensorMapEncodeTiled failed (%d)", (int)r);
-            return (int)cudaErrorInvalidValue;
-        }
-    }
-    return 0;
-}
-
-// mode: 0 8-warp groups, 1 16-warp crew, 2 8-warp groups + tensor-map weight copies, 3 crew + tensor-map copies
-int launch_fwd_pair(const FwdParams& P, void* stream, int mode = 0) {
-    static int sm_count = 0;
-    static bool configured = false;
-    if (sm_count == 0) {
-        sm_count = nerf_b200_sm_count();
-        if (sm_count <= 0) {
-            sm_count = 0;
-            nerf::set_last_error("nerf_mlp_fwd setup: no CUDA device");
-            return (int)cudaErrorNoDevice;
-        }
-    }
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) {
-            nerf::set_last_error("nerf_mlp_fwd setup: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        configured = true;
-    }
-    PairMaps maps;
-    memset(&maps, 0, sizeof(maps));
-    if (mode >= 2) {
-        int rc = make_pair_maps(P.blob, maps);
-        if (rc) return rc;
-    }
-    const long n_tiles = (P.M + kTileM - 1) / kTileM;
-    const long n_quads = (n_tiles + 3) / 4;
-    const long clusters = n_quads < sm_count / 2 ? n_quads : sm_count / 2;
-    const unsigned grid = (unsigned)(2 * clusters);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (mode) {
-        case 0: mlp_fwd_pair_kernel<false, false><<<grid, kThreads, kSmemBytes, st>>>(P, maps); break;
-        case 1: mlp_fwd_pair_kernel<true, false><<<grid, kThreads, kSmemBytes, st>>>(P, maps); break;
-        case 2: mlp_fwd_pair_kernel<false, true><<<grid, kThreads, kSmemBytes, st>>>(P, maps); break;
-        default: mlp_fwd_pair_kernel<true, true><<<grid, kThreads, kSmemBytes, st>>>(P, maps); break;
-    }
-    return nerf::check_launch("nerf_mlp_fwd (CTA pairs)");
-}
-
-#endif  // NERF_B200_EXPERIMENTS
-
 int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0, const float* in1,
                 int in_stride, long M, int S, const float* vterm, int vterm_div, float* raw_out) {
     if (M < 0 || vterm_div < 1) return nerf::arg_error("nerf_mlp_fwd");
@@ -2197,32 +1157,11 @@ extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail,
     if (rc) return rc;
     if (M == 0) return 0;
     memcpy(&P.ct, host_tail, sizeof(ConstTail));
-#ifndef NERF_B200_EXPERIMENTS
     return launch_fwd(P, 9, stream);
-#else
-    if (g_use_pairs == 3) return launch_fwd_tr(P, stream);
-    if (g_use_pairs == 4) return launch_fwd_ts(P, stream);
-    if (g_use_pairs == 5) return launch_fwd_pair(P, stream, 1);
-    if (g_use_pairs == 6) return launch_fwd_pair(P, stream, 2);
-    if (g_use_pairs == 7) return launch_fwd_pair(P, stream, 3);
-    return g_use_pairs == 1 ? launch_fwd_pair(P, stream) : launch_fwd(P, g_use_pairs == 2 ? 10 : 9, stream);
-#endif
 }
-
-#ifdef NERF_B200_EXPERIMENTS
-// Kernel behind nerf_mlp_fwd_host_tail: 0 (default) single CTA per SM; 1 CTA pairs (tcgen05
-// cta_group::2, half the weight bytes staged and read per SM); 2 single CTA with one 16-warp epilogue
-// crew.  All give the same results; the switch exists for A/B timing and tests.
-extern "C" int nerf_mlp_fwd_use_pairs(int enable) {
-    const int old = g_use_pairs;
-    if (enable >= 0) g_use_pairs = enable;     // 0 single CTA, 1 CTA pairs, 2 single CTA with the 16-warp crew
-    return old;
-}
-
-#endif  // NERF_B200_EXPERIMENTS
 
 // Test-support entry: additionally dumps the FP32 post-activation output of MMA layer
-// `probe_layer` (0 = l1 ... 8 = l9, 9 = l10; 256 floats per row, l10 uses the first 128).
+// `probe_layer` (0 = l1 ... 7 = l8, 8 = l10 with l9 folded in; 256 floats per row, l10 uses the first 128).
 extern "C" int nerf_mlp_fwd_probe(const void* packed, int in_mode, const float* in0, const float* in1,
                                   int in_stride, long M, int S, const float* vterm, int vterm_div,
                                   float* raw_out, int probe_layer, float* probe_out, void* stream) {
@@ -2247,30 +1186,9 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
     if (rc) return rc;
     if (M == 0) return 0;
     P.stats_out = stats_out;
-    if (variant >= 1000) {     // event trace behind the 148 x 8 counters (probe kernel, or the CTA-pair kernels 1100..1103)
+    if (variant >= 1000) {     // event trace behind the 148 x 8 counters (probe kernel)
         P.trace_out = stats_out + 148 * 8;
         variant -= 1000;
-        if (variant >= 100) P.stats_out = nullptr;      // the pair kernels trace without the wait counters
-    }
-    if (variant == 100) {      // CTA-pair kernel (needs a host tail: the caller's tail is read from the blob here)
-        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return (int)e;
-        return launch_fwd_pair(P, stream);
-    }
-    if (variant == 101) {      // CTA pairs with the 16-warp crew
-        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return (int)e;
-        return launch_fwd_pair(P, stream, 1);
-    }
-    if (variant == 102 || variant == 103) {      // CTA pairs with tensor-map weight copies (103: + crew)
-        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return (int)e;
-        return launch_fwd_pair(P, stream, variant - 100);
-    }
-    if (variant == 200) {      // TS kernel
-        cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return (int)e;
-        return launch_fwd_ts(P, stream);
     }
     if (variant == 9 || variant == 10 || (variant >= 13 && variant <= 23)) {   // host-tail kernels
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);

@@ -40,12 +40,41 @@ __device__ __forceinline__ int source_col(int l, int chunk, int k) {
     return chunk * 64 + k;                                        // square layers, l10[:, :256]
 }
 
-__device__ __forceinline__ int param_index(int l) {  // MMA layer -> index in ParamPtrs
-    return l <= 8 ? l : 10;                          // L1..L9 -> 0..8, L10 -> 10 (l10)
+__device__ __forceinline__ int param_index(int l) {  // MMA layer -> index in ParamPtrs (L1..L8 -> 0..7)
+    return l;
 }
 
 __device__ __forceinline__ int in_features(int l) {
-    return l == 0 ? 63 : (l == 5 ? 319 : (l == 9 ? 283 : 256));
+    return l == 0 ? 63 : (l == 5 ? 319 : 256);
+}
+
+// The folded layer (mlp_layout.h): W'[o][i..i+7] = sum_k l10.weight[o][k] * l9.weight[k][i..i+7], k = 0..255,
+// FP32, ascending k.  Both blobs (forward stages and the transposed stages of the dZ chain) take their
+// BF16 values from this one function, so they round the same FP32 numbers.
+__device__ __forceinline__ void fold_row8(const ParamPtrs& p, int o, int i, float (&acc)[8]) {
+    const float* w10 = p.w[10] + (size_t)o * 283;
+    const float* w9 = p.w[8] + i;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int k = 0; k < kHidden; ++k) {
+        const float a = __ldg(w10 + k);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)k * kHidden));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)k * kHidden) + 1);
+        acc[0] = fmaf(a, b0.x, acc[0]); acc[1] = fmaf(a, b0.y, acc[1]); acc[2] = fmaf(a, b0.z, acc[2]); acc[3] = fmaf(a, b0.w, acc[3]);
+        acc[4] = fmaf(a, b1.x, acc[4]); acc[5] = fmaf(a, b1.y, acc[5]); acc[6] = fmaf(a, b1.z, acc[6]); acc[7] = fmaf(a, b1.w, acc[7]);
+    }
+}
+// the same numbers for one input feature i and eight output rows o..o+7 (transposed stages)
+__device__ __forceinline__ void fold_col8(const ParamPtrs& p, int o, int i, float (&acc)[8]) {
+    const float* w10 = p.w[10] + (size_t)o * 283;
+    const float* w9 = p.w[8] + i;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int k = 0; k < kHidden; ++k) {
+        const float b = __ldg(w9 + (size_t)k * kHidden);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(__ldg(w10 + (size_t)e * 283 + k), b, acc[e]);
+    }
 }
 
 // one thread = one 16-byte chunk (8 consecutive k) of one stage row
@@ -56,15 +85,22 @@ __device__ __forceinline__ void pack_weights_item(const ParamPtrs& p, uint8_t* _
     int c16 = gid % 8;
     int l, chunk, half;
     stage_coords(stage, l, chunk, half);
-    const float* W = p.w[param_index(l)];
-    const int ld = in_features(l);
     const int out_row = half * kStageRows + r;
     __nv_bfloat16 v[8];
+    if (l == kNumMmaLayers - 1) {                 // l10' = l10[:, :256] . l9
+        float acc[8];
+        fold_row8(p, out_row, chunk * 64 + c16 * 8, acc);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        int col = source_col(l, chunk, c16 * 8 + e);
-        float x = col >= 0 ? W[(size_t)out_row * ld + col] : 0.f;
-        v[e] = __float2bfloat16_rn(x);
+        for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(acc[e]);
+    } else {
+        const float* W = p.w[param_index(l)];
+        const int ld = in_features(l);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int col = source_col(l, chunk, c16 * 8 + e);
+            float x = col >= 0 ? W[(size_t)out_row * ld + col] : 0.f;
+            v[e] = __float2bfloat16_rn(x);
+        }
     }
     uint4 q;
     q.x = (uint32_t)__bfloat16_as_ushort(v[0]) | ((uint32_t)__bfloat16_as_ushort(v[1]) << 16);
@@ -88,17 +124,27 @@ __device__ __forceinline__ void pack_weights_bwd_item(const ParamPtrs& p, uint8_
     const int j = stage < 4 ? 0 : 1 + (stage - 4) / 8;
     const int local = stage - bwd_first_stage(j);
     const int chunk = local / 2, half = local % 2;
-    const int pi = j == 0 ? 10 : 9 - j;                 // l10, l9, l8, l7, l6, l5, l4, l3, l2
-    const int ld = pi == 10 ? 283 : (pi == 5 ? 319 : 256);
-    const int col_off = pi == 5 ? kPeDim : 0;           // l6: the h5 columns follow the 63 PE columns
-    const float* W = p.w[pi];
     const int n = half * kStageRows + r;
     uint32_t q[4];
+    if (j == 0) {                                       // (l10[:, :256] . l9)^T: row = input feature of l9, column = output of l10
+        float acc[8];
+        fold_col8(p, chunk * 64 + c16 * 8, n, acc);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int k = chunk * 64 + c16 * 8 + 2 * e;
-        __nv_bfloat162 h = __floats2bfloat162_rn(W[(size_t)k * ld + col_off + n], W[(size_t)(k + 1) * ld + col_off + n]);
-        q[e] = *reinterpret_cast<uint32_t*>(&h);
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
+            q[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    } else {
+        const int pi = 8 - j;                           // l8, l7, l6, l5, l4, l3, l2
+        const int ld = pi == 5 ? 319 : 256;
+        const int col_off = pi == 5 ? kPeDim : 0;       // l6: the h5 columns follow the 63 PE columns
+        const float* W = p.w[pi];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = chunk * 64 + c16 * 8 + 2 * e;
+            __nv_bfloat162 h = __floats2bfloat162_rn(W[(size_t)k * ld + col_off + n], W[(size_t)(k + 1) * ld + col_off + n]);
+            q[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
     }
     *reinterpret_cast<uint4*>(blob + (size_t)stage * kStageBytes + swz128_offset(r, c16 * 8)) =
         make_uint4(q[0], q[1], q[2], q[3]);
@@ -120,8 +166,8 @@ __global__ void pack_tail_bwd_kernel(ParamPtrs p, float* __restrict__ tail) {
 __device__ __forceinline__ void pack_tail_item(const ParamPtrs& p, float* __restrict__ tail, int i) {
     if (i >= kTailFloats) return;
     float v = 0.f;
-    if (i < kTailWAlpha) {                       // biases b1..b9
-        v = p.b[i / kHidden][i % kHidden];
+    if (i < kTailWAlpha) {                       // biases b1..b8 (row 8 unused)
+        v = i / kHidden < 8 ? p.b[i / kHidden][i % kHidden] : 0.f;
     } else if (i < kTailBAlpha) {
         v = p.w[9][i - kTailWAlpha];
     } else if (i < kTailW11) {
@@ -135,8 +181,10 @@ __device__ __forceinline__ void pack_tail_item(const ParamPtrs& p, float* __rest
         int k = i - kTailW10View;
         int n = k / 28, c = k % 28;
         v = c < kViewPeDim ? p.w[10][(size_t)n * 283 + 256 + c] : 0.f;
-    } else {
-        v = p.b[10][i - kTailB10];
+    } else {                                     // l10.bias + l10.weight[:, :256] . l9.bias (l9 folded into l10)
+        const int o = i - kTailB10;
+        v = p.b[10][o];
+        for (int k = 0; k < kHidden; ++k) v = fmaf(p.w[10][(size_t)o * 283 + k], p.b[8][k], v);
     }
     tail[i] = v;
 }

@@ -476,8 +476,21 @@ def viewdir_term_bwd(dz, rows, dirs, vterm_div, embedded, blob, stream=None):
     return blob
 
 
-def mlp_bwd_params(act, dz, grad_raw, rows, dirs, vterm_div, embedded, blob, side_stream=None):
-    """dW/db of every layer accumulated into the fp32 gradient blob (3 launches).
+def mlp_bwd_unfold(blob, params, stream=None):
+    """Gradients of l9 and of l10's first 256 columns from the blob's scratch region (l9 is folded into
+    l10, csrc/mlp_layout.h).  params: the Model's 24 tensors in registration order.  Once per backward
+    pass, after mlp_bwd_dw and viewdir_term_bwd."""
+    lib = _lib.load()
+    w9, b9, w10 = (f32c(params[i].detach()) for i in (16, 17, 20))     # l9.weight, l9.bias, l10.weight
+    check(lib.nerf_mlp_bwd_unfold(ptr(blob), ptr(w9), ptr(b9), ptr(w10), _cuda_stream(stream, blob.device)),
+          "nerf_mlp_bwd_unfold")
+    return blob
+
+
+def mlp_bwd_params(act, dz, grad_raw, rows, dirs, vterm_div, embedded, blob, side_stream=None, params=None):
+    """dW/db of every layer accumulated into the fp32 gradient blob (3 launches + the unfold of the
+    folded l9/l10 gradients when the Model's ``params`` are given; callers that schedule the launches
+    themselves call mlp_bwd_unfold last).
 
     With ``side_stream`` the two small CUDA-core kernels (l_alpha/l11 heads, l10 view columns) run on
     that stream next to the tensor-core dW kernel instead of after it; the caller's stream waits for
@@ -493,6 +506,8 @@ def mlp_bwd_params(act, dz, grad_raw, rows, dirs, vterm_div, embedded, blob, sid
     viewdir_term_bwd(dz, rows, dirs, vterm_div, embedded, blob, stream=small)
     if side_stream is not None:
         main.wait_stream(side_stream)
+    if params is not None:
+        mlp_bwd_unfold(blob, params)
     return blob
 
 

@@ -175,7 +175,7 @@ class Model(nn.Module):
         rows = spec["rows"]
         dz = K.mlp_bwd_dz(packed_bwd, grad_raw.reshape(rows, 4), act, rows)
         K.mlp_bwd_params(act, dz, grad_raw.reshape(rows, 4), rows, spec["dirs"], spec["vterm_div"],
-                         spec.get("dirs_embedded", False), blob)
+                         spec.get("dirs_embedded", False), blob, params=self.ordered_params())
         return blob
 
     def _backward_raw(self, spec, act, packed_bwd, grad_raw):

@@ -203,6 +203,10 @@ class TrainStep:
                 K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=dz)
                 K.mlp_bwd_params(act, dz, graw, rows, rays, s, False, self.blob[idx], side_stream=side if sched == 1 else None)
         main.wait_stream(side)
+        # l9 is folded into l10 (csrc/mlp_layout.h): its gradients and those of l10's first 256 columns
+        # follow from the G = dZ10^T h8 the dW kernel left in the blob and from db10 (view-column kernel)
+        for idx in range(2):
+            K.mlp_bwd_unfold(self.blob[idx], self.params[idx])
         return self.loss
 
     @torch.no_grad()

@@ -230,6 +230,16 @@ size_t nerf_grad_blob_bytes(void);
 int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, float* grad_blob, void* stream);
 int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, long M, float* grad_blob,
                        void* stream);
+/* l9 is folded into l10 in the forward pass and in the dZ chain (feat = l9(h8) feeds l10 without an
+ * activation, model.py:100-104; csrc/mlp_layout.h), so nerf_mlp_bwd_dw leaves G = dZ10^T . h8 in the
+ * blob's scratch region instead of the gradients of l9 and of l10's first 256 columns.  This call forms
+ * them by the chain rule -- dW10[:, :256] += G W9^T + db10 (x) b9, dW9 += W10[:, :256]^T G,
+ * db9 += W10[:, :256]^T db10 -- from the FP32 parameters l9.weight [256,256], l9.bias [256],
+ * l10.weight [128,283].  Call it ONCE per backward pass, after nerf_mlp_bwd_dw and
+ * nerf_viewdir_term_bwd (which produces db10) have completed on `stream`. */
+int nerf_mlp_bwd_unfold(float* grad_blob, const float* l9_weight, const float* l9_bias,
+                        const float* l10_weight, void* stream);
+
 /* dirs / dir_stride / embedded / vterm_div exactly as passed to nerf_viewdir_term + nerf_mlp_fwd */
 int nerf_viewdir_term_bwd(const void* dz, const float* dirs, int dir_stride, int embedded, long M,
                           int vterm_div, float* grad_blob, void* stream);

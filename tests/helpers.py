@@ -16,8 +16,9 @@ def bf16(t):
 def emulate_field(p, pe63, vterm, probe=None):
     """The kernel's arithmetic restated on the CPU: every tensor-core operand (activations and
     weights) rounded to BF16, FP32+ accumulation, FP32 bias/activation, FP32 sigma and rgb heads.
-    pe63 [M,63] fp32 encoding, vterm [M,128].  Returns raw [M,4] (and layer `probe`'s
-    post-activation values)."""
+    pe63 [M,63] fp32 encoding, vterm [M,128] (vterm_reference: includes the folded l9 bias).
+    l9 is folded into l10 as the kernel does it (csrc/mlp_layout.h): W' = BF16(W10[:, :256] . W9).
+    Returns raw [M,4] (and layer `probe`'s post-activation values: 0..7 = h1..h8, 8 = h10)."""
     W = lambda n: bf16(p[n + ".weight"]).double()
     b = lambda n: p[n + ".bias"].double()
     x = bf16(pe63).double()
@@ -30,9 +31,7 @@ def emulate_field(p, pe63, vterm, probe=None):
     for n in ("l7", "l8"):
         h = torch.relu(bf16(h.float()).double() @ W(n).T + b(n)); acts.append(h)
     sigma = h @ p["l_alpha.weight"].double().T + p["l_alpha.bias"].double()      # fp32 head on fp32 h8
-    feat = bf16(h.float()).double() @ W("l9").T + b("l9"); acts.append(feat)
-    w10 = W("l10")[:, :256]
-    h10 = torch.relu(bf16(feat.float()).double() @ w10.T + vterm.double()); acts.append(h10)
+    h10 = torch.relu(bf16(h.float()).double() @ folded_l10_weight(p).T + vterm.double()); acts.append(h10)
     rgb = h10 @ p["l11.weight"].double().T + p["l11.bias"].double()              # fp32 head on fp32 h10
     raw = torch.cat([rgb, sigma], -1).float()
     if probe is None:
@@ -40,10 +39,17 @@ def emulate_field(p, pe63, vterm, probe=None):
     return raw, acts[probe].float()
 
 
+def folded_l10_weight(p):
+    """W' = l10.weight[:, :256] . l9.weight, formed in FP32 and rounded to BF16 once (as the pack kernels
+    do; model.py:100-104 applies l9 without an activation and feeds only l10) -> fp64 [128,256]."""
+    return bf16((p["l10.weight"][:, :256].double() @ p["l9.weight"].double()).float()).double()
+
+
 def vterm_reference(p, dirs):
-    """W10[:,256:283] . PE4(dir) + b10 in fp64 -> fp32."""
+    """W10[:,256:283] . PE4(dir) + b10 + W10[:, :256] . b9 (the folded l9 bias) in fp64 -> fp32."""
     pe = O.freq_encode(dirs, 4).double()
-    return (pe @ p["l10.weight"][:, 256:].double().T + p["l10.bias"].double()).float()
+    w10 = p["l10.weight"].double()
+    return (pe @ w10[:, 256:].T + p["l10.bias"].double() + w10[:, :256] @ p["l9.bias"].double()).float()
 
 
 def load_model_params(model, p):

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/nerf_b200.h but not exported"
     assert sorted(_lib.public_symbols()) == declared, "ctypes table and header disagree"
     assert lib.nerf_b200_abi_version() == 1
-    assert lib.nerf_packed_model_bytes() == 72 * 16384 + 4 * (9 * 256 + 256 + 4 + 384 + 4 + 128 * 28 + 128)
+    assert lib.nerf_packed_model_bytes() == 64 * 16384 + 4 * (9 * 256 + 256 + 4 + 384 + 4 + 128 * 28 + 128)
 
 
 def test_no_cpu_fallback():

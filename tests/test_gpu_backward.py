@@ -10,11 +10,12 @@ import pytest
 import torch
 
 from oracle import nerf_oracle as O
-from tests.helpers import (bf16, decode_tile_image, focal_of, golden, grad_stats, load_model_params, record)
+from tests.helpers import (bf16, decode_tile_image, focal_of, folded_l10_weight, golden, grad_stats, load_model_params,
+                           record)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-ACT_TILE, DZ_TILE = 675840, 622592     # csrc/mlp_bwd_layout.h: kActTileBytes, kDzTileBytes
+ACT_TILE, DZ_TILE = 610304, 557056     # csrc/mlp_bwd_layout.h: kActTileBytes, kDzTileBytes (no h9 / dZ9: l9 is folded into l10)
 
 
 def _K():
@@ -66,21 +67,26 @@ def _emulated_chain(p, pe, acts, pe_dir, grad_raw, mask_acts=None):
     dz, r = {}, {}
     r16 = lambda t: bf16(t.float()).double()
     dz[10] = r16((g[:, :3] @ p["l11.weight"].double()) * (a[10] > 0))
-    dz[9] = r16(dz[10] @ W("l10")[:, :256])
-    dz[8] = r16((dz[9] @ W("l9") + g[:, 3:4] * p["l_alpha.weight"].double()) * (a[8] > 0))
+    # l9 folded into l10: dZ8 comes straight from dZ10 through W' = BF16(W10[:, :256] . W9); there is no dZ9
+    dz[8] = r16((dz[10] @ folded_l10_weight(p) + g[:, 3:4] * p["l_alpha.weight"].double()) * (a[8] > 0))
     dz[7] = r16((dz[8] @ W("l8")) * (a[7] > 0))
     dz[6] = r16((dz[7] @ W("l7")) * (a[6] > 0))
     dz[5] = r16((dz[6] @ W("l6")[:, 63:]) * (a[5] > 0))
     for i in (4, 3, 2, 1):
         dz[i] = r16((dz[i + 1] @ W(f"l{i + 1}")) * (a[i] > 0))
-    x_in = {1: pe.double()[:, :63], 6: torch.cat([pe.double()[:, :63], vals[5]], -1), 10: vals[9]}
-    for i in range(1, 10):
+    x_in = {1: pe.double()[:, :63], 6: torch.cat([pe.double()[:, :63], vals[5]], -1)}
+    for i in range(1, 9):
         x = x_in.get(i, vals.get(i - 1))
         r[f"l{i}.weight"] = dz[i].T @ x
         r[f"l{i}.bias"] = dz[i].sum(0)
     dv = dz[10]
-    r["l10.weight"] = torch.cat([dv.T @ vals[9], dv.T @ pe_dir.double()], -1)
-    r["l10.bias"] = dv.sum(0)
+    # the unfold (nerf_mlp_bwd_unfold): G = dZ10^T h8, then the chain rule through feat = W9 h8 + b9 in FP32
+    G, db10 = dv.T @ vals[8], dv.sum(0)
+    w9, b9, w10a = p["l9.weight"].double(), p["l9.bias"].double(), p["l10.weight"][:, :256].double()
+    r["l10.weight"] = torch.cat([G @ w9.T + db10[:, None] * b9[None, :], dv.T @ pe_dir.double()], -1)
+    r["l10.bias"] = db10
+    r["l9.weight"] = w10a.T @ G
+    r["l9.bias"] = w10a.T @ db10
     r["l_alpha.weight"] = (g[:, 3:4] * vals[8]).sum(0, keepdim=True)
     r["l_alpha.bias"] = g[:, 3].sum().reshape(1)
     r["l11.weight"] = g[:, :3].T @ vals[10]
@@ -125,11 +131,11 @@ def test_field_backward_stages(rows, S):
     want_pe = torch.cat([O.freq_encode(pts, 10), torch.zeros(rows, 1)], -1)
     assert (pe - bf16(want_pe)).abs().max() <= 2e-2          # bf16 ulp at |x|<=2 is 1.6e-2 (sin/cos anchors)
     saved = {}
-    for i in range(1, 10):
+    for i in range(1, 9):
         saved[i] = decode_tile_image(act, n_tiles, ACT_TILE, 16384 + (i - 1) * 65536, 4)[:rows]
         err = (saved[i] - acts[i]).abs().max().item()
         assert err <= 2e-2 * max(1.0, acts[i].abs().max().item()), (i, err)
-    saved[10] = decode_tile_image(act, n_tiles, ACT_TILE, 16384 + 9 * 65536, 2)[:rows]
+    saved[10] = decode_tile_image(act, n_tiles, ACT_TILE, 16384 + 8 * 65536, 2)[:rows]
     assert (saved[10] - acts[10]).abs().max() <= 2e-2 * max(1.0, acts[10].abs().max().item())
     pe_dir = O.freq_encode(dirs.repeat_interleave(S, 0), 4)
     dz_emu, g_emu = _emulated_chain(p, pe, saved, pe_dir, grad_raw)
@@ -144,10 +150,10 @@ def test_field_backward_stages(rows, S):
     dz = K.mlp_bwd_dz(model.packed_bwd(), grad_raw.to(DEV), act, rows)
     torch.cuda.synchronize()
     assert dz.numel() == n_tiles * DZ_TILE
-    full = decode_tile_image(dz, n_tiles, DZ_TILE, 9 * 65536, 2)
+    full = decode_tile_image(dz, n_tiles, DZ_TILE, 8 * 65536, 2)
     assert full[rows:].abs().max().item() == 0 if full.shape[0] > rows else True, "padding rows must carry zero gradient"
-    for i in range(10, 0, -1):
-        off, nb = (9 * 65536, 2) if i == 10 else ((i - 1) * 65536, 4)
+    for i in (10, 8, 7, 6, 5, 4, 3, 2, 1):          # no dZ9: l9 is folded into l10
+        off, nb = (8 * 65536, 2) if i == 10 else ((i - 1) * 65536, 4)
         got = decode_tile_image(dz, n_tiles, DZ_TILE, off, nb)[:rows]
         # (a) the kernel's own arithmetic (BF16 operands, masks from the saved activations): tight
         se = grad_stats(got, dz_emu[i])
@@ -165,7 +171,7 @@ def test_field_backward_stages(rows, S):
 
     # 3. parameter gradients
     blob = torch.zeros(K.grad_blob_floats(), device=DEV)
-    K.mlp_bwd_params(act, dz, grad_raw.to(DEV), rows, dirs.to(DEV), S, False, blob)
+    K.mlp_bwd_params(act, dz, grad_raw.to(DEV), rows, dirs.to(DEV), S, False, blob, params=model.ordered_params())
     grads = [torch.empty_like(q) for q in model.ordered_params()]
     K.grad_unpack(blob, grads)
     torch.cuda.synchronize()

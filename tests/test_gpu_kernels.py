@@ -222,7 +222,7 @@ def test_field_embedded_mode_layers(rows):
     vt = vterm_reference(p, dirs)
     xd = x.to(DEV).contiguous()
     vtd = K.viewdir_term(packed, x[:, 63:].contiguous().to(DEV), embedded=True)
-    for layer in range(10):
+    for layer in range(9):          # h1..h8, h10 (l9 is folded into l10)
         raw, probe = K.mlp_fwd(packed, K.IN_EMBEDDED, xd, None, rows, 1, vtd, 1, in_stride=90, probe_layer=layer)
         want_raw, want_act = emulate_field(p, x[:, :63], vt, probe=layer)
         width = want_act.shape[1]

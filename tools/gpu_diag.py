@@ -41,7 +41,7 @@ def layer_report(rows):
     vtd = K.viewdir_term(packed, x[:, 63:].contiguous().to(DEV), embedded=True)
     print(f"vterm max err {(vtd.cpu() - vt).abs().max().item():.3e}")
     ok = True
-    for layer in range(10):
+    for layer in range(9):
         raw, probe = K.mlp_fwd(packed, K.IN_EMBEDDED, xd, None, rows, 1, vtd, 1, in_stride=90, probe_layer=layer)
         torch.cuda.synchronize()
         want_raw, want = emulate_field(p, x[:, :63], vt, probe=layer)
@@ -81,12 +81,7 @@ def timing():
         z = K.sample_coarse(rays, S)
         vt = K.viewdir_term(packed, rays)
         ref = None
-        for tag, tail, mode in (("smem bias", None, 0), ("host tail, single CTA", ht, 0), ("host tail, CTA pairs", ht, 1),
-                                ("host tail, single CTA, 16-warp crew", ht, 2), ("host tail, mixed orientation", ht, 3), ("host tail, TS (activations in TMEM)", ht, 4),
-                                ("host tail, CTA pairs + 16-warp crew", ht, 5),
-                                ("host tail, CTA pairs, tensor-map weight copies", ht, 6),
-                                ("host tail, CTA pairs + crew, tensor-map weight copies", ht, 7)):
-            K.use_pairs(mode)
+        for tag, tail in (("biases staged in shared memory", None), ("biases in the kernel parameters (production)", ht)):
             for _ in range(3):
                 raw = K.mlp_fwd(packed, K.IN_RAYS, rays, z, n_rays * S, S, vt, S, host_tail=tail)
             torch.cuda.synchronize()

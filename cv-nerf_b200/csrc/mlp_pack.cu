@@ -56,6 +56,9 @@ __device__ __forceinline__ void fold_row8(const ParamPtrs& p, int o, int i, floa
     const float* w9 = p.w[8] + i;
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // (unrolled so that the loads of eight k -- L2 hits right after an optimizer step -- are in flight together;
+    // the accumulation order per output stays k = 0, 1, 2, ...)
+#pragma unroll 8
     for (int k = 0; k < kHidden; ++k) {
         const float a = __ldg(w10 + k);
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)k * kHidden));
@@ -70,6 +73,7 @@ __device__ __forceinline__ void fold_col8(const ParamPtrs& p, int o, int i, floa
     const float* w9 = p.w[8] + i;
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 8
     for (int k = 0; k < kHidden; ++k) {
         const float b = __ldg(w9 + (size_t)k * kHidden);
 #pragma unroll
@@ -184,7 +188,8 @@ __device__ __forceinline__ void pack_tail_item(const ParamPtrs& p, float* __rest
     } else {                                     // l10.bias + l10.weight[:, :256] . l9.bias (l9 folded into l10)
         const int o = i - kTailB10;
         v = p.b[10][o];
-        for (int k = 0; k < kHidden; ++k) v = fmaf(p.w[10][(size_t)o * 283 + k], p.b[8][k], v);
+#pragma unroll 16
+        for (int k = 0; k < kHidden; ++k) v = fmaf(__ldg(p.w[10] + (size_t)o * 283 + k), __ldg(p.b[8] + k), v);
     }
     tail[i] = v;
 }

@@ -294,7 +294,7 @@ def test_train_step_gradients_match_reference_fixture(name):
     whole = grad_stats(all_got, all_ref)
     print(name, "whole gradient vector (1 191 688 values) vs the fp32 reference:", whole)
     record("grad_e2e_whole", dict(fixture=name, rel_l2=whole["rel_l2"], cos=whole["cos"], rays=int(keep.sum()), n_flip=n_flip))
-    assert whole["rel_l2"] <= 0.08 and whole["cos"] >= 0.997, whole
+    assert whole["rel_l2"] <= 0.04 and whole["cos"] >= 0.999, whole     # measured 0.021 / 0.0039, cos 0.99986 / 0.99999
     for tag, net, q in (("coarse", coarse, cq), ("fine", fine, fq)):
         for k, prm in net.named_parameters():
             st = grad_stats(prm.grad.detach().cpu(), q[k].grad)

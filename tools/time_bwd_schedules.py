@@ -22,9 +22,11 @@ ts = TrainStep(coarse, fine, height=400, width=400, focal=555.5555, n_rays=n, pe
                ndc=False, near=2., far=6., seed=1)
 image = torch.rand(400, 400, 3, device=dev)
 pose = pose_spherical(-180., -30., 4.)[:3, :4].to(dev)
+configs = [(0, 0), (2, 0), (3, 30), (3, 40), (3, 50), (4, 30), (4, 40), (4, 50)]
 for rnd in range(2):
-    for sched in (0, 1, 2):
+    for sched, split in configs:
         os.environ["NERF_B200_BWD_SCHED"] = str(sched)
+        os.environ["NERF_B200_BWD_SPLIT"] = str(split)
         for _ in range(3):
             ts.step(image, pose)
         torch.cuda.synchronize()
@@ -34,4 +36,4 @@ for rnd in range(2):
             ts.step(image, pose)
         e1.record()
         torch.cuda.synchronize()
-        print(f"round {rnd} schedule {sched}: {e0.elapsed_time(e1) / reps:.3f} ms per train step ({n} rays)")
+        print(f"round {rnd} schedule {sched} split {split}: {e0.elapsed_time(e1) / reps:.3f} ms per train step ({n} rays)")

@@ -91,10 +91,6 @@ _SIGNATURES = {
     "nerf_mlp_bwd_heads": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_long, c_float_p, ctypes.c_void_p]),
     "nerf_viewdir_term_bwd": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_long,
                                              ctypes.c_int, c_float_p, ctypes.c_void_p]),
-    "nerf_mlp_bwd_dz_ex": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
-                                          ctypes.c_int, ctypes.c_void_p]),
-    "nerf_mlp_bwd_dw_ex": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, c_float_p, ctypes.c_int,
-                                          ctypes.c_void_p]),
     "nerf_mlp_bwd_unfold": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     "nerf_grad_unpack": (ctypes.c_int, [c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]),
     "nerf_mse_loss_grad": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_long, c_float_p, c_float_p,

@@ -225,16 +225,7 @@ int job_weight(const LayerJob& j) { return (j.a_blocks + j.b_blocks) * 16; }
 extern "C" size_t nerf_grad_blob_bytes(void) { return (size_t)nerf::kGradFloats * 4; }
 
 // dW / db of l1..l10 (tensor-core layers) accumulated into grad_blob (+=).
-extern "C" int nerf_mlp_bwd_dw_ex(const void* act_save, const void* dz, long M, float* grad_blob, int max_ctas,
-                                  void* stream);
-
 extern "C" int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, float* grad_blob, void* stream) {
-    return nerf_mlp_bwd_dw_ex(act_save, dz, M, grad_blob, 0, stream);
-}
-
-// max_ctas > 0 limits the grid (one CTA per SM), see nerf_mlp_bwd_dz_ex.
-extern "C" int nerf_mlp_bwd_dw_ex(const void* act_save, const void* dz, long M, float* grad_blob, int max_ctas,
-                                  void* stream) {
     nerf::DeviceGuard device_guard(grad_blob);
     if (M < 0 || (M > 0 && (!act_save || !dz || !grad_blob))) return nerf::arg_error("nerf_mlp_bwd_dw");
     if (M == 0) return 0;
@@ -276,8 +267,7 @@ extern "C" int nerf_mlp_bwd_dw_ex(const void* act_save, const void* dz, long M, 
     // split the SMs over the layers in proportion to their traffic, at most one CTA per tile
     const long cap = P.n_tiles;
     int total = kNumJobsLayers;
-    const int budget = (max_ctas >= kNumJobsLayers && max_ctas < sm_count) ? max_ctas : sm_count;
-    while (total < budget) {
+    while (total < sm_count) {
         int best = -1;
         double best_load = 0.;
         for (int i = 0; i < kNumJobsLayers; ++i) {

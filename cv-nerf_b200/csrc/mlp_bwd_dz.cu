@@ -336,19 +336,8 @@ extern "C" size_t nerf_mlp_dz_bytes(long M) {
     return M <= 0 ? 0 : (size_t)((M + kTileM - 1) / kTileM) * nerf::kDzTileBytes;
 }
 
-extern "C" int nerf_mlp_bwd_dz_ex(const void* packed_bwd, const float* grad_raw, const void* act_save, long M,
-                                  void* dz_out, int max_ctas, void* stream);
-
 extern "C" int nerf_mlp_bwd_dz(const void* packed_bwd, const float* grad_raw, const void* act_save, long M,
                                void* dz_out, void* stream) {
-    return nerf_mlp_bwd_dz_ex(packed_bwd, grad_raw, act_save, M, dz_out, 0, stream);
-}
-
-// max_ctas > 0 limits the persistent grid (one CTA per SM) so that another kernel can run beside this one
-// on the remaining SMs (train.TrainStep overlaps the write-bound dZ chain of one network with the
-// read-bound dW contraction of the other).
-extern "C" int nerf_mlp_bwd_dz_ex(const void* packed_bwd, const float* grad_raw, const void* act_save, long M,
-                                  void* dz_out, int max_ctas, void* stream) {
     nerf::DeviceGuard device_guard(dz_out);
     if (M < 0 || (M > 0 && (!packed_bwd || !grad_raw || !act_save || !dz_out))) return nerf::arg_error("nerf_mlp_bwd_dz");
     if (M == 0) return 0;
@@ -376,8 +365,7 @@ extern "C" int nerf_mlp_bwd_dz_ex(const void* packed_bwd, const float* grad_raw,
     P.blob = (const uint8_t*)packed_bwd; P.grad_raw = grad_raw; P.act = (const uint8_t*)act_save;
     P.dz = (uint8_t*)dz_out; P.M = M;
     const long n_pairs = ((M + kTileM - 1) / kTileM + 1) / 2;
-    const int cap = (max_ctas > 0 && max_ctas < sm_count) ? max_ctas : sm_count;
-    const unsigned grid = (unsigned)(n_pairs < cap ? n_pairs : cap);
+    const unsigned grid = (unsigned)(n_pairs < sm_count ? n_pairs : sm_count);
     mlp_bwd_dz_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
     return nerf::check_launch("nerf_mlp_bwd_dz");
 }

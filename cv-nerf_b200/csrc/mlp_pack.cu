@@ -82,8 +82,18 @@ __device__ __forceinline__ void fold_col8(const ParamPtrs& p, int o, int i, floa
 }
 
 // one thread = one 16-byte chunk (8 consecutive k) of one stage row
-__device__ __forceinline__ void pack_weights_item(const ParamPtrs& p, uint8_t* __restrict__ blob, int gid) {
+// fold_sel: 0 = every stage; 1 = skip the folded layer's stages; 2 = only them (gid counts from their first
+// item).  The folded layer costs a 256-long dot product per value, so the one-launch re-pack of the training
+// step gives those items blocks of their own, one warp each, spread over the SMs (eight warps of them in one
+// block serialise on that SM's L1 port: 85 us instead of ~10).
+constexpr int kFoldFwdFirst = layer_first_stage(kNumMmaLayers - 1) * kStageRows * 8;
+constexpr int kFoldFwdItems = 4 * kStageRows * 8;
+constexpr int kFoldBwdItems = 4 * kStageRows * 8;      // the transposed blob starts with them
+
+__device__ __forceinline__ void pack_weights_item(const ParamPtrs& p, uint8_t* __restrict__ blob, int gid, int fold_sel = 0) {
+    if (fold_sel == 2) gid += kFoldFwdFirst;
     if (gid >= kNumStages * kStageRows * 8) return;
+    if (fold_sel == 1 && gid >= kFoldFwdFirst) return;
     int stage = gid / (kStageRows * 8);
     int r = (gid / 8) % kStageRows;
     int c16 = gid % 8;
@@ -120,8 +130,9 @@ __global__ void pack_weights_kernel(ParamPtrs p, uint8_t* __restrict__ blob) {
     pack_weights_item(p, blob, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__device__ __forceinline__ void pack_weights_bwd_item(const ParamPtrs& p, uint8_t* __restrict__ blob, int gid) {
+__device__ __forceinline__ void pack_weights_bwd_item(const ParamPtrs& p, uint8_t* __restrict__ blob, int gid, int fold_sel = 0) {
     if (gid >= kBwdStages * kStageRows * 8) return;
+    if ((fold_sel == 1 && gid < kFoldBwdItems) || (fold_sel == 2 && gid >= kFoldBwdItems)) return;
     const int stage = gid / (kStageRows * 8);
     const int r = (gid / 8) % kStageRows;
     const int c16 = gid % 8;
@@ -167,8 +178,19 @@ __global__ void pack_tail_bwd_kernel(ParamPtrs p, float* __restrict__ tail) {
     pack_tail_bwd_item(p, tail, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__device__ __forceinline__ void pack_tail_item(const ParamPtrs& p, float* __restrict__ tail, int i) {
+// b10' = l10.bias + l10.weight[:, :256] . l9.bias for one output, by one warp (lanes stride over k)
+__device__ __forceinline__ void pack_b10_warp(const ParamPtrs& p, float* __restrict__ tail, int o, int lane) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = lane; k < kHidden; k += 32) v = fmaf(__ldg(p.w[10] + (size_t)o * 283 + k), __ldg(p.b[8] + k), v);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) tail[kTailB10 + o] = v + p.b[10][o];
+}
+
+__device__ __forceinline__ void pack_tail_item(const ParamPtrs& p, float* __restrict__ tail, int i, bool skip_b10 = false) {
     if (i >= kTailFloats) return;
+    if (skip_b10 && i >= kTailB10) return;
     float v = 0.f;
     if (i < kTailWAlpha) {                       // biases b1..b8 (row 8 unused)
         v = i / kHidden < 8 ? p.b[i / kHidden][i % kHidden] : 0.f;
@@ -194,8 +216,15 @@ __device__ __forceinline__ void pack_tail_item(const ParamPtrs& p, float* __rest
     tail[i] = v;
 }
 
+// (the folded bias is always formed by pack_b10_warp, so that the stand-alone pack and the training step's
+// one-launch re-pack write the same bits)
 __global__ void pack_tail_kernel(ParamPtrs p, float* __restrict__ tail) {
-    pack_tail_item(p, tail, blockIdx.x * blockDim.x + threadIdx.x);
+    const int b10_blocks = kL10Out / 8;                      // eight warps per block, one output per warp
+    if ((int)blockIdx.x < b10_blocks) {
+        pack_b10_warp(p, tail, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
+        return;
+    }
+    pack_tail_item(p, tail, (blockIdx.x - b10_blocks) * blockDim.x + threadIdx.x, true);
 }
 
 // Everything the training step re-packs after an optimizer step, for up to two Models, in ONE
@@ -204,7 +233,9 @@ constexpr int kPackFwdBlocks = (kNumStages * kStageRows * 8 + 255) / 256;
 constexpr int kPackBwdBlocks = (kBwdStages * kStageRows * 8 + 255) / 256;
 constexpr int kPackTailBlocks = (kTailFloats + 255) / 256;
 constexpr int kPackTailBwdBlocks = (kBwdTailFloats + 255) / 256;
-constexpr int kPackBlocksPerModel = kPackFwdBlocks + kPackBwdBlocks + kPackTailBlocks + kPackTailBwdBlocks;
+constexpr int kPackFoldBlocks = (kFoldFwdItems + kFoldBwdItems) / 32 + kL10Out;   // one warp of fold items per block,
+                                                                                   // then one warp per folded bias
+constexpr int kPackBlocksPerModel = kPackFwdBlocks + kPackBwdBlocks + kPackTailBlocks + kPackTailBwdBlocks + kPackFoldBlocks;
 
 struct PackAll {
     ParamPtrs p[2];
@@ -216,12 +247,21 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ P
     const int model = blockIdx.x / kPackBlocksPerModel;
     int b = blockIdx.x % kPackBlocksPerModel;
     const ParamPtrs& p = A.p[model];
-    if (b < kPackFwdBlocks) { pack_weights_item(p, A.fwd[model], b * 256 + threadIdx.x); return; }
+    if (b < kPackFoldBlocks) {              // first, so that the long items start first
+        if (threadIdx.x >= 32) return;
+        const int item = b * 32 + threadIdx.x;
+        if (item < kFoldFwdItems) pack_weights_item(p, A.fwd[model], item, 2);
+        else if (item < kFoldFwdItems + kFoldBwdItems) pack_weights_bwd_item(p, A.bwd[model], item - kFoldFwdItems, 2);
+        else pack_b10_warp(p, reinterpret_cast<float*>(A.fwd[model] + kWeightBytes), b - (kFoldFwdItems + kFoldBwdItems) / 32, threadIdx.x);
+        return;
+    }
+    b -= kPackFoldBlocks;
+    if (b < kPackFwdBlocks) { pack_weights_item(p, A.fwd[model], b * 256 + threadIdx.x, 1); return; }
     b -= kPackFwdBlocks;
-    if (b < kPackBwdBlocks) { pack_weights_bwd_item(p, A.bwd[model], b * 256 + threadIdx.x); return; }
+    if (b < kPackBwdBlocks) { pack_weights_bwd_item(p, A.bwd[model], b * 256 + threadIdx.x, 1); return; }
     b -= kPackBwdBlocks;
     if (b < kPackTailBlocks) {
-        pack_tail_item(p, reinterpret_cast<float*>(A.fwd[model] + kWeightBytes), b * 256 + threadIdx.x);
+        pack_tail_item(p, reinterpret_cast<float*>(A.fwd[model] + kWeightBytes), b * 256 + threadIdx.x, true);
         return;
     }
     b -= kPackTailBlocks;
@@ -319,7 +359,7 @@ extern "C" int nerf_pack_model(const float* const* host_params, void* packed_out
     cudaStream_t st = (cudaStream_t)stream;
     int n = kNumStages * kStageRows * 8;
     pack_weights_kernel<<<nerf::blocks_for(n, 256), 256, 0, st>>>(p, (uint8_t*)packed_out);
-    pack_tail_kernel<<<nerf::blocks_for(kTailFloats, 256), 256, 0, st>>>(
+    pack_tail_kernel<<<nerf::blocks_for(kTailFloats, 256) + kL10Out / 8, 256, 0, st>>>(
         p, (float*)((uint8_t*)packed_out + kWeightBytes));
     return nerf::check_launch("nerf_pack_model");
 }

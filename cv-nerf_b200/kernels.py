@@ -424,13 +424,13 @@ def pack_models_train(param_lists, packed, packed_bwd):
     check(lib.nerf_pack_models_train(len(param_lists), arr, out, outb, stream_of(flat[0])), "nerf_pack_models_train")
 
 
-def mlp_bwd_dz(packed_bwd, grad_raw, act, rows, dz=None, stream=None, max_ctas=0):
+def mlp_bwd_dz(packed_bwd, grad_raw, act, rows, dz=None, stream=None):
     lib = _lib.load()
     grad_raw = f32c(grad_raw)
     if dz is None:
         dz = torch.empty(dz_bytes(rows), dtype=torch.uint8, device=grad_raw.device)
-    check(lib.nerf_mlp_bwd_dz_ex(packed_bwd.data_ptr(), ptr(grad_raw), act.data_ptr(), rows, dz.data_ptr(), int(max_ctas),
-                                 _cuda_stream(stream, grad_raw.device)), "nerf_mlp_bwd_dz")
+    check(lib.nerf_mlp_bwd_dz(packed_bwd.data_ptr(), ptr(grad_raw), act.data_ptr(), rows, dz.data_ptr(),
+                              _cuda_stream(stream, grad_raw.device)), "nerf_mlp_bwd_dz")
     return dz
 
 
@@ -455,11 +455,11 @@ def mlp_bwd_heads(act, grad_raw, rows, blob, stream=None):
     return blob
 
 
-def mlp_bwd_dw(act, dz, rows, blob, stream=None, max_ctas=0):
+def mlp_bwd_dw(act, dz, rows, blob, stream=None):
     """dW/db of the tensor-core layers into the gradient blob (l9/l10: G = dZ10^T h8 into its scratch region)."""
     lib = _lib.load()
-    check(lib.nerf_mlp_bwd_dw_ex(_byte_ptr(act, "act"), _byte_ptr(dz, "dz"), rows, ptr(blob), int(max_ctas),
-                                 _cuda_stream(stream, blob.device)), "nerf_mlp_bwd_dw")
+    check(lib.nerf_mlp_bwd_dw(_byte_ptr(act, "act"), _byte_ptr(dz, "dz"), rows, ptr(blob),
+                              _cuda_stream(stream, blob.device)), "nerf_mlp_bwd_dw")
     return blob
 
 

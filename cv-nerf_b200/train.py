@@ -189,42 +189,11 @@ class TrainStep:
                 (1, self.fine, graw_f.view(rows_f, 4), self.act_f, rows_f, self.s_f, self.dz))
         # NERF_B200_BWD_SCHED (A/B timing, tools/time_bwd_schedules.py): 0 everything on one stream,
         # 1 small kernels beside dW, 2 (default) as described above.  On a power-capped B200 the three
-        # are within run-to-run noise of each other (5.75-6.1 ms per step).
+        # are within run-to-run noise of each other.  (Round 2 also tried running the two networks' dZ / dW
+        # kernels side by side on disjoint SM sets -- write-bound beside read-bound: 5.05-5.58 ms against
+        # 5.03-5.09 ms for this schedule, profiles/r02_bwd_schedules.txt -- and dropped it.)
         sched = int(os.environ.get("NERF_B200_BWD_SCHED", "2"))
-        if sched in (3, 4):
-            # The tensor-core gradient kernels are HBM-bound in opposite directions (dZ chain: writes, dW:
-            # reads) and run one persistent CTA per SM, so two of them can share the GPU on disjoint SM
-            # sets.  3: the coarse network's dW runs on `split` SMs beside the fine network's dZ chain.
-            # 4: the two networks' whole chains (dZ -> dW) run side by side, the coarse one on `split` SMs.
-            split = int(os.environ.get("NERF_B200_BWD_SPLIT", "40"))
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            second = self.side2
-            for idx, net, graw, act, rows, s, dz in jobs:
-                K.mlp_bwd_heads(act, graw, rows, self.blob[idx], stream=side)
-            (ic, netc, grc, actc, rowsc, sc, dzc), (i_f, netf, grf, actf, rowsf, sf, dzf) = jobs
-            pk_bc, pk_bf = netc.packed_bwd(), netf.packed_bwd()
-            if sched == 3:
-                K.mlp_bwd_dz(pk_bc, grc, actc, rowsc, dz=dzc)
-                second.wait_stream(main)
-                side.wait_stream(main)
-                K.viewdir_term_bwd(dzc, rowsc, rays, sc, False, self.blob[ic], stream=side)
-                K.mlp_bwd_dw(actc, dzc, rowsc, self.blob[ic], stream=second, max_ctas=split)
-                K.mlp_bwd_dz(pk_bf, grf, actf, rowsf, dz=dzf, max_ctas=sms - split)
-                side.wait_stream(main)
-                K.viewdir_term_bwd(dzf, rowsf, rays, sf, False, self.blob[i_f], stream=side)
-                main.wait_stream(second)
-                K.mlp_bwd_dw(actf, dzf, rowsf, self.blob[i_f])
-            else:
-                second.wait_stream(main)
-                K.mlp_bwd_dz(pk_bc, grc, actc, rowsc, dz=dzc, stream=second, max_ctas=split)
-                K.mlp_bwd_dw(actc, dzc, rowsc, self.blob[ic], stream=second, max_ctas=split)
-                K.mlp_bwd_dz(pk_bf, grf, actf, rowsf, dz=dzf, max_ctas=sms - split)
-                K.mlp_bwd_dw(actf, dzf, rowsf, self.blob[i_f], max_ctas=sms - split)
-                main.wait_stream(second)
-                side.wait_stream(main)
-                K.viewdir_term_bwd(dzc, rowsc, rays, sc, False, self.blob[ic], stream=side)
-                K.viewdir_term_bwd(dzf, rowsf, rays, sf, False, self.blob[i_f], stream=side)
-        elif sched == 2:
+        if sched == 2:
             for idx, net, graw, act, rows, s, dz in jobs:
                 K.mlp_bwd_heads(act, graw, rows, self.blob[idx], stream=side)
             for idx, net, graw, act, rows, s, dz in jobs:

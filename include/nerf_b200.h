@@ -230,14 +230,6 @@ size_t nerf_grad_blob_bytes(void);
 int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, float* grad_blob, void* stream);
 int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, long M, float* grad_blob,
                        void* stream);
-/* nerf_mlp_bwd_dz / nerf_mlp_bwd_dw on at most max_ctas SMs (0 = all; the kernels run one persistent
- * CTA per SM), so that two of them can share the GPU: the training step runs the HBM-write-bound dZ
- * chain of one network beside the HBM-read-bound dW contraction of the other. */
-int nerf_mlp_bwd_dz_ex(const void* packed_bwd, const float* grad_raw, const void* act_save, long M,
-                       void* dz_out, int max_ctas, void* stream);
-int nerf_mlp_bwd_dw_ex(const void* act_save, const void* dz, long M, float* grad_blob, int max_ctas,
-                       void* stream);
-
 /* l9 is folded into l10 in the forward pass and in the dZ chain (feat = l9(h8) feeds l10 without an
  * activation, model.py:100-104; csrc/mlp_layout.h), so nerf_mlp_bwd_dw leaves G = dZ10^T . h8 in the
  * blob's scratch region instead of the gradients of l9 and of l10's first 256 columns.  This call forms

@@ -22,7 +22,7 @@ ts = TrainStep(coarse, fine, height=400, width=400, focal=555.5555, n_rays=n, pe
                ndc=False, near=2., far=6., seed=1)
 image = torch.rand(400, 400, 3, device=dev)
 pose = pose_spherical(-180., -30., 4.)[:3, :4].to(dev)
-configs = [(0, 0), (2, 0), (3, 30), (3, 40), (3, 50), (4, 30), (4, 40), (4, 50)]
+configs = [(0, 0), (1, 0), (2, 0)]
 for rnd in range(2):
     for sched, split in configs:
         os.environ["NERF_B200_BWD_SCHED"] = str(sched)

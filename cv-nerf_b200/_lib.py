@@ -91,6 +91,16 @@ _SIGNATURES = {
     "nerf_mlp_bwd_heads": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_long, c_float_p, ctypes.c_void_p]),
     "nerf_viewdir_term_bwd": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_long,
                                              ctypes.c_int, c_float_p, ctypes.c_void_p]),
+    "nerf_mlp_bwd_dw_det_scratch_bytes": (ctypes.c_size_t, []),
+    "nerf_bwd_det_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_long]),
+    "nerf_mlp_bwd_dw_det": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, c_float_p, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
+    "nerf_mlp_bwd_heads_det": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_long, c_float_p, ctypes.c_void_p,
+                                              ctypes.c_void_p]),
+    "nerf_viewdir_term_bwd_det": (ctypes.c_int, [ctypes.c_void_p, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                                                 ctypes.c_int, c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "nerf_mse_loss_grad_det": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_long, c_float_p, c_float_p, ctypes.c_void_p,
+                                              ctypes.c_void_p]),
     "nerf_mlp_bwd_unfold": (ctypes.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, ctypes.c_void_p]),
     "nerf_grad_unpack": (ctypes.c_int, [c_float_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]),
     "nerf_mse_loss_grad": (ctypes.c_int, [c_float_p, c_float_p, ctypes.c_long, c_float_p, c_float_p,

@@ -56,7 +56,11 @@ struct DwParams {
     const uint8_t* dz;
     float* grad;
     long n_tiles;
+    float* partial;      // deterministic mode: per-CTA partial sums [grid][kPartFloats] instead of atomics into grad
 };
+
+// one CTA's partial result in deterministic mode: dW rows [256][256] (job-local row-major, pitch 256) + db [256]
+constexpr int kPartFloats = 256 * 256 + 256;
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dw_kernel(const __grid_constant__ DwParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -179,8 +183,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dw_kernel(const __grid_co
                 }
             }
             if (t_end > t_begin) {
-                atomicAdd(P.grad + J.bias_off + f, s0);
-                atomicAdd(P.grad + J.bias_off + f + 1, s1);
+                if (P.partial) {
+                    float* pb = P.partial + (size_t)blockIdx.x * kPartFloats + 256 * 256;
+                    pb[f] = s0;
+                    pb[f + 1] = s1;
+                } else {
+                    atomicAdd(P.grad + J.bias_off + f, s0);
+                    atomicAdd(P.grad + J.bias_off + f + 1, s1);
+                }
             }
         }
         // ===================== drain: accumulators -> gradient blob =====================
@@ -197,15 +207,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dw_kernel(const __grid_co
             const int c_end = m_blocks == 2 ? n_cols : c_begin + n_cols / 2;
             const int out_row = mb * 128 + quad * 32 + lane;
             float* dst = P.grad + J.out_off + (size_t)out_row * J.out_pitch;
+            float* dst_det = P.partial ? P.partial + (size_t)blockIdx.x * kPartFloats + (size_t)out_row * 256 : nullptr;
             const uint32_t tacc = tmem_base + ((uint32_t)(quad * 32) << 16) + mb * 256;
             for (int c = c_begin; c < c_end; c += 16) {
                 uint32_t v[16];
                 umma::tmem_ld16(tacc + c, v);
                 umma::tmem_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    umma::red_add_v4(dst + c + q * 4, __uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
-                                     __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                for (int q = 0; q < 4; ++q) {
+                    if (dst_det)
+                        *reinterpret_cast<float4*>(dst_det + c + q * 4) =
+                            make_float4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
+                                        __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                    else
+                        umma::red_add_v4(dst + c + q * 4, __uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]),
+                                         __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                }
             }
         }
     }
@@ -217,6 +234,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dw_kernel(const __grid_co
     }
 }
 
+// Deterministic mode, second launch: every blob element adds its CTAs' partial sums in CTA order.
+__global__ void __launch_bounds__(256) dw_reduce_kernel(const __grid_constant__ DwParams P) {
+    const LayerJob& J = P.jobs[blockIdx.y];
+    const int rows = J.a_blocks * 64, cols = J.b_blocks * 64;
+    const int n_w = rows * cols, n_items = n_w + (J.bias_off >= 0 ? rows : 0);
+    for (int item = blockIdx.x * 256 + threadIdx.x; item < n_items; item += gridDim.x * 256) {
+        const bool is_w = item < n_w;
+        const int r = is_w ? item / cols : item - n_w, c = is_w ? item % cols : 0;
+        const size_t local = is_w ? (size_t)r * 256 + c : (size_t)256 * 256 + r;
+        float sum = 0.f;
+        for (int part = 0; part < J.parts; ++part) {
+            if (P.n_tiles * (part + 1) / J.parts <= P.n_tiles * part / J.parts) continue;     // this CTA had no tiles
+            sum += P.partial[(size_t)(J.first_cta + part) * kPartFloats + local];
+        }
+        float* dst = is_w ? P.grad + J.out_off + (size_t)r * J.out_pitch + c : P.grad + J.bias_off + r;
+        *dst += sum;
+    }
+}
+
 // bytes one tile of layer job k moves (balances the split of the grid)
 int job_weight(const LayerJob& j) { return (j.a_blocks + j.b_blocks) * 16; }
 
@@ -225,7 +261,26 @@ int job_weight(const LayerJob& j) { return (j.a_blocks + j.b_blocks) * 16; }
 extern "C" size_t nerf_grad_blob_bytes(void) { return (size_t)nerf::kGradFloats * 4; }
 
 // dW / db of l1..l10 (tensor-core layers) accumulated into grad_blob (+=).
+static int launch_dw(const void* act_save, const void* dz, long M, float* grad_blob, float* partial, void* stream);
+
 extern "C" int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, float* grad_blob, void* stream) {
+    return launch_dw(act_save, dz, M, grad_blob, nullptr, stream);
+}
+
+// Deterministic accumulation: per-CTA partial sums into `scratch`, then an ordered reduction (second launch).
+extern "C" int nerf_mlp_bwd_dw_det(const void* act_save, const void* dz, long M, float* grad_blob, void* scratch,
+                                   void* stream) {
+    if (!scratch) return nerf::arg_error("nerf_mlp_bwd_dw_det: scratch");
+    return launch_dw(act_save, dz, M, grad_blob, (float*)scratch, stream);
+}
+
+extern "C" size_t nerf_mlp_bwd_dw_det_scratch_bytes(void) {
+    int sms = nerf_b200_sm_count();
+    if (sms <= 0) sms = 148;
+    return (size_t)sms * kPartFloats * 4;
+}
+
+static int launch_dw(const void* act_save, const void* dz, long M, float* grad_blob, float* partial, void* stream) {
     nerf::DeviceGuard device_guard(grad_blob);
     if (M < 0 || (M > 0 && (!act_save || !dz || !grad_blob))) return nerf::arg_error("nerf_mlp_bwd_dw");
     if (M == 0) return 0;
@@ -248,7 +303,7 @@ extern "C" int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, flo
         configured = true;
     }
     DwParams P;
-    P.act = (const uint8_t*)act_save; P.dz = (const uint8_t*)dz; P.grad = grad_blob;
+    P.act = (const uint8_t*)act_save; P.dz = (const uint8_t*)dz; P.grad = grad_blob; P.partial = partial;
     P.n_tiles = (M + kTileRows - 1) / kTileRows;
     // layer table: l1, l2..l5, l6 (PE columns), l6 (h5 columns), l7, l8, and the folded l10': G = dZ10^T . h8
     // into the scratch region of the blob (nerf_mlp_bwd_unfold turns it into the gradients of l9 and l10)
@@ -285,5 +340,6 @@ extern "C" int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, flo
         first += P.jobs[i].parts;
     }
     mlp_bwd_dw_kernel<<<(unsigned)first, kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    if (partial) dw_reduce_kernel<<<dim3(64, kNumJobsLayers), 256, 0, (cudaStream_t)stream>>>(P);
     return nerf::check_launch("nerf_mlp_bwd_dw");
 }

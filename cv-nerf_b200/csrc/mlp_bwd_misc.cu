@@ -44,10 +44,16 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
 // <= 80 registers, 10 KB shared memory) fits on an SM BESIDE the persistent dZ-chain CTA, which leaves
 // 10 K registers and ~30 KB: the training step launches it on a side stream under that tensor-bound
 // kernel instead of next to the HBM-bound dW kernel.
+constexpr int kHeadItems = 256 + 3 * 128 + 4;     // dW_alpha [256], dW11 [3][128], db11 [3], db_alpha
+__device__ __forceinline__ int head_item_offset(int i) {
+    return i < 256 ? kG_WAlpha + i : i < 256 + 384 ? kG_W11 + (i - 256) : (i - 640 < 3 ? kG_B11 + (i - 640) : kG_BAlpha);
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) heads_bwd_kernel(const uint8_t* __restrict__ act,
                                                                const float* __restrict__ grad_raw, long M,
-                                                               long n_tiles, float* __restrict__ grad) {
+                                                               long n_tiles, float* __restrict__ grad,
+                                                               float* __restrict__ partial) {
     __shared__ float red[WARPS][256 + 3 * 128 + 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float a8[8], r0[8], r1[8], r2[8], gb[4] = {0.f, 0.f, 0.f, 0.f};
@@ -108,11 +114,18 @@ __global__ void __launch_bounds__(WARPS * 32) heads_bwd_kernel(const uint8_t* __
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) s += red[w][i];
-        float* dst = i < 256 ? grad + kG_WAlpha + i
-                   : i < 256 + 384 ? grad + kG_W11 + (i - 256)
-                   : (i - 640 < 3 ? grad + kG_B11 + (i - 640) : grad + kG_BAlpha);
-        atomicAdd(dst, s);
+        if (partial) { partial[(size_t)blockIdx.x * kHeadItems + i] = s; continue; }     // deterministic mode
+        atomicAdd(grad + head_item_offset(i), s);
     }
+}
+
+// Deterministic mode, second launches: blob element += its blocks' partial sums in block order.
+__global__ void heads_reduce_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kHeadItems) return;
+    float s = 0.f;
+    for (int b = 0; b < n_blocks; ++b) s += partial[(size_t)b * kHeadItems + i];
+    grad[head_item_offset(i)] += s;
 }
 
 // ------------------------------------------------------------------ l10 view columns / bias
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(WARPS * 32) heads_bwd_kernel(const uint8_t* __
 __global__ void __launch_bounds__(128) viewdir_term_bwd_kernel(const uint8_t* __restrict__ dz,
                                                                const float* __restrict__ dirs, int dir_stride,
                                                                int embedded, long M, int div, long count,
-                                                               float* __restrict__ grad) {
+                                                               float* __restrict__ grad, float* __restrict__ partial) {
     __shared__ float pe[8][28];
     __shared__ float part[8][128];
     const int j = threadIdx.x;
@@ -179,9 +192,25 @@ __global__ void __launch_bounds__(128) viewdir_term_bwd_kernel(const uint8_t* __
             accb += dv;
         }
     }
+    if (partial) {                          // deterministic mode: [block][128][28] = 27 view columns + bias
+        float* pp = partial + ((size_t)blockIdx.x * 128 + j) * 28;
+#pragma unroll
+        for (int e = 0; e < kViewPeDim; ++e) pp[e] = acc[e];
+        pp[kViewPeDim] = accb;
+        return;
+    }
 #pragma unroll
     for (int e = 0; e < kViewPeDim; ++e) atomicAdd(grad + kG_W10 + j * 288 + 256 + e, acc[e]);
     atomicAdd(grad + kG_B10 + j, accb);
+}
+
+__global__ void view_reduce_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * 28) return;
+    const int j = i / 28, e = i % 28;
+    float s = 0.f;
+    for (int b = 0; b < n_blocks; ++b) s += partial[(size_t)b * 128 * 28 + i];
+    grad[e < kViewPeDim ? kG_W10 + j * 288 + 256 + e : kG_B10 + j] += s;
 }
 
 // ------------------------------------------------------------------ unfold (l9 folded into l10)
@@ -263,7 +292,7 @@ __global__ void grad_unpack_kernel(const float* __restrict__ blob, UnpackPtrs ou
 __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restrict__ x,
                                                             const float* __restrict__ target, long n,
                                                             float inv_n, float* __restrict__ grad,
-                                                            float* __restrict__ loss) {
+                                                            float* __restrict__ loss, float* __restrict__ partial) {
     __shared__ float part[8];
     float acc = 0.f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -278,39 +307,96 @@ __global__ void __launch_bounds__(256) mse_loss_grad_kernel(const float* __restr
     if (threadIdx.x == 0 && loss) {
         float s = 0.f;
         for (int w = 0; w < 8; ++w) s += part[w];
-        atomicAdd(loss, s * inv_n);
+        if (partial) partial[blockIdx.x] = s * inv_n;      // deterministic mode
+        else atomicAdd(loss, s * inv_n);
     }
+}
+
+__global__ void loss_reduce_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ loss) {
+    float s = 0.f;
+    for (int b = 0; b < n_blocks; ++b) s += partial[b];
+    *loss += s;
 }
 
 }  // namespace
 
-extern "C" int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, long M, float* grad_blob,
-                                  void* stream) {
+static long heads_grid(long n_tiles) {
+    int sms = nerf_b200_sm_count();
+    if (sms <= 0) sms = 148;
+    return n_tiles < 6L * sms ? n_tiles : 6L * sms;
+}
+
+static long view_grid(long count) {
+    int sms = nerf_b200_sm_count();
+    if (sms <= 0) sms = 148;
+    const long groups = (count + 7) / 8;
+    return groups < 8L * sms ? groups : 8L * sms;
+}
+
+static long loss_grid(long n) {
+    const long grid = (n + 255) / 256;
+    return grid > 1024 ? 1024 : grid;
+}
+
+static int launch_heads(const void* act_save, const float* grad_raw, long M, float* grad_blob, float* partial, void* stream) {
     nerf::DeviceGuard device_guard(grad_blob);
     if (M < 0 || (M > 0 && (!act_save || !grad_raw || !grad_blob))) return nerf::arg_error("nerf_mlp_bwd_heads");
     if (M == 0) return 0;
     const long n_tiles = (M + kTileRows - 1) / kTileRows;
-    int sms = nerf_b200_sm_count();
-    if (sms <= 0) sms = 148;
-    const long grid = n_tiles < 6L * sms ? n_tiles : 6L * sms;
+    const long grid = heads_grid(n_tiles);
     heads_bwd_kernel<4><<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)act_save, grad_raw, M, n_tiles,
-                                                                         grad_blob);
+                                                                         grad_blob, partial);
+    if (partial) heads_reduce_kernel<<<(kHeadItems + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, (int)grid, grad_blob);
     return nerf::check_launch("nerf_mlp_bwd_heads");
 }
 
-extern "C" int nerf_viewdir_term_bwd(const void* dz, const float* dirs, int dir_stride, int embedded, long M,
-                                     int vterm_div, float* grad_blob, void* stream) {
+static int launch_view(const void* dz, const float* dirs, int dir_stride, int embedded, long M, int vterm_div,
+                       float* grad_blob, float* partial, void* stream) {
     nerf::DeviceGuard device_guard(grad_blob);
     if (M < 0 || vterm_div < 1 || (M > 0 && (!dz || !dirs || !grad_blob))) return nerf::arg_error("nerf_viewdir_term_bwd");
     if (M == 0) return 0;
     const long count = (M + vterm_div - 1) / vterm_div;
-    int sms = nerf_b200_sm_count();
-    if (sms <= 0) sms = 148;
-    const long groups = (count + 7) / 8;
-    const long grid = groups < 8L * sms ? groups : 8L * sms;
+    const long grid = view_grid(count);
     viewdir_term_bwd_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>((const uint8_t*)dz, dirs, dir_stride,
-                                                                             embedded, M, vterm_div, count, grad_blob);
+                                                                             embedded, M, vterm_div, count, grad_blob, partial);
+    if (partial) view_reduce_kernel<<<(128 * 28 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, (int)grid, grad_blob);
     return nerf::check_launch("nerf_viewdir_term_bwd");
+}
+
+extern "C" int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, long M, float* grad_blob,
+                                  void* stream) {
+    return launch_heads(act_save, grad_raw, M, grad_blob, nullptr, stream);
+}
+
+extern "C" int nerf_viewdir_term_bwd(const void* dz, const float* dirs, int dir_stride, int embedded, long M,
+                                     int vterm_div, float* grad_blob, void* stream) {
+    return launch_view(dz, dirs, dir_stride, embedded, M, vterm_div, grad_blob, nullptr, stream);
+}
+
+// ---- deterministic accumulation (parity / debugging runs) ---------------------------------------------
+// The kernels above add per-block sums to the blob with floating-point atomics, so two runs differ in the
+// last bits of a gradient.  The _det variants write the per-block partial sums to `scratch` and a second
+// launch adds them to the blob in block order: bitwise reproducible on a given GPU model.
+// nerf_bwd_det_scratch_bytes(kind, size): kind 1 heads (size = M), 2 view columns (size = rays), 3 loss
+// (size = n); the dW kernel has nerf_mlp_bwd_dw_det_scratch_bytes().
+extern "C" size_t nerf_bwd_det_scratch_bytes(int kind, long size) {
+    if (size <= 0) return 0;
+    if (kind == 1) return (size_t)heads_grid((size + kTileRows - 1) / kTileRows) * kHeadItems * 4;
+    if (kind == 2) return (size_t)view_grid(size) * 128 * 28 * 4;
+    if (kind == 3) return (size_t)loss_grid(size) * 4;
+    return 0;
+}
+
+extern "C" int nerf_mlp_bwd_heads_det(const void* act_save, const float* grad_raw, long M, float* grad_blob,
+                                      void* scratch, void* stream) {
+    if (!scratch) return nerf::arg_error("nerf_mlp_bwd_heads_det: scratch");
+    return launch_heads(act_save, grad_raw, M, grad_blob, (float*)scratch, stream);
+}
+
+extern "C" int nerf_viewdir_term_bwd_det(const void* dz, const float* dirs, int dir_stride, int embedded, long M,
+                                         int vterm_div, float* grad_blob, void* scratch, void* stream) {
+    if (!scratch) return nerf::arg_error("nerf_viewdir_term_bwd_det: scratch");
+    return launch_view(dz, dirs, dir_stride, embedded, M, vterm_div, grad_blob, (float*)scratch, stream);
 }
 
 extern "C" int nerf_mlp_bwd_unfold(float* grad_blob, const float* l9_weight, const float* l9_bias,
@@ -334,14 +420,25 @@ extern "C" int nerf_grad_unpack(const float* grad_blob, float* const* host_grads
     return nerf::check_launch("nerf_grad_unpack");
 }
 
-extern "C" int nerf_mse_loss_grad(const float* x, const float* target, long n, float* grad_out, float* loss_accum,
-                                  void* stream) {
+static int launch_loss(const float* x, const float* target, long n, float* grad_out, float* loss_accum, float* partial,
+                       void* stream) {
     nerf::DeviceGuard device_guard(loss_accum);
     if (n < 0 || (n > 0 && (!x || !target))) return nerf::arg_error("nerf_mse_loss_grad");
     if (n == 0) return 0;
-    long grid = (n + 255) / 256;
-    if (grid > 1024) grid = 1024;
+    const long grid = loss_grid(n);
     mse_loss_grad_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, target, n, 1.f / (float)n, grad_out,
-                                                                          loss_accum);
+                                                                          loss_accum, partial);
+    if (partial && loss_accum) loss_reduce_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(partial, (int)grid, loss_accum);
     return nerf::check_launch("nerf_mse_loss_grad");
+}
+
+extern "C" int nerf_mse_loss_grad(const float* x, const float* target, long n, float* grad_out, float* loss_accum,
+                                  void* stream) {
+    return launch_loss(x, target, n, grad_out, loss_accum, nullptr, stream);
+}
+
+extern "C" int nerf_mse_loss_grad_det(const float* x, const float* target, long n, float* grad_out, float* loss_accum,
+                                      void* scratch, void* stream) {
+    if (!scratch) return nerf::arg_error("nerf_mse_loss_grad_det: scratch");
+    return launch_loss(x, target, n, grad_out, loss_accum, (float*)scratch, stream);
 }

@@ -6,6 +6,7 @@ file computes anything on the host.
 """
 import ctypes
 import dataclasses
+import os
 
 import numpy as np
 import torch
@@ -16,6 +17,29 @@ from ._lib import f32c, ptr, stream_of
 RAY_STRIDE = 11
 IN_RAYS, IN_POINTS, IN_EMBEDDED = 0, 1, 2
 FLOP_PER_SAMPLE = 2 * 593408   # unpadded MACs of one Model.forward row
+
+
+# Deterministic accumulation (parity / debugging runs): the gradient kernels then write per-CTA partial sums
+# and add them in CTA order instead of using floating-point atomics -- two runs give bit-identical gradients
+# (the reference's CPU autograd is reproducible; the default here is not, by ~1e-7 relative per element).
+# Set with set_deterministic() or NERF_B200_DETERMINISTIC=1; costs a second small launch per kernel.
+DETERMINISTIC = os.environ.get("NERF_B200_DETERMINISTIC", "0") == "1"
+_DET_SCRATCH = {}
+
+
+def set_deterministic(on=True):
+    """Switch the gradient kernels to ordered accumulation; returns the previous setting."""
+    global DETERMINISTIC
+    old, DETERMINISTIC = DETERMINISTIC, bool(on)
+    return old
+
+
+def _det_scratch(kind, nbytes, dev):
+    key = (kind, dev)
+    buf = _DET_SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _DET_SCRATCH[key] = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+    return buf
 
 
 class LaunchStats:
@@ -450,6 +474,11 @@ def mlp_bwd_heads(act, grad_raw, rows, blob, stream=None):
     it can run as soon as the compositing backward is done)."""
     lib = _lib.load()
     grad_raw = f32c(grad_raw)
+    if DETERMINISTIC:
+        scratch = _det_scratch(1, lib.nerf_bwd_det_scratch_bytes(1, rows), blob.device)
+        check(lib.nerf_mlp_bwd_heads_det(_byte_ptr(act, "act"), ptr(grad_raw), rows, ptr(blob), scratch.data_ptr(),
+                                         _cuda_stream(stream, blob.device)), "nerf_mlp_bwd_heads_det", launches=2)
+        return blob
     check(lib.nerf_mlp_bwd_heads(_byte_ptr(act, "act"), ptr(grad_raw), rows, ptr(blob), _cuda_stream(stream, blob.device)),
           "nerf_mlp_bwd_heads")
     return blob
@@ -458,6 +487,11 @@ def mlp_bwd_heads(act, grad_raw, rows, blob, stream=None):
 def mlp_bwd_dw(act, dz, rows, blob, stream=None):
     """dW/db of the tensor-core layers into the gradient blob (l9/l10: G = dZ10^T h8 into its scratch region)."""
     lib = _lib.load()
+    if DETERMINISTIC:
+        scratch = _det_scratch(0, lib.nerf_mlp_bwd_dw_det_scratch_bytes(), blob.device)
+        check(lib.nerf_mlp_bwd_dw_det(_byte_ptr(act, "act"), _byte_ptr(dz, "dz"), rows, ptr(blob), scratch.data_ptr(),
+                                      _cuda_stream(stream, blob.device)), "nerf_mlp_bwd_dw_det", launches=2)
+        return blob
     check(lib.nerf_mlp_bwd_dw(_byte_ptr(act, "act"), _byte_ptr(dz, "dz"), rows, ptr(blob),
                               _cuda_stream(stream, blob.device)), "nerf_mlp_bwd_dw")
     return blob
@@ -471,6 +505,13 @@ def viewdir_term_bwd(dz, rows, dirs, vterm_div, embedded, blob, stream=None):
     else:
         dirs = f32c(dirs)
         dptr, stride = dirs.data_ptr(), dirs.shape[-1]
+    if DETERMINISTIC:
+        count = (rows + vterm_div - 1) // vterm_div
+        scratch = _det_scratch(2, lib.nerf_bwd_det_scratch_bytes(2, count), blob.device)
+        check(lib.nerf_viewdir_term_bwd_det(_byte_ptr(dz, "dz"), dptr, stride, int(embedded), rows, vterm_div, ptr(blob),
+                                            scratch.data_ptr(), _cuda_stream(stream, blob.device)),
+              "nerf_viewdir_term_bwd_det", launches=2)
+        return blob
     check(lib.nerf_viewdir_term_bwd(_byte_ptr(dz, "dz"), dptr, stride, int(embedded), rows, vterm_div, ptr(blob),
                                     _cuda_stream(stream, blob.device)), "nerf_viewdir_term_bwd")
     return blob
@@ -528,6 +569,11 @@ def mse_loss_grad(x, target, want_grad=True, loss=None):
     if loss is None:
         loss = torch.zeros(1, dtype=torch.float32, device=x.device)
     grad = torch.empty_like(x) if want_grad else None
+    if DETERMINISTIC:
+        scratch = _det_scratch(3, lib.nerf_bwd_det_scratch_bytes(3, x.numel()), x.device)
+        check(lib.nerf_mse_loss_grad_det(ptr(x), ptr(target), x.numel(), ptr(grad), ptr(loss), scratch.data_ptr(),
+                                         stream_of(x)), "nerf_mse_loss_grad_det", launches=2)
+        return loss, grad
     check(lib.nerf_mse_loss_grad(ptr(x), ptr(target), x.numel(), ptr(grad), ptr(loss), stream_of(x)),
           "nerf_mse_loss_grad")
     return loss, grad

@@ -230,6 +230,24 @@ size_t nerf_grad_blob_bytes(void);
 int nerf_mlp_bwd_dw(const void* act_save, const void* dz, long M, float* grad_blob, void* stream);
 int nerf_mlp_bwd_heads(const void* act_save, const float* grad_raw, long M, float* grad_blob,
                        void* stream);
+/* Deterministic accumulation (parity / debugging runs).  nerf_mlp_bwd_dw, nerf_mlp_bwd_heads,
+ * nerf_viewdir_term_bwd and nerf_mse_loss_grad add per-CTA sums with floating-point atomics, so two runs
+ * differ in the last bits of a gradient (the reference's CPU autograd is bitwise reproducible).  The _det
+ * variants write the per-CTA partial sums to `scratch` and add them in CTA order with a second launch:
+ * bitwise reproducible on a given GPU model.  Scratch sizes: nerf_mlp_bwd_dw_det_scratch_bytes();
+ * nerf_bwd_det_scratch_bytes(kind, size) with kind 1 = heads (size = M), 2 = view columns (size = number
+ * of rays), 3 = loss (size = n). */
+size_t nerf_mlp_bwd_dw_det_scratch_bytes(void);
+size_t nerf_bwd_det_scratch_bytes(int kind, long size);
+int nerf_mlp_bwd_dw_det(const void* act_save, const void* dz, long M, float* grad_blob, void* scratch,
+                        void* stream);
+int nerf_mlp_bwd_heads_det(const void* act_save, const float* grad_raw, long M, float* grad_blob,
+                           void* scratch, void* stream);
+int nerf_viewdir_term_bwd_det(const void* dz, const float* dirs, int dir_stride, int embedded, long M,
+                              int vterm_div, float* grad_blob, void* scratch, void* stream);
+int nerf_mse_loss_grad_det(const float* x, const float* target, long n, float* grad_out,
+                           float* loss_accum, void* scratch, void* stream);
+
 /* l9 is folded into l10 in the forward pass and in the dZ chain (feat = l9(h8) feeds l10 without an
  * activation, model.py:100-104; csrc/mlp_layout.h), so nerf_mlp_bwd_dw leaves G = dZ10^T . h8 in the
  * blob's scratch region instead of the gradients of l9 and of l10's first 256 columns.  This call forms

@@ -310,6 +310,10 @@ def run_ours(args):
                      "traffic_source": "ncu --set full capture of round 1 (profiles/r01_fwd_variants_ncu.txt: dram__bytes_read.sum "
                                        "+ dram__bytes_write.sum = 20.4 B per row) x rows per launch of this run; not re-measured here",
                      "kernel": "mlp_fwd_kernel",
+                     # `achieved` counts the REFERENCE's multiply-adds (593 408 per sample).  The kernel
+                     # executes fewer: l9 has no activation and is folded into l10 (csrc/mlp_layout.h), 527 872 per sample
+                     "executed_tflops": achieved * EXECUTED_MAC_PER_SAMPLE / 593408.,
+                     "executed_frac_of_peak": achieved * EXECUTED_MAC_PER_SAMPLE / 593408. / peak,
                      "peak_kind": f"{peak_kind} bf16_tflops_sustained",
                      "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
                      "kernel_share_of_step": kern_ms / total_ms,
@@ -327,6 +331,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+EXECUTED_MAC_PER_SAMPLE = 593408 - 65536 - 32768 + 32768     # l9 (256x256) folded into l10[:, :256] (128x256)
 NCU_DRAM_BYTES_PER_ROW = (135.264e6 + 255.746e6) / 19.2e6     # profiles/r01_fwd_variants_ncu.txt
 TRAIN_FLOP_PER_RAY = (N_COARSE + N_COARSE + N_FINE) * 2 * (593408 + 593408 + 557696)
 
@@ -374,6 +379,20 @@ def bench_train_step(args, dev, world, rank):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = ms.item() / steps
+    # where the data-parallel step spends its time: forward+backward vs gradient exchange + Adam + re-pack
+    # (CUDA events inside TrainStep.step over 10 more steps, max over ranks; not part of the timed region)
+    ts.profile = []
+    for i in range(10):
+        one(warmup + steps + i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    halves = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in ts.profile) / len(ts.profile),
+                           sum(e[1].elapsed_time(e[2]) for e in ts.profile) / len(ts.profile)], device=dev)
+    ts.profile = None
+    if world > 1:
+        dist.all_reduce(halves, op=dist.ReduceOp.MAX)
+    fwd_bwd_ms, update_ms = (float(v) for v in halves.tolist())
     # per-kernel split of one more step (events around each stage; not part of the timed region)
     stages = {}
     if rank == 0:
@@ -399,6 +418,7 @@ def bench_train_step(args, dev, world, rank):
             "steps": steps, "warmup": warmup, "tflops_per_gpu": tflops,
             "frac_of_sustained_bf16_peak": tflops / float(peaks["bf16_tflops_sustained"]),
             "gpu_launches_per_step": launches / steps, "loss_last": float(loss.item()),
+            "forward_backward_ms": fwd_bwd_ms, "exchange_adam_repack_ms": update_ms,
             "grad_exchange_bytes_per_rank": int(ts.blob.numel() * 4) if world > 1 else 0,
             "grad_exchange": ("none" if world == 1 else
                               "fused into Adam: peer loads over NVLink from symmetric memory" if ts.symm is not None

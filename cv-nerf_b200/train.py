@@ -125,6 +125,7 @@ class TrainStep:
         self.v = [[torch.zeros_like(p) for p in ps] for ps in self.params]
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.side = torch.cuda.Stream(device=dev)      # small gradient kernels next to the dW kernel
+        self.profile = None                            # a list collects (start, after backward, after update) events per step
         self.side2 = torch.cuda.Stream(device=dev)                    # second persistent-kernel stream (schedules 3, 4)
 
     def crop_window(self, precrop_frac=None):
@@ -248,8 +249,17 @@ class TrainStep:
         rays, target, _ = K.train_rays(self.h, self.w, self.f, pose, self.n_rays, pix=pix,
                                        seed=self.seed * 0x9E3779B97F4A7C15 + self.it, crop=self.crop_window(precrop_frac),
                                        image=image, ndc=self.ndc, near=self.near, far=self.far)
+        prof = self.profile
+        if prof is not None:        # bench.py: CUDA events around the two halves of the step (no synchronisation here)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         loss = self.forward_backward(rays, target, draws)
+        if prof is not None:
+            ev[1].record()
         self.apply_gradients()
+        if prof is not None:
+            ev[2].record()
+            prof.append(ev)
         return loss
 
     def gradients(self, idx):

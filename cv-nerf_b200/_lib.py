@@ -68,13 +68,13 @@ _SIGNATURES = {
                                         ctypes.c_void_p]),
     "nerf_mlp_fwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int,
                                     ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p,
-                                    ctypes.c_void_p, ctypes.c_void_p]),
+                                    ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]),
     "nerf_mlp_act_bytes": (ctypes.c_size_t, [ctypes.c_long]),
     "nerf_model_host_tail_bytes": (ctypes.c_size_t, []),
     "nerf_model_host_tail": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "nerf_mlp_fwd_host_tail": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p,
                                               ctypes.c_int, ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int,
-                                              c_float_p, ctypes.c_void_p]),
+                                              c_float_p, ctypes.c_long, ctypes.c_void_p]),
     "nerf_mlp_fwd_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_float_p, c_float_p, ctypes.c_int,
                                           ctypes.c_long, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p,
                                           ctypes.c_int, c_float_p, ctypes.c_void_p]),

@@ -52,7 +52,8 @@ constexpr uint32_t kOffPE = 2 * 65536;                // 2 x [128][64] bf16
 constexpr uint32_t kOffW = kOffPE + 2 * 16384;        // ring x 32 KB
 constexpr uint32_t kOffBar = kOffW + kRing * kSlotBytes;
 constexpr uint32_t kOffBias = kOffBar + 256;          // 2 x [256] fp32: the current layer's bias, per group
-constexpr uint32_t kSmemBytes = kOffBias + 2 * 1024;
+constexpr uint32_t kOffPlan = kOffBias + 2 * 1024;     // the weight-ring plan of this launch (RingPlan, 412 bytes)
+constexpr uint32_t kSmemBytes = kOffPlan + 416;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 constexpr uint32_t kIdescN256 = umma::instr_desc_bf16(128, 256);
 constexpr uint32_t kIdescN128 = umma::instr_desc_bf16(128, 128);
@@ -73,7 +74,6 @@ constexpr uint32_t kIdescN128 = umma::instr_desc_bf16(128, 128);
 template <int RING, bool ALIAS, int EXP = 0, bool PEA = false>
 struct Cfg {
     static constexpr int ring = RING;
-    static constexpr bool two_producers = (EXP & 512) != 0;     // EXP bit9
     static constexpr int exp = EXP;
     static constexpr bool pea = PEA;
     static constexpr uint32_t off_pe = ALIAS ? 0u : kOffPE;
@@ -111,6 +111,7 @@ struct FwdParams {
     int probe_layer;
     long long* stats_out;    // debug: [grid][8] cycle counters (or NULL)
     long long* trace_out;    // debug: [4 roles][1024] time-stamped events of CTA 0's 4th and 5th tile pair (or NULL)
+    int tile0;               // parity of the global index of this launch's first 128-row tile (chunk order, see chunk_at)
     uint8_t* act_save;       // training: activation records, kActTileBytes per 128-row tile (or NULL)
 };
 
@@ -495,6 +496,137 @@ __device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float*
     for (int k = 0; k < 3; ++k) rgb[k] = acc[k].x + acc[k].y;
 }
 
+// ---------------------------------------------------------------------------- weight ring plan
+// Order in which a sub-tile consumes the K chunks of layer l.  Tiles of even GLOBAL index (FwdParams::tile0
+// + local tile) run forward (0, 1, .., n-1), odd ones backward, so that the sub-tile issued second starts with
+// the chunk the first one finished with: the three slots of the ring still hold the first sub-tile's last
+// three chunks, and of the 8 chunk uses of a layer only 5 need a copy from L2 (43 instead of 68 per tile pair:
+// the kernel was bound by the refill chain of its three 32 KB slots, not by the tensor pipe).  l6 keeps its
+// PE chunk (0) last and the chunk that reads A block 0 (1) ahead of a later h5 chunk in both orders (PEA).
+// The summation order of a row therefore depends on the parity of its global 128-row tile; callers that shard
+// a batch at multiples of 128 rows and pass the shard's first row get bit-identical results.
+__host__ __device__ constexpr int chunk_at(int l, bool rev, int idx) {
+    if (l == 5) {
+        if (!rev) return idx == 4 ? 0 : idx + 1;                                   // 1 2 3 4 0
+        return idx == 0 ? 4 : idx == 1 ? 3 : idx == 2 ? 1 : idx == 3 ? 2 : 0;      // 4 3 1 2 0
+    }
+    return rev ? layer_chunks(l) - 1 - idx : idx;
+}
+
+// The first sub-tile keeps (does not release) its last RING chunks, provided the second sub-tile starts with one
+// of them (otherwise nothing is kept and the second sub-tile fetches everything: the plan can then never run
+// out of free slots).
+// Slot bookkeeping.  Fills take the free slots in the order they were released (a FIFO).  The plan is a pure
+// function of (ring depth, tile parity) and periodic over one to three tile pairs (the slots come back
+// permuted after a pair), so it is worked out at COMPILE time into a table of 16-bit entries in issue order,
+// one per (layer, sub-tile, chunk) = 68 per tile pair, copied to shared memory at kernel start.  The one
+// thread that issues tcgen05.mma then runs a flat loop over the entries, fetching the next one under the
+// current chunk's MMAs: whatever it executes or waits for between two chunks is tensor idle time (the same
+// bookkeeping done in that thread made the kernel 1.5x slower; nested loops with two wait sites, +20 %).
+//   bits 0-2  chunk (source of the copy)             bit 8   FIRST: first chunk of the sub-tile's layer
+//   bits 3-4  slot                                            (wait for the A operand, overwrite D)
+//   bit 5     first use of a fill (wait / copy)       bit 9   LAST: last chunk (commit the accumulator)
+//   bit 6     release the slot after use              bit 10  PE chunk of l6 (PEA: wait for the restored block)
+//   bit 7     sub-tile (issue order)                  bit 11  chunk that frees A block 0 in l6 (PEA: signal it)
+//   bits 12-13 A block read by the chunk              bit 14  N = 128 (l10)     bit 15  A operand is the PE tile
+constexpr int kPlanMaxPairs = 3;
+constexpr int kPlanPerPair = 68;
+struct RingPlan {
+    unsigned short e[kPlanMaxPairs * kPlanPerPair];
+    unsigned short period, pad;
+};
+struct RingPlans {
+    RingPlan p[3][2];      // [ring depth - 1][tile parity]
+};
+enum : unsigned {
+    kPlanFirstUse = 1u << 5, kPlanRelease = 1u << 6, kPlanG = 1u << 7, kPlanFirst = 1u << 8, kPlanLast = 1u << 9,
+    kPlanPeChunk = 1u << 10, kPlanFreesBlock0 = 1u << 11, kPlanN128 = 1u << 14, kPlanPeSrc = 1u << 15
+};
+
+constexpr RingPlan make_ring_plan(int ring, bool rev0, bool reuse = true, bool both_forward = false) {
+    RingPlan t{};
+    int fifo[8] = {0, 1, 2, 0, 0, 0, 0, 0};
+    int head = 0, count = ring;
+    int where[5] = {-1, -1, -1, -1, -1};
+    t.period = 0;
+    for (int pair = 0; pair < 6; ++pair) {
+        int q = 0;
+        for (int l = 0; l < kNumMmaLayers; ++l) {
+            const int n = layer_chunks(l);
+            int keep_from = n > ring ? n - ring : 0;
+            {
+                const int want = chunk_at(l, !rev0, 0);
+                bool found = false;
+                for (int idx = keep_from; idx < n; ++idx) found = found || chunk_at(l, rev0, idx) == want;
+                if (!found || !reuse) keep_from = n;
+            }
+            for (int g = 0; g < 2; ++g) {
+                for (int idx = 0; idx < n; ++idx, ++q) {
+                    const int c = chunk_at(l, both_forward ? false : (g == 0 ? rev0 : !rev0), idx);
+                    const bool first_use = where[c] < 0;
+                    if (first_use) {
+                        where[c] = fifo[head];
+                        head = (head + 1) & 7;
+                        --count;
+                    }
+                    const bool release = g == 1 || idx < keep_from;
+                    const int a_block = l == 0 ? 0 : (l == 5 ? (c == 0 ? 0 : c - 1) : c);
+                    unsigned e = (unsigned)c | ((unsigned)where[c] << 3) | (first_use ? kPlanFirstUse : 0u) |
+                                 (release ? kPlanRelease : 0u) | (g ? kPlanG : 0u) | (idx == 0 ? kPlanFirst : 0u) |
+                                 (idx == n - 1 ? kPlanLast : 0u) | ((l == 5 && c == 0) ? kPlanPeChunk : 0u) |
+                                 ((l == 5 && c == 1) ? kPlanFreesBlock0 : 0u) | ((unsigned)a_block << 12) |
+                                 (layer_halves(l) == 1 ? kPlanN128 : 0u) | ((l == 0 || (l == 5 && c == 0)) ? kPlanPeSrc : 0u);
+                    if (pair < kPlanMaxPairs) t.e[pair * kPlanPerPair + q] = (unsigned short)e;
+                    if (release) {
+                        fifo[(head + count) & 7] = where[c];
+                        ++count;
+                        where[c] = -1;
+                    }
+                }
+            }
+        }
+        // the plan repeats once the free slots are back in their initial order
+        bool initial = true;
+        for (int i = 0; i < ring; ++i) initial = initial && fifo[(head + i) & 7] == i;
+        if (initial && t.period == 0) t.period = (unsigned short)(pair + 1);
+    }
+    return t;
+}
+static_assert(2 * (1 + 7 * 4 + 5) == kPlanPerPair, "entries per tile pair");
+
+constexpr RingPlans make_ring_plans() {
+    RingPlans r{};
+    for (int ring = 1; ring <= 3; ++ring)
+        for (int par = 0; par < 2; ++par) r.p[ring - 1][par] = make_ring_plan(ring, par != 0);
+    return r;
+}
+constexpr bool ring_plans_ok(const RingPlans& r) {
+    for (int ring = 0; ring < 3; ++ring)
+        for (int par = 0; par < 2; ++par)
+            if (r.p[ring][par].period < 1 || r.p[ring][par].period > kPlanMaxPairs) return false;
+    return true;
+}
+static_assert(ring_plans_ok(make_ring_plans()), "the ring plan must repeat within kPlanMaxPairs tile pairs");
+
+__constant__ RingPlans c_ring_plans = make_ring_plans();
+#ifdef NERF_B200_EXPERIMENTS
+constexpr RingPlans make_ring_plans_noreuse() {      // A/B: the same chunk orders, every use copies its chunk again
+    RingPlans r{};
+    for (int ring = 1; ring <= 3; ++ring)
+        for (int par = 0; par < 2; ++par) r.p[ring - 1][par] = make_ring_plan(ring, par != 0, false);
+    return r;
+}
+__constant__ RingPlans c_ring_plans_noreuse = make_ring_plans_noreuse();
+constexpr RingPlans make_ring_plans_round1() {       // A/B: both sub-tiles forward, no re-use (the round-1 schedule)
+    RingPlans r{};
+    for (int ring = 1; ring <= 3; ++ring)
+        for (int par = 0; par < 2; ++par) r.p[ring - 1][par] = make_ring_plan(ring, false, false, true);
+    return r;
+}
+__constant__ RingPlans c_ring_plans_round1 = make_ring_plans_round1();
+static_assert(ring_plans_ok(make_ring_plans_noreuse()) && ring_plans_ok(make_ring_plans_round1()), "plan period");
+#endif
+
 // ---------------------------------------------------------------------------- kernel
 // WIDE (inference, CT only): all 16 epilogue warps work on ONE sub-tile at a time (four threads per
 // row, 64 columns each) and alternate between the two sub-tiles, instead of 8 warps per sub-tile.
@@ -519,6 +651,7 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
     const uint32_t bar_a_ready = bar_w_empty + 8 * kMaxRing;  // [2]
     const uint32_t bar_acc_full = bar_a_ready + 16;           // [2]
     const uint32_t bar_pe_free = bar_acc_full + 16;           // [2]  PEA: l6's MMAs on A block 0 (h5) completed
+    const uint32_t bar_unused = bar_w_full + 8 * (kMaxRing - 1);   // takes the commits of chunks that keep their slot
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (2 * kMaxRing + 6));
     static_assert(8 * (2 * kMaxRing + 6) + 4 <= 256, "barrier region");
     long long t_wait0 = 0, t_wait1 = 0, t_begin = 0;
@@ -541,6 +674,8 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
             umma::mbar_init(bar_w_full + 8 * s, 1);
             umma::mbar_init(bar_w_empty + 8 * s, 1);
         }
+        static_assert(kRing < kMaxRing, "the last full-barrier slot is the unused one");
+        umma::mbar_init(bar_unused, 1);
         for (int g = 0; g < 2; ++g) {
             umma::mbar_init(bar_a_ready + 8 * g, (WIDE ? 2 : 1) * kEpiWarpsPerGroup * 32);
             umma::mbar_init(bar_acc_full + 8 * g, 1);
@@ -552,96 +687,61 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
         umma::tmem_alloc(umma::smem_u32(tmem_slot), 512);
         umma::tmem_relinquish();
     }
+    // The ring plan of this launch goes to shared memory: the constant bank is streamed through by the
+    // epilogues (11.8 KB of biases per tile pair), so an indexed constant load in the MMA thread misses its
+    // cache almost every time (measured: +390 cycles per chunk, the kernel 1.5x slower).
+    static_assert(kRing >= 1 && kRing <= 3, "ring plans exist for one to three slots");
+    static_assert(sizeof(RingPlan) <= 416, "plan region");
+    {
+#ifdef NERF_B200_EXPERIMENTS
+        const RingPlan& src = (CFG::exp & 65536)   ? c_ring_plans_round1.p[kRing - 1][P.tile0 & 1]
+                              : (CFG::exp & 32768) ? c_ring_plans_noreuse.p[kRing - 1][P.tile0 & 1]
+                                                   : c_ring_plans.p[kRing - 1][P.tile0 & 1];
+#else
+        const RingPlan& src = c_ring_plans.p[kRing - 1][P.tile0 & 1];
+#endif
+        for (int i = threadIdx.x; i < (int)(sizeof(RingPlan) / 2); i += blockDim.x)
+            reinterpret_cast<unsigned short*>(smem + kOffPlan)[i] = reinterpret_cast<const unsigned short*>(&src)[i];
+    }
+    const uint32_t plan_addr = sbase + kOffPlan;                  // 16-bit entries, kPlanPerPair per tile pair
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int plan_period = (int)reinterpret_cast<const RingPlan*>(smem + kOffPlan)->period;
 
-    if (warp == 0 || warp == 18) {
-        // ===================== producer(s): weight slots, L2 -> smem =====================
-        // two_producers: warp 0 arms the slot barrier with the whole byte count and copies the first half
-        // of the slot, warp 18 the second half
-        constexpr bool kTwo = CFG::two_producers;
-        const bool second = warp == 18;
+    if (warp == 0) {
+        // ===================== producer: weight slots, L2 -> smem =====================
+        // Follows the ring plan (c_ring_plans): per layer it copies the chunks of the sub-tile that is issued
+        // first, and for the second sub-tile only the chunks that are no longer resident.
         if (lane == 0 && !(CFG::exp & 8)) {
-            uint32_t it = 0;
+            uint32_t parity = 0;         // bit s: how often slot s was filled so far (mod 2)
             long pair_no = 0;
+            int pp = 0;                  // pair_no mod the plan's period
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_no) {
+                uint32_t q_addr = plan_addr + (uint32_t)pp * (kPlanPerPair * 2);
                 for (int l = 0; l < kNumMmaLayers; ++l) {
                     // one slot = one K chunk with all its N halves (adjacent stages in the blob)
                     const int first = layer_first_stage(l), chunks = layer_chunks(l);
                     // EXP bit5 (timing): the same copies and hand-offs, but only 1 KB per slot
                     const uint32_t bytes = (CFG::exp & 32) ? 1024u : layer_halves(l) * kStageBytes;
-                    auto fetch = [&](int g, int j) {
-                        const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-                        ++it;
+                    for (int i = 0; i < 2 * chunks; ++i, q_addr += 2) {
+                        const uint32_t e = umma::ld_shared_u16(q_addr);
+                        if (!(e & kPlanFirstUse)) continue;          // the other sub-tile's copy is still resident
+                        const int j = (int)(e & 7u), g = (int)((e >> 7) & 1u);
+                        const uint32_t slot = (e >> 3) & 3u, ph = (parity >> slot) & 1u;
+                        parity ^= 1u << slot;
                         long long t0 = PROBE ? clock64() : 0;
                         rec(0, pair_no, 1, l, g, j);                 // waits for a free slot
-                        if (CFG::exp & 256) {     // EXP bit8 (A/B): the producer spins on test_wait instead of suspending
-                            while (!umma::mbar_test_wait(bar_w_empty + 8 * slot, ph ^ 1)) {}
-                        } else {
-                            umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
-                        }
+                        umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
                         rec(0, pair_no, 2, l, g, j);                 // slot free: copy issued
                         if (PROBE) t_wait0 += clock64() - t0;
-                        if (!second) umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
-                        const uint32_t part = kTwo ? bytes / 2 : bytes, off = second ? part : 0u;
-                        umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes + off,
-                                       P.blob + (size_t)first * kStageBytes + (size_t)j * bytes + off, part,
-                                       bar_w_full + 8 * slot);
-                    };
-                    {
-                        // l6 accumulates its PE chunk (chunk 0) last in every variant of this kernel, so that
-                        // they all sum in the same order
-                        for (int g = 0; g < 2; ++g)
-                            for (int jj = 0; jj < chunks; ++jj) fetch(g, l == 5 ? (jj + 1) % chunks : jj);
+                        umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
+                        umma::bulk_g2s(sbase + kOffW + slot * kSlotBytes,
+                                       P.blob + (size_t)first * kStageBytes + (size_t)j * bytes, bytes, bar_w_full + 8 * slot);
                     }
                 }
-            }
-        }
-    } else if (warp == 1 && !PROBE && (CFG::exp & 128)) {      // EXP bit7 (A/B): measured 3.5 % SLOWER than the lone-lane issuer below
-        // ===================== MMA issuer (whole warp, one elected lane issues) =====================
-        // The 32 lanes run the loop converged and wait on the barriers together; only the tcgen05
-        // instructions sit behind elect.sync.  With a lone lane inside `if (lane == 0)` the compiler
-        // wraps every tcgen05.mma in an elect/branch loop and moves each descriptor through R2UR; here
-        // the descriptors live in uniform registers and the issue sequence of a chunk is straight-line.
-        uint32_t it = 0, n_ready[2] = {0, 0};
-        for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-            for (int l = 0; l < kNumMmaLayers; ++l) {
-                const int chunks = layer_chunks(l);
-                const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
-                for (int g = 0; g < 2; ++g) {
-                    umma::mbar_wait_warp(bar_a_ready + 8 * g, n_ready[g] & 1);
-                    ++n_ready[g];
-                    umma::tc_fence_after();
-                    const uint32_t d_base = tmem_base + g * 256;
-                    const uint32_t a_tile = sbase + kOffA + g * 65536;
-                    const uint32_t pe_tile = sbase + kOffPE + g * 16384;
-                    for (int jj = 0; jj < chunks; ++jj) {
-                        const int j = l == 5 ? (jj + 1) % chunks : jj;          // l6: PE chunk last
-                        uint32_t a_addr;
-                        if (l == 0) a_addr = pe_tile;
-                        else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
-                        else a_addr = a_tile + j * 16384;
-                        const uint32_t slot = it % kRing, ph = (it / kRing) & 1;
-                        ++it;
-                        // (one polling lane + __syncwarp for the rest instead of the warp-wide wait: half the speed)
-                        if (!(CFG::exp & 8)) umma::mbar_wait_warp(bar_w_full + 8 * slot, ph);
-                        umma::tc_fence_after();
-                        const uint32_t b_addr = sbase + kOffW + slot * kSlotBytes;
-                        if (umma::elect_one()) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                umma::mma_bf16_ss(d_base, umma::smem_desc_sw128(a_addr + kk * 32),
-                                                  umma::smem_desc_sw128(b_addr + kk * 32), idesc,
-                                                  (jj > 0 || kk > 0) ? 1u : 0u);
-                            }
-                            umma::mma_commit(bar_w_empty + 8 * slot);
-                            if (jj == chunks - 1) umma::mma_commit(bar_acc_full + 8 * g);
-                        }
-                        __syncwarp();
-                    }
-                }
+                if (++pp == plan_period) pp = 0;
             }
         }
     } else if (warp == 1) {
@@ -649,91 +749,95 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
         if (lane == 0) {
             // Everything this one thread executes between tcgen05.mma instructions is tensor-pipe idle time
             // once the pipe's short queue has drained (four clock64 per chunk cost the probe build 20 %), so
-            // the ring position is kept incrementally and the descriptors are built from precomputed words.
-            uint32_t slot = 0, ph = 0, n_ready[2] = {0, 0};
+            // the ring state is a few packed register words and the descriptors are built from precomputed words.
+            uint32_t parity = 0;         // bit s: how often slot s was filled so far (mod 2)
+            int pp = 0;                  // pair_no mod the plan's period
+            uint32_t n_ready = 0;        // bit g: parity of sub-tile g's next a_ready phase
             constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << (46 - 32)) | (2u << (61 - 32));   // smem_desc_sw128, high word
             auto desc = [&](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
             auto desc_lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
             const uint32_t w_lo = desc_lo(sbase + kOffW);
+            const uint32_t a_lo0 = desc_lo(sbase + kOffA), pe_lo0 = desc_lo(sbase + kOffPE);
             long pair_no = 0;
             for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_no) {
-                for (int l = 0; l < kNumMmaLayers; ++l) {
-                    const int chunks = layer_chunks(l);
+                // EXP bit11: wait profile of the production layout, sampled on one tile pair in eight (two
+                // clock64 around every wait would cost ~10 % if taken always)
+                const bool sampled = (CFG::exp & 2048) && P.trace_out && (pair_no & 7) == 3;
+                uint32_t q_addr = plan_addr + (uint32_t)pp * (kPlanPerPair * 2);
+                uint32_t e = umma::ld_shared_u16(q_addr);
+                // 18 segments per tile pair: (layer, sub-tile in issue order).  What is constant over a segment
+                // (accumulator, instruction descriptor, A tile) stays out of the chunk loop: every operand that
+                // changes between two tcgen05.mma costs the lone issuing thread a register -> uniform-register move.
+#pragma unroll 1
+                for (int seg = 0; seg < 2 * kNumMmaLayers; ++seg) {
+                    const int l = seg >> 1;
+                    const uint32_t g = (uint32_t)seg & 1u;
+                    const uint32_t d_base = tmem_base + g * 256;
                     const uint32_t idesc = layer_halves(l) == 2 ? kIdescN256 : kIdescN128;
-                    // waits until sub-tile g's A operand (or its re-encoded PE block) is written
-                    // EXP bit11: wait profile of the production layout, sampled on one tile pair in eight (two
-                    // clock64 around every wait would cost ~10 % if taken always): cycles per (layer, sub-tile)
-                    // waiting for the A operand and per (layer, chunk) waiting for the weight slot
-                    const bool sampled = (CFG::exp & 2048) && P.trace_out && (pair_no & 7) == 3;
-                    auto wait_a = [&](int g) {
+                    const uint32_t a_seg = a_lo0 + g * (65536 >> 4), pe_seg = pe_lo0 + g * (16384 >> 4);
+                    {
+                        // waits until sub-tile g's A operand is written
                         long long t0 = (PROBE || sampled) ? clock64() : 0;
-                        rec(1, pair_no, 1, l, g, 0);                     // waits for the A operand
-                        umma::mbar_wait(bar_a_ready + 8 * g, n_ready[g] & 1);
+                        rec(1, pair_no, 1, l, (int)g, 0);
+                        umma::mbar_wait(bar_a_ready + 8 * g, (n_ready >> g) & 1u);
                         if (sampled) atomicAdd((unsigned long long*)P.trace_out + 64 + l * 2 + g, (unsigned long long)(clock64() - t0));
-                        rec(1, pair_no, 2, l, g, 0);                     // A operand ready
+                        rec(1, pair_no, 2, l, (int)g, 0);
                         if (PROBE) t_wait0 += clock64() - t0;
-                        ++n_ready[g];
+                        n_ready ^= 1u << g;
                         umma::tc_fence_after();
-                    };
-                    // one K chunk: weight slot, four MMAs (the first one overwrites D when `fresh`), slot release
-                    auto chunk = [&](int g, int j, uint32_t a_addr, bool fresh) {
-                        long long t1 = (PROBE || sampled) ? clock64() : 0;
-                        rec(1, pair_no, 3, l, g, j);                 // waits for the weight slot
-                        // (no tcgen05 fence here: the slot was written by the TMA engine, whose complete_tx
-                        // on this barrier orders it before the MMAs that follow the wait)
-                        if (!(CFG::exp & 8)) umma::mbar_wait(bar_w_full + 8 * slot, ph);
-                        if (sampled) {
-                            atomicAdd((unsigned long long*)P.trace_out + l * 5 + j, (unsigned long long)(clock64() - t1));
-                            if (l == 0 && j == 0 && g == 0) atomicAdd((unsigned long long*)P.trace_out + 100, 1ull);
-                        }
-                        rec(1, pair_no, 4, l, g, j);                 // weight slot full
-                        if (PROBE) t_wait1 += clock64() - t1;
+                    }
+                    uint32_t accumulate = 0u;
+                    bool last;
+#pragma unroll 1
+                    do {
+                        q_addr += 2;
+                        // the next entry is fetched under this chunk's MMAs (the last fetch reads the pad word)
+                        const uint32_t e_next = umma::ld_shared_u16(q_addr);
+                        // everything the MMAs need is worked out BEFORE the waits: after a wait resolves, the
+                        // tensor pipe is idle until the first tcgen05.mma is issued
+                        const uint32_t slot = (e >> 3) & 3u;
                         // B = [N rows][64] K-major; the two 128-row halves are contiguous
                         const uint32_t b_lo = w_lo + slot * (kSlotBytes >> 4);
-                        const uint32_t a_lo = desc_lo(a_addr);
-                        const uint32_t d_base = tmem_base + g * 256;
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            umma::mma_bf16_ss(d_base, desc(a_lo + kk * 2), desc(b_lo + kk * 2), idesc,
-                                              (!fresh || kk > 0) ? 1u : 0u);
+                        const uint32_t a_lo = (!kPEA && (e & kPlanPeSrc)) ? pe_seg : a_seg + ((e >> 12) & 3u) * (16384 >> 4);
+                        // one commit per chunk without a branch: the slot's release, or a barrier nobody waits on
+                        const uint32_t release_bar = (e & kPlanRelease) ? bar_w_empty + 8 * slot : bar_unused;
+                        const uint32_t ph_full = (parity >> slot) & 1u;
+                        last = (e & kPlanLast) != 0;
+                        if (kPEA && (e & kPlanPeChunk)) {
+                            // PEA, l6: the PE block is restored into block 0 of the A tile once the MMAs that read
+                            // h5's block 0 have completed; the PE chunk closes the layer
+                            umma::mbar_wait(bar_a_ready + 8 * g, (n_ready >> g) & 1u);
+                            n_ready ^= 1u << g;
+                            umma::tc_fence_after();
                         }
-                        umma::mma_commit(bar_w_empty + 8 * slot);
-                        if (++slot == (uint32_t)kRing) { slot = 0; ph ^= 1; }
-                        rec(1, pair_no, 5, l, g, j);                 // chunk's four MMAs issued
-                    };
-                    if (kPEA && l == 5) {
-                        // l6 with the PE block restored in place: the four h5 chunks first; block 0 is
-                        // released to the epilogue group as soon as its MMAs are done, the group stores the PE
-                        // chunks it kept in registers (a few dozen cycles, under the three remaining h5
-                        // chunks), then the PE chunk closes the layer
-                        for (int g = 0; g < 2; ++g) {
-                            wait_a(g);
-                            const uint32_t a_tile = sbase + kOffA + g * 65536;
-                            for (int j = 1; j < chunks; ++j) {
-                                chunk(g, j, a_tile + (j - 1) * 16384, j == 1);
-                                if (j == 1) umma::mma_commit(bar_pe_free + 8 * g);
+                        if (e & kPlanFirstUse) {
+                            parity ^= 1u << slot;
+                            if (!(CFG::exp & 8)) {
+                                // first use of a fill: wait for the copy (no tcgen05 fence here: the slot was written by
+                                // the TMA engine, whose complete_tx on this barrier orders it before the MMAs that follow)
+                                long long t1 = (PROBE || sampled) ? clock64() : 0;
+                                rec(1, pair_no, 3, l, (int)g, (int)(e & 7u));
+                                umma::mbar_wait(bar_w_full + 8 * slot, ph_full);
+                                if (sampled) {
+                                    atomicAdd((unsigned long long*)P.trace_out + l * 5 + (e & 7u), (unsigned long long)(clock64() - t1));
+                                    if (seg == 0) atomicAdd((unsigned long long*)P.trace_out + 100, 1ull);
+                                }
+                                rec(1, pair_no, 4, l, (int)g, (int)(e & 7u));
+                                if (PROBE) t_wait1 += clock64() - t1;
                             }
-                            wait_a(g);
-                            chunk(g, 0, a_tile, false);
-                            umma::mma_commit(bar_acc_full + 8 * g);
                         }
-                        continue;
-                    }
-                    for (int g = 0; g < 2; ++g) {
-                        wait_a(g);
-                        const uint32_t a_tile = sbase + kOffA + g * 65536;
-                        const uint32_t pe_tile = kPEA ? a_tile : sbase + kOffPE + g * 16384;
-                        for (int jj = 0; jj < chunks; ++jj) {
-                            const int j = l == 5 ? (jj + 1) % chunks : jj;      // l6: PE chunk last
-                            uint32_t a_addr;
-                            if (l == 0) a_addr = pe_tile;
-                            else if (l == 5) a_addr = (j == 0) ? pe_tile : a_tile + (j - 1) * 16384;
-                            else a_addr = a_tile + j * 16384;
-                            chunk(g, j, a_addr, jj == 0);
-                        }
-                        umma::mma_commit(bar_acc_full + 8 * g);
-                    }
+                        umma::mma_bf16_ss(d_base, desc(a_lo), desc(b_lo), idesc, accumulate);
+#pragma unroll
+                        for (int kk = 1; kk < 4; ++kk) umma::mma_bf16_ss(d_base, desc(a_lo + kk * 2), desc(b_lo + kk * 2), idesc, 1u);
+                        accumulate = 1u;
+                        umma::mma_commit(release_bar);
+                        if (kPEA && (e & kPlanFreesBlock0)) umma::mma_commit(bar_pe_free + 8 * g);
+                        rec(1, pair_no, 5, l, (int)g, (int)(e & 7u));
+                        e = e_next;
+                    } while (!last);
+                    umma::mma_commit(bar_acc_full + 8 * g);
                 }
+                if (++pp == plan_period) pp = 0;
             }
         }
     } else if (WIDE) {
@@ -1000,7 +1104,7 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
 }
 
 template <bool PROBE, class CFG, bool SAVE = false, bool CT = false, bool WIDE = false>
-__global__ void __launch_bounds__(CFG::two_producers ? kThreadsFwd2 : kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 mlp_fwd_kernel(const __grid_constant__ FwdParams P) {
     mlp_fwd_body<PROBE, CFG, SAVE, CT, WIDE>(P);
 }
@@ -1049,6 +1153,8 @@ FwdKernel fwd_variant(int v) {
         case 19: return mlp_fwd_kernel<false, Cfg<3, false, 16384, true>, false, true>;   // production with 32-column TMEM loads in the hidden epilogue (A/B)
         case 20: return mlp_fwd_kernel_r112<false, Cfg<3, false, 16384, true>, false, true>;   // ... and a 112-register budget
         case 21: return mlp_fwd_kernel_r112<false, Cfg<3, false, 0, true>, false, true>;       // production with a 112-register budget (A/B)
+        case 22: return mlp_fwd_kernel<false, Cfg<3, false, 32768, true>, false, true>;        // production without weight-slot re-use (A/B)
+        case 23: return mlp_fwd_kernel<false, Cfg<3, false, 65536, true>, false, true>;        // ... and both sub-tiles forward: the round-1 schedule (A/B)
 #endif
         default: return nullptr;
     }
@@ -1094,7 +1200,7 @@ int launch_fwd(const FwdParams& P, int variant, void* stream) {
 }
 
 int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0, const float* in1,
-                int in_stride, long M, int S, const float* vterm, int vterm_div, float* raw_out) {
+                int in_stride, long M, int S, const float* vterm, int vterm_div, float* raw_out, long row0 = 0) {
     if (M < 0 || vterm_div < 1) return nerf::arg_error("nerf_mlp_fwd");
     if (M > 0 && (!packed || !in0 || !vterm || !raw_out)) return nerf::arg_error("nerf_mlp_fwd: null pointer");
     if (in_mode == NERF_IN_RAYS) {
@@ -1108,6 +1214,9 @@ int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0,
     P.in_mode = in_mode; P.in0 = in0; P.in1 = in1; P.in_stride = in_stride;
     P.M = M; P.S = S < 1 ? 1 : S; P.vterm = vterm; P.vterm_div = vterm_div; P.raw_out = raw_out;
     P.probe_out = nullptr; P.probe_layer = -1; P.stats_out = nullptr; P.trace_out = nullptr; P.act_save = nullptr;
+    // parity of the global index of the first tile: the chunk order of a row's contraction follows the parity of
+    // its global 128-row tile (chunk_at); a shard that does not start on a tile boundary is numbered from 0
+    P.tile0 = (row0 > 0 && (row0 % kTileM) == 0) ? (int)((row0 / kTileM) & 1) : 0;
     return 0;
 }
 
@@ -1115,10 +1224,10 @@ int fill_params(FwdParams& P, const void* packed, int in_mode, const float* in0,
 
 extern "C" int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, const float* in1,
                             int in_stride, long M, int S, const float* vterm, int vterm_div,
-                            float* raw_out, void* act_save, void* stream) {
+                            float* raw_out, void* act_save, long row0, void* stream) {
     nerf::DeviceGuard device_guard(raw_out);
     FwdParams P;
-    int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out);
+    int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out, row0);
     if (rc) return rc;
     if (M == 0) return 0;
     if (act_save && ((uintptr_t)act_save & 15)) return nerf::arg_error("nerf_mlp_fwd: act_save must be 16-byte aligned");
@@ -1149,11 +1258,11 @@ extern "C" int nerf_model_host_tail(const void* packed, void* host_tail_out, voi
 // nerf_mlp_fwd with biases, l_alpha and l11 travelling in the kernel parameters (inference path).
 extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail, int in_mode, const float* in0,
                                       const float* in1, int in_stride, long M, int S, const float* vterm,
-                                      int vterm_div, float* raw_out, void* stream) {
+                                      int vterm_div, float* raw_out, long row0, void* stream) {
     nerf::DeviceGuard device_guard(raw_out);
     if (!host_tail) return nerf::arg_error("nerf_mlp_fwd_host_tail: host_tail");
     FwdParams P;
-    int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out);
+    int rc = fill_params(P, packed, in_mode, in0, in1, in_stride, M, S, vterm, vterm_div, raw_out, row0);
     if (rc) return rc;
     if (M == 0) return 0;
     memcpy(&P.ct, host_tail, sizeof(ConstTail));

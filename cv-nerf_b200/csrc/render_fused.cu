@@ -80,7 +80,7 @@ extern "C" int nerf_render_fused(const void* packed_coarse, const void* host_tai
     };
     mark(0);
     if ((rc = nerf_mlp_fwd_host_tail(packed_coarse, host_tail_coarse, NERF_IN_RAYS, rays, f(L.z_c), 0, n * S_c, S_c,
-                                     f(L.vt_c), S_c, f(L.raw_c), stream)))
+                                     f(L.vt_c), S_c, f(L.raw_c), ray0 * S_c, stream)))
         return rc;
     mark(1);
     rc = noise > 0.f ? nerf_composite_fwd_rng(f(L.raw_c), f(L.z_c), rays + 3, NERF_RAY_STRIDE, noise, seed,
@@ -91,7 +91,7 @@ extern "C" int nerf_render_fused(const void* packed_coarse, const void* host_tai
     if ((rc = nerf_resample_merge_rng(f(L.z_c), f(L.w_c), seed, ray0, n, S_c, n_fine, f(L.z_f), stream))) return rc;
     mark(2);
     if ((rc = nerf_mlp_fwd_host_tail(packed_fine, host_tail_fine, NERF_IN_RAYS, rays, f(L.z_f), 0, n * S_f, S_f, f(L.vt_f),
-                                     S_f, f(L.raw_f), stream)))
+                                     S_f, f(L.raw_f), ray0 * S_f, stream)))
         return rc;
     mark(3);
     return noise > 0.f ? nerf_composite_fwd_rng(f(L.raw_f), f(L.z_f), rays + 3, NERF_RAY_STRIDE, noise, seed,

@@ -202,6 +202,11 @@ __device__ __forceinline__ float4 ld_shared_v4f(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
     return r;
 }
+__device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (uint32_t)v;
+}
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
     uint32_t r;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");

@@ -374,10 +374,11 @@ def model_host_tail(packed):
 
 
 def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_stride=0,
-            probe_layer=None, act_save=None, host_tail=None):
+            probe_layer=None, act_save=None, host_tail=None, row0=0):
     """-> raw [rows,4] (and the probed layer's FP32 activations when probe_layer is given).
     act_save: uint8 buffer of act_bytes(rows) that receives the activation records (training).
-    host_tail: model_host_tail(packed) -> the inference fast path (same results)."""
+    host_tail: model_host_tail(packed) -> the inference fast path (same results).
+    row0: global index of the first row when the call is a shard of a larger batch (include/nerf_b200.h)."""
     lib = _lib.load()
     raw = torch.empty((rows, 4), dtype=torch.float32, device=in0.device)
     st = stream_of(in0)
@@ -388,12 +389,12 @@ def mlp_fwd(packed, mode, in0, in1, rows, samples_per_ray, vterm, vterm_div, in_
             ev[0].record(torch.cuda.current_stream(in0.device))
         if host_tail is not None and act_save is None:
             check(lib.nerf_mlp_fwd_host_tail(packed.data_ptr(), host_tail.data_ptr(), mode, ptr(in0), ptr(in1),
-                                             in_stride, rows, samples_per_ray, ptr(vterm), vterm_div, ptr(raw), st),
+                                             in_stride, rows, samples_per_ray, ptr(vterm), vterm_div, ptr(raw), int(row0), st),
                   "nerf_mlp_fwd_host_tail")
         else:
             check(lib.nerf_mlp_fwd(packed.data_ptr(), mode, ptr(in0), ptr(in1), in_stride, rows, samples_per_ray,
                                    ptr(vterm), vterm_div, ptr(raw),
-                                   None if act_save is None else act_save.data_ptr(), st), "nerf_mlp_fwd")
+                                   None if act_save is None else act_save.data_ptr(), int(row0), st), "nerf_mlp_fwd")
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(in0.device))
             STATS.timed.append((ev[0], ev[1], rows))

@@ -73,9 +73,9 @@ def process_volume_info(raw_rgba, t_samples, r_dirs, noise=0.0, bkg=False, *, no
     return _composite(raw_rgba, f32c(t_samples), r_dirs, nz, bool(bkg))
 
 
-def _field(model, rays, z):
+def _field(model, rays, z, ray0=0):
     n, s = z.shape
-    spec = dict(mode=K.IN_RAYS, in0=rays, in1=z, rows=n * s, samples=s, vterm_div=s, dirs=rays)
+    spec = dict(mode=K.IN_RAYS, in0=rays, in1=z, rows=n * s, samples=s, vterm_div=s, dirs=rays, row0=int(ray0) * s)
     return model.field(spec).reshape(n, s, 4)
 
 
@@ -112,7 +112,7 @@ def render_rays(ray_batch, coarse_model, q_fn=None, n_coarse_samples=64, perturb
         return on_dev(injected) * noise if injected is not None else K.RngNoise(float(noise), rng, stream)
 
     want_all = extras or maps
-    raw_c = _field(coarse_model, rays, z_c)
+    raw_c = _field(coarse_model, rays, z_c, rng.ray0)
     rgb_c, w_c = _composite(raw_c, z_c, rays, noise_for(draws.noise_c, K.RNG_NOISE_C), bool(white_bkg))
 
     if draws.u is not None:
@@ -121,7 +121,7 @@ def render_rays(ray_batch, coarse_model, q_fn=None, n_coarse_samples=64, perturb
         z_f = K.resample_merge(z_c, w_c.detach(), rng=rng, n_fine=n_fine_samples)
 
     run = coarse_model if fine_model is None else fine_model
-    raw_f = _field(run, rays, z_f)
+    raw_f = _field(run, rays, z_f, rng.ray0)
     # the fine pass's weights are only materialised when somebody reads them (0.49 GB per 800x800 frame)
     rgb_f, w_f = _composite(raw_f, z_f, rays, noise_for(draws.noise_f, K.RNG_NOISE_F), bool(white_bkg),
                             want_weights=want_all)

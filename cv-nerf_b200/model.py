@@ -167,7 +167,8 @@ class Model(nn.Module):
         vterm = K.viewdir_term(packed, spec["dirs"], embedded=spec.get("dirs_embedded", False))
         return K.mlp_fwd(packed, spec["mode"], spec["in0"], spec.get("in1"), spec["rows"],
                          spec.get("samples", 1), vterm, spec["vterm_div"], spec.get("in_stride", 0),
-                         act_save=act_save, host_tail=None if act_save is not None else self.host_tail())
+                         act_save=act_save, host_tail=None if act_save is not None else self.host_tail(),
+                         row0=spec.get("row0", 0))
 
     def _backward_blob(self, spec, act, packed_bwd, grad_raw, blob):
         """grad_raw [rows,4] -> parameter gradients accumulated into the fp32 blob (see

@@ -182,10 +182,15 @@ int nerf_freq_encode(const float* x, long n, int dim, int n_freq, float* out, vo
  * M rows; S samples per ray (row r belongs to ray r / S, only used by NERF_IN_RAYS);
  * vterm [ceil(M / vterm_div), 128] from nerf_viewdir_term.
  * act_save: NULL, or a buffer of nerf_mlp_act_bytes(M) bytes that receives the BF16 activations
- * the backward pass needs. */
+ * the backward pass needs.
+ * row0: global index of the first row when this call is one shard of a larger batch (0 otherwise).
+ * The two 128-row sub-tiles a CTA works on consume a layer's K chunks in opposite orders (the second
+ * re-uses the weight slots of the first, csrc/mlp_fwd.cu chunk_at), chosen by the parity of the row's
+ * GLOBAL tile index; shards that start at a multiple of 128 rows and pass row0 reproduce the unsharded
+ * result bit for bit (other shard points agree to fp32 summation order, ~1e-7). */
 int nerf_mlp_fwd(const void* packed, int in_mode, const float* in0, const float* in1, int in_stride,
                  long M, int S, const float* vterm, int vterm_div, float* raw_out, void* act_save,
-                 void* stream);
+                 long row0, void* stream);
 
 size_t nerf_mlp_act_bytes(long M);
 
@@ -199,7 +204,7 @@ size_t nerf_model_host_tail_bytes(void);
 int nerf_model_host_tail(const void* packed, void* host_tail_out, void* stream);
 int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail, int in_mode, const float* in0,
                            const float* in1, int in_stride, long M, int S, const float* vterm,
-                           int vterm_div, float* raw_out, void* stream);
+                           int vterm_div, float* raw_out, long row0, void* stream);
 /* Test support: nerf_mlp_fwd that additionally writes the FP32 post-activation output of tensor-core
  * layer `probe_layer` (0 = l1 ... 8 = l9, 9 = l10) to probe_out [M,256] (l10 fills the first 128
  * columns).  The layer-by-layer parity tests compare it with a CPU emulation of the kernel's rounding

@@ -65,10 +65,16 @@ def test_render_with_rng_equals_render_with_the_same_draws_injected(perturb, noi
     for key in ("z_c", "z_f"):
         assert torch.equal(ea[key], eb[key]), key
     assert torch.equal(a, b) and torch.equal(ea["rgb_c"], eb["rgb_c"])
-    # chunked calls draw what the whole call draws (keys carry the global ray index)
+    # chunked calls draw what the whole call draws (keys carry the global ray index).  The pixels are bit-identical
+    # when the split falls on a 128-row tile boundary of both passes (the field kernel sums a row's K chunks in
+    # the order given by the parity of its global tile, include/nerf_b200.h); otherwise equal to fp32 summation order
     with torch.no_grad():
         parts = [M.render(16, 16, 20., rays=rays[:, i:j], rng=rng.shifted(i), **kw)[0] for i, j in ((0, 50), (50, 203))]
-    assert torch.equal(torch.cat(parts, 0), a)
+    got = torch.cat(parts, 0)
+    if (50 * S_c) % 128 == 0 and (50 * (S_c + n_fine)) % 128 == 0:
+        assert torch.equal(got, a)
+    else:
+        assert (got - a).abs().max().item() <= 2e-6
 
 
 def test_row_sharded_frame_with_rng_equals_whole_frame_and_seed_follows_torch():

@@ -37,13 +37,13 @@ cyc = buf[:148 * 8].view(148, 8)[:, 5].double().mean().item()
 print(f"sampled tile pairs: {pairs}; kernel cycles per CTA {cyc:.3e}")
 print("weight-slot wait, cycles per tile pair (both sub-tiles), by layer and chunk:")
 tot_w = 0
-for l in range(10):
+for l in range(9):
     row = [tr[l * 5 + j] / pairs for j in range(5)]
     tot_w += sum(row)
     print(f"  layer {l}: " + "  ".join(f"{v:7.0f}" for v in row))
 print("A-operand wait, cycles per tile pair, by layer (X, Y):")
 tot_a = 0
-for l in range(10):
+for l in range(9):
     a = [tr[64 + l * 2 + g] / pairs for g in range(2)]
     tot_a += sum(a)
     print(f"  layer {l}: {a[0]:7.0f} {a[1]:7.0f}")

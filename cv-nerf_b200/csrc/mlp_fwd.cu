@@ -431,11 +431,15 @@ __device__ __forceinline__ void epilogue_hidden_ct(int l, uint32_t tacc, int c0,
 // l10 (+ hoisted view term, ReLU) and l11 in FP32 over this thread's 64 columns [c0, c0+64):
 // partial rgb_raw.
 // SAVE: h10 (post-ReLU, BF16) is written to blocks 0..1 of the A tile for the activation record.
-template <bool PROBE, bool SAVE, bool CT, int NIT = 4>
-__device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0, const float* __restrict__ vt,
+// C0 >= 0: the first column as a compile-time constant, so that the host-tail build addresses l11's weights
+// with immediate offsets into the parameter bank (uniform loads feeding FFMA2 directly; a runtime c0 turns
+// them into 96 register-indexed constant loads per thread, which cost the tile boundary ~1500 cycles).
+template <bool PROBE, bool SAVE, bool CT, int NIT = 4, int C0 = -1>
+__device__ __forceinline__ void epilogue_rgb(uint32_t tacc, int c0_rt, const float* __restrict__ vt,
                                              const float* __restrict__ w11, float (&rgb)[3],
                                              float* probe_row, uint32_t row_addr, uint32_t swz, const ConstTail& ct,
                                              uint32_t* mw = nullptr) {
+    const int c0 = C0 >= 0 ? C0 : c0_rt;
     uint32_t v[2][16];
     float4 t[2][4];
     umma::tmem_ld16(tacc + c0, v[0]);
@@ -941,7 +945,9 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
         long pair_no = 0;
         const bool tracer = (ew & 7) == 0 && lane == 0;        // first warp of the group
         uint4 pe_regs[4];
-        bool pe_ahead = false;
+        bool pe_ahead = false, pe_stored = false;
+        const float* vt_row = nullptr;
+        long long t_rgb = 0;      // variant 18: start of the sampled tile's rgb epilogue
         for (long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++pair_no) {
             const long grow_raw = (pair * 2 + g) * kTileM + row;
             const bool valid = grow_raw < P.M;
@@ -959,11 +965,17 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                 if (half == 0) input_encode<0>(P, grow, pe_regs);
                 else input_encode<1>(P, grow, pe_regs);
             }
-            if (half == 0) input_store<0>(pe_regs, pe_tile, row);
-            else input_store<1>(pe_regs, pe_tile, row);
+            if (!pe_stored) {      // (stored at the end of the previous tile otherwise)
+                if (half == 0) input_store<0>(pe_regs, pe_tile, row);
+                else input_store<1>(pe_regs, pe_tile, row);
+                umma::fence_proxy_async_smem();
+                umma::mbar_arrive(bar_a_ready + 8 * g);
+            }
             pe_ahead = false;
-            umma::fence_proxy_async_smem();
-            umma::mbar_arrive(bar_a_ready + 8 * g);
+            pe_stored = false;
+            if ((CFG::exp & 2048) && t_rgb) atomicAdd((unsigned long long*)P.trace_out + 101 + g, (unsigned long long)(clock64() - t_rgb));
+            t_rgb = 0;
+            const bool esampled = (CFG::exp & 2048) && P.trace_out && tracer && (pair_no & 7) == 3;
             uint8_t* act_tile = nullptr;
             uint8_t* mask_tile = nullptr;          // every thread stores its own mask words
             if (SAVE) {
@@ -992,12 +1004,22 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                     else input_encode<1>(P, nxt < P.M ? nxt : P.M - 1, pe_regs);
                     pe_ahead = true;
                 }
+                if (l == kNumMmaLayers - 1) {
+                    // the row's view term (l10's hoisted view-direction columns), 64 floats per thread: brought
+                    // into L1 while l10's MMAs run, its L2 latency would otherwise sit on the tile boundary's
+                    // MMA -> epilogue -> MMA chain four times
+                    vt_row = P.vterm + (grow / P.vterm_div) * kL10Out;
+                    umma::prefetch_l1(vt_row + half * 64);
+                    umma::prefetch_l1(vt_row + half * 64 + 32);
+                }
                 if (tracer) rec(2 + g, pair_no, 1, l, g, 0);           // waits for the accumulator
                 umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
                 if (tracer) rec(2 + g, pair_no, 2, l, g, 0);           // accumulator complete
                 if (PROBE) t_wait0 += clock64() - t0;
                 ++n_full;
                 umma::tc_fence_after();
+                const long long t_epi = ((CFG::exp & 2048) && esampled) ? clock64() : 0;
+                if ((CFG::exp & 2048) && esampled && l == kNumMmaLayers - 1) t_rgb = t_epi;
                 if (PROBE) probe_row = (P.probe_out && P.probe_layer == l && valid) ? P.probe_out + grow * 256 : nullptr;
                 if (SAVE && kPEA && l == 0) {
                     // the PE record copy reads block 0, which l1's epilogue is about to overwrite
@@ -1019,6 +1041,7 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                     umma::fence_proxy_async_smem();
                     umma::tc_fence_before();
                     umma::mbar_arrive(bar_a_ready + 8 * g);
+                    if ((CFG::exp & 2048) && esampled) atomicAdd((unsigned long long*)P.trace_out + 104 + l * 2 + g, (unsigned long long)(clock64() - t_epi));
                     if (tracer) rec(2 + g, pair_no, 3, l, g, 0);       // this warp's part of the A operand written
                     // stage the next hidden layer's bias (after l9 comes l1 of the next tile); both
                     // barriers fall into the time the group would wait for the tensor core anyway
@@ -1048,9 +1071,24 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                     }
                 } else {
                     float rgb[3];
-                    const float* vt = P.vterm + (grow / P.vterm_div) * kL10Out;
-                    epilogue_rgb<PROBE, SAVE, CT>(tacc, half * 64, vt, tail + kTailW11, rgb, probe_row, a_row_addr, swz, P.ct, mw);
+                    if (CT && !PROBE && !SAVE) {
+                        if (half == 0) epilogue_rgb<false, false, true, 4, 0>(tacc, 0, vt_row, nullptr, rgb, nullptr, a_row_addr, swz, P.ct, mw);
+                        else epilogue_rgb<false, false, true, 4, 64>(tacc, 64, vt_row, nullptr, rgb, nullptr, a_row_addr, swz, P.ct, mw);
+                    } else {
+                        epilogue_rgb<PROBE, SAVE, CT>(tacc, half * 64, vt_row, tail + kTailW11, rgb, probe_row, a_row_addr, swz, P.ct, mw);
+                    }
                     umma::tc_fence_before();
+                    if (kPEA && !SAVE && pe_ahead) {
+                        // the accumulator is read and l10's MMAs have left the A tile: hand the next tile's PE
+                        // (block 0) to the tensor core before this tile's output is combined and written
+                        if (half == 0) input_store<0>(pe_regs, pe_tile, row);
+                        else input_store<1>(pe_regs, pe_tile, row);
+                        umma::fence_proxy_async_smem();
+                        umma::mbar_arrive(bar_a_ready + 8 * g);
+                        pe_stored = true;
+                        if ((CFG::exp & 2048) && t_rgb) atomicAdd((unsigned long long*)P.trace_out + 101 + g, (unsigned long long)(clock64() - t_rgb));
+                        t_rgb = 0;
+                    }
                     if (SAVE && mask_tile)
                         *reinterpret_cast<uint2*>(mask_tile + act_mask_slot(8, row, half)) = make_uint2(mw[0], mw[1]);
                     if (SAVE) {
@@ -1075,8 +1113,10 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                             reinterpret_cast<float4*>(P.raw_out)[grow] = o;
                         }
                     }
-                    // the next tile's encoding overwrites the hand-over slot: wait for the read
-                    umma::named_bar_sync(pair_bar, 64);
+                    // the next tile's encoding overwrites the hand-over slot: wait for the read (PEA: the slot lies
+                    // in block 3, which l1's epilogue rewrites only after every thread of the group has handed
+                    // over the PE, that is after this read)
+                    if (!kPEA) umma::named_bar_sync(pair_bar, 64);
                 }
             }
         }

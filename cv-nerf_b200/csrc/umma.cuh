@@ -138,6 +138,10 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* 
 }
 
 // pull a contiguous global range into L2 (no shared-memory destination, no completion tracking)
+// pulls the 128-byte line holding `p` into the SM's L1
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }

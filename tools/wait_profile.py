@@ -48,3 +48,7 @@ for l in range(9):
     tot_a += sum(a)
     print(f"  layer {l}: {a[0]:7.0f} {a[1]:7.0f}")
 print(f"per tile pair: weight-slot waits {tot_w:.0f}, A-operand waits {tot_a:.0f} cycles")
+print("epilogue of the first warp of each group, accumulator complete -> A operand handed over, cycles (X, Y):")
+for l in range(8):
+    print(f"  layer {l}: {tr[104 + l * 2] / pairs:7.0f} {tr[105 + l * 2] / pairs:7.0f}")
+print(f"  rgb epilogue + next tile's PE: {tr[101] / pairs:7.0f} {tr[102] / pairs:7.0f}")

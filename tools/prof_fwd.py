@@ -1,5 +1,4 @@
-"""Launches of the inference field kernel variants (100000 rays x 192 samples) for an ncu capture:
-per variant one warm-up + one launch, in the order single CTA, CTA pairs, 16-warp crew."""
+"""Two launches of the production inference field kernel (100000 rays x 192 samples) for an ncu capture."""
 import os
 import sys
 
@@ -24,10 +23,7 @@ z = K.sample_coarse(rays, S)
 pk = net.packed()
 ht = net.host_tail()
 vt = K.viewdir_term(pk, rays)
-modes = [int(a) for a in sys.argv[1:]] or [0, 1, 2]
-for mode in modes:
-    K.use_pairs(mode)
-    for _ in range(2):
-        raw = K.mlp_fwd(pk, K.IN_RAYS, rays, z, n * S, S, vt, S, host_tail=ht)
-    torch.cuda.synchronize()
+for _ in range(2):
+    raw = K.mlp_fwd(pk, K.IN_RAYS, rays, z, n * S, S, vt, S, host_tail=ht)
+torch.cuda.synchronize()
 print("ok", float(raw[0, 0]))

@@ -123,9 +123,8 @@ _SIGNATURES = {
 }
 
 # symbols of the experiments build only (make -C cv-nerf_b200/csrc experiments; NERF_B200_LIB selects the
-# library): the round-1 design alternatives of the field kernel and their cycle-counter entry
+# library): the A/B variants of the field kernel behind their cycle-counter entry
 _EXPERIMENT_SIGNATURES = {
-    "nerf_mlp_fwd_use_pairs": (ctypes.c_int, [ctypes.c_int]),
     "nerf_mlp_fwd_stats": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_long, ctypes.c_int,
                                           c_float_p, c_float_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
 }
@@ -141,7 +140,7 @@ def public_symbols():
 
 def has_experiments():
     """True when the loaded library is the experiments build (libnerf_b200_exp.so)."""
-    return hasattr(load(), "nerf_mlp_fwd_use_pairs")
+    return hasattr(load(), "nerf_mlp_fwd_stats")
 
 
 def load():

@@ -351,16 +351,6 @@ def freq_encode(x, n_freq):
     return out.reshape(*x.shape[:-1], out.shape[-1])
 
 
-def use_pairs(enable=None):
-    """Experiments build only (libnerf_b200_exp.so): select one of the round-1 design alternatives of
-    the field kernel for the inference path (0 = the production single-CTA kernel; DESIGN.md 4.1);
-    returns the previous setting.  ``None`` only queries."""
-    if not _lib.has_experiments():
-        raise _lib.NerfB200Error("kernel variants exist only in the experiments build: make -C cv-nerf_b200/csrc "
-                                 "experiments, then NERF_B200_LIB=cv-nerf_b200/libnerf_b200_exp.so")
-    return int(_lib.load().nerf_mlp_fwd_use_pairs(-1 if enable is None else int(enable)))
-
-
 def model_host_tail(packed):
     """Pinned host copy of the blob's biases / l_alpha / l11 for the inference fast path
     (synchronises the current stream once)."""

@@ -527,12 +527,12 @@ __host__ __device__ constexpr int chunk_at(int l, bool rev, int idx) {
 // thread that issues tcgen05.mma then runs a flat loop over the entries, fetching the next one under the
 // current chunk's MMAs: whatever it executes or waits for between two chunks is tensor idle time (the same
 // bookkeeping done in that thread made the kernel 1.5x slower; nested loops with two wait sites, +20 %).
-//   bits 0-2  chunk (source of the copy)             bit 8   FIRST: first chunk of the sub-tile's layer
-//   bits 3-4  slot                                            (wait for the A operand, overwrite D)
-//   bit 5     first use of a fill (wait / copy)       bit 9   LAST: last chunk (commit the accumulator)
-//   bit 6     release the slot after use              bit 10  PE chunk of l6 (PEA: wait for the restored block)
-//   bit 7     sub-tile (issue order)                  bit 11  chunk that frees A block 0 in l6 (PEA: signal it)
-//   bits 12-13 A block read by the chunk              bit 14  N = 128 (l10)     bit 15  A operand is the PE tile
+//   bits 0-2  chunk (source of the copy)             bit 9   LAST: last chunk of the sub-tile's layer
+//   bits 3-5  slot                                            (commit the accumulator)
+//   bit 6     first use of a fill (wait / copy)       bit 10  PE chunk of l6 (PEA: wait for the restored block)
+//   bit 7     release the slot after use              bit 11  chunk that frees A block 0 in l6 (PEA: signal it)
+//   bit 8     sub-tile (issue order)                  bits 12-13 A block read by the chunk
+//                                                     bit 15  A operand is the PE tile (layouts with PE tiles)
 constexpr int kPlanMaxPairs = 3;
 constexpr int kPlanPerPair = 68;
 struct RingPlan {
@@ -543,13 +543,14 @@ struct RingPlans {
     RingPlan p[3][2];      // [ring depth - 1][tile parity]
 };
 enum : unsigned {
-    kPlanFirstUse = 1u << 5, kPlanRelease = 1u << 6, kPlanG = 1u << 7, kPlanFirst = 1u << 8, kPlanLast = 1u << 9,
-    kPlanPeChunk = 1u << 10, kPlanFreesBlock0 = 1u << 11, kPlanN128 = 1u << 14, kPlanPeSrc = 1u << 15
+    kPlanSlotShift = 3, kPlanSlotMask = 7,
+    kPlanFirstUse = 1u << 6, kPlanRelease = 1u << 7, kPlanG = 1u << 8, kPlanLast = 1u << 9,
+    kPlanPeChunk = 1u << 10, kPlanFreesBlock0 = 1u << 11, kPlanPeSrc = 1u << 15
 };
 
 constexpr RingPlan make_ring_plan(int ring, bool rev0, bool reuse = true, bool both_forward = false) {
     RingPlan t{};
-    int fifo[8] = {0, 1, 2, 0, 0, 0, 0, 0};
+    int fifo[8] = {0, 1, 2, 3, 4, 5, 6, 7};
     int head = 0, count = ring;
     int where[5] = {-1, -1, -1, -1, -1};
     t.period = 0;
@@ -575,11 +576,11 @@ constexpr RingPlan make_ring_plan(int ring, bool rev0, bool reuse = true, bool b
                     }
                     const bool release = g == 1 || idx < keep_from;
                     const int a_block = l == 0 ? 0 : (l == 5 ? (c == 0 ? 0 : c - 1) : c);
-                    unsigned e = (unsigned)c | ((unsigned)where[c] << 3) | (first_use ? kPlanFirstUse : 0u) |
-                                 (release ? kPlanRelease : 0u) | (g ? kPlanG : 0u) | (idx == 0 ? kPlanFirst : 0u) |
+                    unsigned e = (unsigned)c | ((unsigned)where[c] << kPlanSlotShift) | (first_use ? kPlanFirstUse : 0u) |
+                                 (release ? kPlanRelease : 0u) | (g ? kPlanG : 0u) |
                                  (idx == n - 1 ? kPlanLast : 0u) | ((l == 5 && c == 0) ? kPlanPeChunk : 0u) |
                                  ((l == 5 && c == 1) ? kPlanFreesBlock0 : 0u) | ((unsigned)a_block << 12) |
-                                 (layer_halves(l) == 1 ? kPlanN128 : 0u) | ((l == 0 || (l == 5 && c == 0)) ? kPlanPeSrc : 0u);
+                                 ((l == 0 || (l == 5 && c == 0)) ? kPlanPeSrc : 0u);
                     if (pair < kPlanMaxPairs) t.e[pair * kPlanPerPair + q] = (unsigned short)e;
                     if (release) {
                         fifo[(head + count) & 7] = where[c];
@@ -613,6 +614,21 @@ constexpr bool ring_plans_ok(const RingPlans& r) {
 static_assert(ring_plans_ok(make_ring_plans()), "the ring plan must repeat within kPlanMaxPairs tile pairs");
 
 __constant__ RingPlans c_ring_plans = make_ring_plans();
+
+// CTA-pair kernel: five 16 KB slots (each CTA stages its half of a chunk).  With five slots the second sub-tile
+// finds EVERY chunk of the layer resident: 34 fills per tile pair, each chunk of the model once.
+constexpr int kPairRing = 5;
+struct PairPlans {
+    RingPlan p[2];         // [tile parity]
+};
+constexpr PairPlans make_pair_plans() {
+    PairPlans r{};
+    for (int par = 0; par < 2; ++par) r.p[par] = make_ring_plan(kPairRing, par != 0);
+    return r;
+}
+static_assert(make_pair_plans().p[0].period >= 1 && make_pair_plans().p[0].period <= kPlanMaxPairs &&
+              make_pair_plans().p[1].period >= 1 && make_pair_plans().p[1].period <= kPlanMaxPairs, "pair plan period");
+__constant__ PairPlans c_pair_plans = make_pair_plans();
 #ifdef NERF_B200_EXPERIMENTS
 constexpr RingPlans make_ring_plans_noreuse() {      // A/B: the same chunk orders, every use copies its chunk again
     RingPlans r{};
@@ -732,8 +748,8 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                     for (int i = 0; i < 2 * chunks; ++i, q_addr += 2) {
                         const uint32_t e = umma::ld_shared_u16(q_addr);
                         if (!(e & kPlanFirstUse)) continue;          // the other sub-tile's copy is still resident
-                        const int j = (int)(e & 7u), g = (int)((e >> 7) & 1u);
-                        const uint32_t slot = (e >> 3) & 3u, ph = (parity >> slot) & 1u;
+                        const int j = (int)(e & 7u), g = (e & kPlanG) ? 1 : 0;
+                        const uint32_t slot = (e >> kPlanSlotShift) & kPlanSlotMask, ph = (parity >> slot) & 1u;
                         parity ^= 1u << slot;
                         long long t0 = PROBE ? clock64() : 0;
                         rec(0, pair_no, 1, l, g, j);                 // waits for a free slot
@@ -754,6 +770,10 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
             // Everything this one thread executes between tcgen05.mma instructions is tensor-pipe idle time
             // once the pipe's short queue has drained (four clock64 per chunk cost the probe build 20 %), so
             // the ring state is a few packed register words and the descriptors are built from precomputed words.
+            // (The warp-uniform form of this loop that the CTA-pair kernel uses -- whole warp, elected issuer,
+            // operands on the uniform datapath -- was tried here too: 4.62e7 cycles per CTA against 3.67e7.  At
+            // 156 cycles per MMA this kernel is not bound by the issue instructions, and the extra divergence /
+            // reconvergence per chunk lengthens every wait -> first-MMA hand-off.)
             uint32_t parity = 0;         // bit s: how often slot s was filled so far (mod 2)
             int pp = 0;                  // pair_no mod the plan's period
             uint32_t n_ready = 0;        // bit g: parity of sub-tile g's next a_ready phase
@@ -799,7 +819,7 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                         const uint32_t e_next = umma::ld_shared_u16(q_addr);
                         // everything the MMAs need is worked out BEFORE the waits: after a wait resolves, the
                         // tensor pipe is idle until the first tcgen05.mma is issued
-                        const uint32_t slot = (e >> 3) & 3u;
+                        const uint32_t slot = (e >> kPlanSlotShift) & kPlanSlotMask;
                         // B = [N rows][64] K-major; the two 128-row halves are contiguous
                         const uint32_t b_lo = w_lo + slot * (kSlotBytes >> 4);
                         const uint32_t a_lo = (!kPEA && (e & kPlanPeSrc)) ? pe_seg : a_seg + ((e >> 12) & 3u) * (16384 >> 4);
@@ -1113,10 +1133,10 @@ __device__ __forceinline__ void mlp_fwd_body(const FwdParams& P) {
                             reinterpret_cast<float4*>(P.raw_out)[grow] = o;
                         }
                     }
-                    // the next tile's encoding overwrites the hand-over slot: wait for the read (PEA: the slot lies
-                    // in block 3, which l1's epilogue rewrites only after every thread of the group has handed
-                    // over the PE, that is after this read)
-                    if (!kPEA) umma::named_bar_sync(pair_bar, 64);
+                    // the hand-over slot is rewritten by the next tile's encoding (PEA: by half 1's l1 epilogue, block
+                    // 3): wait for the read.  With the early PE hand-over above this barrier is off the tile
+                    // boundary's MMA -> epilogue -> MMA chain.
+                    umma::named_bar_sync(pair_bar, 64);
                 }
             }
         }
@@ -1157,12 +1177,348 @@ __global__ void __maxnreg__(112) mlp_fwd_kernel_r112(const __grid_constant__ Fwd
     mlp_fwd_body<PROBE, CFG, SAVE, CT, WIDE>(P);
 }
 
-// The round-1 design alternatives of this kernel (activations in tensor memory / TS-form MMA, mixed
-// orientation, CTA pairs with tcgen05 cta_group::2, with and without tensor-map weight copies) were
-// removed from the tree in round 2, when l9 was folded into l10 (9 tensor-core layers): they lost
-// against mlp_fwd_kernel by 13..35 % and shared none of its later improvements.  Their measurements are
-// in DESIGN.md section 4.1 and profiles/r01_*.txt, their last buildable source in the commit before
-// "Fold l9 into l10".
+// ---------------------------------------------------------------------------- CTA-pair kernel (inference)
+// The same network on tcgen05 cta_group::2: the two CTAs of a cluster (one TPC) run ONE M=256 x N=256 MMA per
+// K step over their two 128-row sub-tiles, and each CTA stages only ITS half of every weight chunk (128 of the
+// 256 output rows; 64 of l10's 128).  The SS-form MMA of a single CTA fetches 12 KB of operands from shared
+// memory per step and takes 156 cycles for it; the pair MMA fetches 8 KB per SM and runs at the tensor core's
+// 128 cycles (tools/probes/pair_mma_rate_probe.cu), and the bytes the copy engine writes into shared memory
+// halve as well.  Round 1 had this design and lost 13 % with it: a sub-tile's epilogue took ~3500 cycles then
+// and, with the hand-offs crossing the pair, did not fit under the other sub-tile's 2048 MMA cycles.  The
+// epilogue now takes ~1000.
+//   tiles      a cluster takes four 128-row tiles at a time: CTA r, group g -> tile 4q + 2r + g, so g is the
+//              parity of the global tile and the chunk orders (chunk_at) -- hence every row's summation order
+//              and the output bits -- are those of mlp_fwd_kernel
+//   warp 0     (both CTAs) producer of the CTA's own 16 KB half-chunks: ring of five, plan c_pair_plans
+//   warp 1     leader: MMA issuer (tcgen05.mma.cta_group::2; commits multicast to both CTAs);
+//              peer: relays "my half-chunk has landed" to the leader's w_peer barriers
+//   warps 2-17 the two epilogue groups of mlp_fwd_kernel (PE in the A tile, host tail); a warp signals "my part
+//              of the A tile is written" with one arrive on the LEADER's barrier (remote from the peer)
+constexpr uint32_t kPairOffW = kOffPE;                 // no PE tiles: 96 KB for the ring
+static_assert(kPairOffW + kPairRing * kStageBytes <= kOffBar, "pair ring does not fit");
+constexpr uint32_t kIdescPairN256 = umma::instr_desc_bf16(256, 256);
+constexpr uint32_t kIdescPairN128 = umma::instr_desc_bf16(256, 128);
+
+template <int EXP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = umma::smem_u32(smem);
+    if ((sbase & 1023u) != 0) __trap();
+    constexpr int R = kPairRing;
+    const uint32_t bar_w_full = sbase + kOffBar;              // [R] this CTA's half-chunk has landed
+    const uint32_t bar_w_empty = bar_w_full + 8 * R;          // [R] the pair's MMAs are done with the slot (multicast commit)
+    const uint32_t bar_w_peer = bar_w_empty + 8 * R;          // [R] leader only: the peer's half-chunk has landed
+    const uint32_t bar_a_ready = bar_w_peer + 8 * R;          // [2] leader only: both CTAs' A tiles written
+    const uint32_t bar_acc_full = bar_a_ready + 16;           // [2] accumulators complete (multicast commit)
+    const uint32_t bar_pe_free = bar_acc_full + 16;           // [2] l6's MMAs on A block 0 (h5) completed (multicast commit)
+    const uint32_t bar_unused = bar_pe_free + 16;             // takes the commits of chunks that keep their slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (3 * R + 7));
+    static_assert(8 * (3 * R + 7) + 4 <= 256, "barrier region");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = umma::cluster_ctarank();
+    const long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const long n_tiles = (P.M + kTileM - 1) / kTileM;
+    const long n_quads = (n_tiles + 3) / 4;
+    const long long t_begin = P.stats_out ? clock64() : 0;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < R; ++s) {
+            umma::mbar_init(bar_w_full + 8 * s, 1);
+            umma::mbar_init(bar_w_empty + 8 * s, 1);
+            umma::mbar_init(bar_w_peer + 8 * s, 1);
+        }
+        umma::mbar_init(bar_unused, 1);
+        for (int g = 0; g < 2; ++g) {
+            umma::mbar_init(bar_a_ready + 8 * g, 2 * kEpiWarpsPerGroup);   // one arrive per warp and CTA
+            umma::mbar_init(bar_acc_full + 8 * g, 1);
+            umma::mbar_init(bar_pe_free + 8 * g, 1);
+        }
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) {
+        umma::tmem_alloc_pair(umma::smem_u32(tmem_slot), 512);
+        umma::tmem_relinquish_pair();
+    }
+    {
+        const RingPlan& src = c_pair_plans.p[P.tile0 & 1];
+        for (int i = threadIdx.x; i < (int)(sizeof(RingPlan) / 2); i += blockDim.x)
+            reinterpret_cast<unsigned short*>(smem + kOffPlan)[i] = reinterpret_cast<const unsigned short*>(&src)[i];
+    }
+    const uint32_t plan_addr = sbase + kOffPlan;
+    umma::tc_fence_before();
+    umma::cluster_sync_all();          // barriers of BOTH CTAs initialised before any remote arrive
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int plan_period = (int)reinterpret_cast<const RingPlan*>(smem + kOffPlan)->period;
+
+    if (warp == 0) {
+        // ===================== producer: this CTA's half of every weight chunk =====================
+        if (lane == 0 && !(EXP & 8)) {
+            uint32_t parity = 0;         // bit s: how often slot s was filled so far (mod 2)
+            int pp = 0;
+            for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+                uint32_t q_addr = plan_addr + (uint32_t)pp * (kPlanPerPair * 2);
+                for (int l = 0; l < kNumMmaLayers; ++l) {
+                    const int first = layer_first_stage(l), chunks = layer_chunks(l);
+                    // N = 256: stage (chunk, half = rank); N = 128 (l10): rows [64 rank, 64 rank + 64) of the chunk's stage
+                    const bool n256 = layer_halves(l) == 2;
+                    const uint32_t bytes = n256 ? kStageBytes : kStageBytes / 2;
+                    const uint8_t* src = P.blob + (size_t)first * kStageBytes + (size_t)rank * bytes;
+                    const size_t stride = n256 ? 2 * kStageBytes : kStageBytes;
+                    for (int i = 0; i < 2 * chunks; ++i, q_addr += 2) {
+                        const uint32_t e = umma::ld_shared_u16(q_addr);
+                        if (!(e & kPlanFirstUse)) continue;          // the other sub-tile's copy is still resident
+                        const uint32_t slot = (e >> kPlanSlotShift) & kPlanSlotMask, ph = (parity >> slot) & 1u;
+                        parity ^= 1u << slot;
+                        umma::mbar_wait(bar_w_empty + 8 * slot, ph ^ 1);
+                        umma::mbar_arrive_expect_tx(bar_w_full + 8 * slot, bytes);
+                        umma::bulk_g2s(sbase + kPairOffW + slot * kStageBytes, src + (size_t)(e & 7u) * stride, bytes,
+                                       bar_w_full + 8 * slot);
+                    }
+                }
+                if (++pp == plan_period) pp = 0;
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 1 && (EXP & 8)) {
+            // timing variant without weight streaming: nothing to relay
+        } else if (lane == 0 && rank == 1) {
+            // ===================== peer: relay slot arrivals to the leader =====================
+            uint32_t parity = 0;
+            int pp = 0;
+            const uint32_t leader_w_peer = umma::map_to_cta(bar_w_peer, 0);
+            for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+                uint32_t q_addr = plan_addr + (uint32_t)pp * (kPlanPerPair * 2);
+                for (int i = 0; i < kPlanPerPair; ++i, q_addr += 2) {
+                    const uint32_t e = umma::ld_shared_u16(q_addr);
+                    if (!(e & kPlanFirstUse)) continue;
+                    const uint32_t slot = (e >> kPlanSlotShift) & kPlanSlotMask, ph = (parity >> slot) & 1u;
+                    parity ^= 1u << slot;
+                    umma::mbar_wait(bar_w_full + 8 * slot, ph);
+                    umma::mbar_arrive_remote_cta(leader_w_peer + 8 * slot);
+                }
+                if (++pp == plan_period) pp = 0;
+            }
+        } else if (rank == 0) {
+            // ===================== leader: MMA issuer for the pair =====================
+            // The WHOLE warp runs this loop with warp-uniform values, and one elected lane issues the tensor-core
+            // instructions.  With a lone thread (if (lane == 0) around the loop) the compiler has to move every
+            // operand of every tcgen05.mma from vector registers into uniform registers inside an
+            // elect / R2UR.BROADCAST x7 / branch loop (~17 instructions per MMA): more than the 128 cycles a pair
+            // MMA leaves, so the issue thread, not the tensor pipe, set the pace (~200 cycles per MMA).  Values
+            // the compiler can prove uniform (the plan entry goes through a warp reduction: REDUX writes a
+            // uniform register) stay on the uniform datapath: UIADD + UTCHMMA.
+            const bool issuer = umma::elect_one();
+            uint32_t parity = 0, n_ready = 0;
+            int pp = 0;
+            constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << (46 - 32)) | (2u << (61 - 32));   // smem_desc_sw128, high word
+            auto desc_lo = [&](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+            auto uniform = [&](uint32_t v) { return __reduce_max_sync(0xffffffffu, v); };
+            const uint32_t w_lo = uniform(desc_lo(sbase + kPairOffW));
+            const uint32_t a_lo0 = uniform(desc_lo(sbase + kOffA));
+            const uint32_t tmem_u = uniform(tmem_base);
+            const uint32_t bars_u = uniform(bar_w_full);
+            // all lanes poll together (a uniform loop: no divergence to reconverge from behind a wait; the
+            // elected-lane form "if (issuer) wait; __syncwarp()" costs ~140 cycles per chunk)
+            auto wait = [&](uint32_t bar, uint32_t ph) { umma::mbar_wait_warp(bar, ph); };
+            long quad_no = 0;
+            for (long quad = cluster_id; quad < n_quads; quad += n_clusters, ++quad_no) {
+                const bool sampled = (EXP & 2048) && P.trace_out && (quad_no & 7) == 3;
+                uint32_t q_addr = plan_addr + (uint32_t)pp * (kPlanPerPair * 2);
+                uint32_t e = uniform(umma::ld_shared_u16(q_addr));
+#pragma unroll 1
+                for (int seg = 0; seg < 2 * kNumMmaLayers; ++seg) {
+                    const int l = seg >> 1;
+                    const uint32_t g = (uint32_t)seg & 1u;
+                    const uint32_t d_base = tmem_u + g * 256;
+                    const uint32_t idesc = layer_halves(l) == 2 ? kIdescPairN256 : kIdescPairN128;
+                    const uint32_t a_seg = a_lo0 + g * (65536 >> 4);
+                    {
+                        const long long t0 = sampled ? clock64() : 0;
+                        wait(bars_u + 8 * (3 * R) + 8 * g, (n_ready >> g) & 1u);          // bar_a_ready[g]
+                        if (sampled && issuer) atomicAdd((unsigned long long*)P.trace_out + 64 + l * 2 + g, (unsigned long long)(clock64() - t0));
+                        n_ready ^= 1u << g;
+                        umma::tc_fence_after();
+                    }
+                    uint32_t accumulate = 0u;
+                    bool last;
+#pragma unroll 1
+                    do {
+                        q_addr += 2;
+                        const uint32_t e_next = uniform(umma::ld_shared_u16(q_addr));
+                        const uint32_t slot = (e >> kPlanSlotShift) & kPlanSlotMask;
+                        const uint32_t b_lo = w_lo + slot * (kStageBytes >> 4);
+                        const uint32_t a_lo = a_seg + ((e >> 12) & 3u) * (16384 >> 4);
+                        const uint32_t release_bar = (e & kPlanRelease) ? bars_u + 8 * R + 8 * slot : bars_u + 8 * (3 * R + 6);   // bar_w_empty[slot] / bar_unused
+                        const uint32_t ph_full = (parity >> slot) & 1u;
+                        last = (e & kPlanLast) != 0;
+                        if (e & kPlanPeChunk) {
+                            // l6: both CTAs have restored the PE block into block 0 of their A tiles
+                            wait(bars_u + 8 * (3 * R) + 8 * g, (n_ready >> g) & 1u);
+                            n_ready ^= 1u << g;
+                            umma::tc_fence_after();
+                        }
+                        if ((e & kPlanFirstUse) && !(EXP & 8)) {
+                            parity ^= 1u << slot;
+                            const long long t1 = sampled ? clock64() : 0;
+                            wait(bars_u + 8 * slot, ph_full);                  // own half: bar_w_full[slot]
+                            wait(bars_u + 8 * (2 * R) + 8 * slot, ph_full);    // the peer's half: bar_w_peer[slot]
+                            if (sampled && issuer) {
+                                atomicAdd((unsigned long long*)P.trace_out + l * 5 + (e & 7u), (unsigned long long)(clock64() - t1));
+                                if (seg == 0) atomicAdd((unsigned long long*)P.trace_out + 100, 1ull);
+                            }
+                        }
+                        // four MMAs, the slot's release (or a barrier nobody waits on) and, after the chunk that frees
+                        // A block 0 in l6, bar_pe_free[g]
+                        umma::mma_chunk_pair_elect(d_base, a_lo, b_lo, kDescHi, idesc, accumulate, release_bar,
+                                                   (e & kPlanFreesBlock0) ? bars_u + 8 * (3 * R + 4) + 8 * g : 0u);
+                        accumulate = 1u;
+                        e = e_next;
+                    } while (!last);
+                    umma::mma_commit_pair_elect(bars_u + 8 * (3 * R + 2) + 8 * g);      // bar_acc_full[g]
+                }
+                if (++pp == plan_period) pp = 0;
+            }
+        }
+    } else {
+        // ===================== epilogue groups (as in mlp_fwd_kernel: PE in the A tile, host tail) =====================
+        const int ew = warp - 2;
+        const int g = ew >> 3;
+        const int half = (ew >> 2) & 1;
+        const int quadrant = warp & 3;
+        const int row = quadrant * 32 + lane;
+        const uint32_t pair_bar = 1 + g * 4 + quadrant;
+        const uint32_t a_row_addr = sbase + kOffA + g * 65536 + row * 128;
+        const uint32_t swz = (uint32_t)(row & 7) << 4;
+        uint8_t* pe_tile = smem + kOffA + g * 65536;
+        float4* xchg = reinterpret_cast<float4*>(smem + kOffA + g * 65536 + 3 * 16384 + row * 128);
+        const uint32_t tacc = tmem_base + ((uint32_t)(quadrant * 32) << 16) + g * 256;
+        const uint32_t leader_a_ready = umma::map_to_cta(bar_a_ready + 8 * g, 0);
+        // "this warp's part of the group's A tile is written": every lane has fenced its stores towards the
+        // async proxy and its TMEM loads towards the tensor core; one lane tells the leader's MMA warp.  The
+        // arrive has CTA-scope release semantics, as in CUTLASS's ClusterBarrier::arrive(cta_id): the
+        // .release.cluster form is a cluster-wide fence for the thread and cost ~2000 cycles per hand-over here.
+        auto signal_a_ready = [&]() {
+            umma::fence_proxy_async_smem();
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive_remote_cta(leader_a_ready);
+        };
+        const bool tracer = (EXP & 2048) && (ew & 7) == 0 && lane == 0;
+        uint32_t n_full = 0, n_pe_free = 0;
+        uint4 pe_regs[4];
+        bool pe_ahead = false, pe_stored = false;
+        const float* vt_row = nullptr;
+        long long t_rgb = 0;
+        long quad_no = 0;
+        for (long quad = cluster_id; quad < n_quads; quad += n_clusters, ++quad_no) {
+            const long grow_raw = (quad * 4 + rank * 2 + g) * kTileM + row;
+            const bool valid = grow_raw < P.M;
+            const long grow = valid ? grow_raw : P.M - 1;
+            if (!pe_ahead) {
+                if (half == 0) input_encode<0>(P, grow, pe_regs);
+                else input_encode<1>(P, grow, pe_regs);
+            }
+            if (!pe_stored) {      // (stored at the end of the previous tile otherwise)
+                if (half == 0) input_store<0>(pe_regs, pe_tile, row);
+                else input_store<1>(pe_regs, pe_tile, row);
+                signal_a_ready();
+            }
+            pe_ahead = false;
+            pe_stored = false;
+            const bool esampled = tracer && P.trace_out && (quad_no & 7) == 3;
+            float sigma = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < kNumMmaLayers; ++l) {
+                if (l == kNumMmaLayers - 1) {
+                    if (quad + n_clusters < n_quads) {
+                        const long nxt = ((quad + n_clusters) * 4 + rank * 2 + g) * kTileM + row;
+                        if (half == 0) input_encode<0>(P, nxt < P.M ? nxt : P.M - 1, pe_regs);
+                        else input_encode<1>(P, nxt < P.M ? nxt : P.M - 1, pe_regs);
+                        pe_ahead = true;
+                    }
+                    vt_row = P.vterm + (grow / P.vterm_div) * kL10Out;
+                    umma::prefetch_l1(vt_row + half * 64);
+                    umma::prefetch_l1(vt_row + half * 64 + 32);
+                }
+                umma::mbar_wait_warp(bar_acc_full + 8 * g, n_full & 1);
+                ++n_full;
+                umma::tc_fence_after();
+                const long long t_epi = esampled ? clock64() : 0;
+                if (esampled && l == kNumMmaLayers - 1) t_rgb = t_epi;
+                if (l < kNumMmaLayers - 1) {
+                    if (half == 0) epilogue_hidden_ct<8, EXP & 7, 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
+                    else epilogue_hidden_ct<8, EXP & 7, 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
+                    if ((EXP & 2048) && esampled) {
+                        // split of the hand-over: epilogue body / proxy + tcgen05 fences / warp sync + remote arrive
+                        const long long t1 = clock64();
+                        umma::fence_proxy_async_smem();
+                        umma::tc_fence_before();
+                        const long long t2 = clock64();
+                        __syncwarp();
+                        if (lane == 0) umma::mbar_arrive_remote_cta(leader_a_ready);
+                        const long long t3 = clock64();
+                        atomicAdd((unsigned long long*)P.trace_out + 130, (unsigned long long)(t1 - t_epi));
+                        atomicAdd((unsigned long long*)P.trace_out + 131, (unsigned long long)(t2 - t1));
+                        atomicAdd((unsigned long long*)P.trace_out + 132, (unsigned long long)(t3 - t2));
+                    } else {
+                        signal_a_ready();
+                    }
+                    if (esampled) atomicAdd((unsigned long long*)P.trace_out + 104 + l * 2 + g, (unsigned long long)(clock64() - t_epi));
+                    if (l == 4) {
+                        // l6's MMAs on block 0 (h5) have completed in both CTAs: put the tile's PE back into it
+                        umma::mbar_wait_warp(bar_pe_free + 8 * g, n_pe_free & 1);
+                        ++n_pe_free;
+                        if (half == 0) input_store<0>(pe_regs, pe_tile, row);
+                        else input_store<1>(pe_regs, pe_tile, row);
+                        signal_a_ready();
+                    }
+                } else {
+                    float rgb[3];
+                    if (half == 0) epilogue_rgb<false, false, true, 4, 0>(tacc, 0, vt_row, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
+                    else epilogue_rgb<false, false, true, 4, 64>(tacc, 64, vt_row, nullptr, rgb, nullptr, a_row_addr, swz, P.ct);
+                    if (pe_ahead) {
+                        // the accumulator is read and l10's MMAs have left the A tile: hand the next tile's PE
+                        // (block 0) to the tensor core before this tile's output is combined and written
+                        if (half == 0) input_store<0>(pe_regs, pe_tile, row);
+                        else input_store<1>(pe_regs, pe_tile, row);
+                        signal_a_ready();
+                        pe_stored = true;
+                        if (t_rgb) atomicAdd((unsigned long long*)P.trace_out + 101 + g, (unsigned long long)(clock64() - t_rgb));
+                        t_rgb = 0;
+                    } else {
+                        umma::tc_fence_before();
+                    }
+                    // combine the two column halves of the row: half 1 hands its partial sums over (slot in block 3 of
+                    // the A tile, dead after l10's MMAs)
+                    if (half == 1) *xchg = make_float4(rgb[0], rgb[1], rgb[2], sigma);
+                    umma::named_bar_sync(pair_bar, 64);
+                    if (half == 0) {
+                        const float4 o2 = *xchg;
+                        if (valid) {
+                            float4 o;
+                            o.x = rgb[0] + o2.x + P.ct.b11[0];
+                            o.y = rgb[1] + o2.y + P.ct.b11[1];
+                            o.z = rgb[2] + o2.z + P.ct.b11[2];
+                            o.w = sigma + o2.w + P.ct.balpha[0];
+                            reinterpret_cast<float4*>(P.raw_out)[grow] = o;
+                        }
+                    }
+                    umma::named_bar_sync(pair_bar, 64);     // half 1's next l1 epilogue rewrites the slot
+                }
+            }
+        }
+    }
+    umma::tc_fence_before();
+    umma::cluster_sync_all();          // no CTA frees tensor memory while its partner still uses it
+    if (P.stats_out && threadIdx.x == 0) P.stats_out[(long)blockIdx.x * 8 + 5] = clock64() - t_begin;
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc_pair(tmem_base, 512);
+    }
+}
 
 using FwdKernel = void (*)(const FwdParams);   // (__grid_constant__ does not change the type)
 
@@ -1198,6 +1554,64 @@ FwdKernel fwd_variant(int v) {
 #endif
         default: return nullptr;
     }
+}
+
+// CTA-pair kernel: clusters of two CTAs, one cluster per TPC.  Returns NERF_ERR_UNSUPPORTED-like negative
+// codes through arg_error only for real errors; the caller falls back to nothing (there is no other path
+// for `variant`), so a device that cannot co-schedule the clusters reports the launch error.
+int launch_fwd_pair(const FwdParams& P, int exp, void* stream) {
+    constexpr int kMaxDevices = 64;
+    static int max_clusters[kMaxDevices] = {};
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        nerf::set_last_error("nerf_mlp_fwd (CTA pairs) setup: %s", e0 != cudaSuccess ? cudaGetErrorString(e0) : "device index");
+        return e0 != cudaSuccess ? (int)e0 : NERF_ERR_UNSUPPORTED;
+    }
+    FwdKernel k = exp == 2048 ? mlp_fwd_pair_kernel<2048> : mlp_fwd_pair_kernel<0>;
+#ifdef NERF_B200_EXPERIMENTS
+    // timing-only variants (wrong numerics): bit0 no A-tile stores, bit2 no TMEM loads, bit3 no weight streaming
+    if (exp == 1) k = mlp_fwd_pair_kernel<1>;
+    if (exp == 4) k = mlp_fwd_pair_kernel<4>;
+    if (exp == 5) k = mlp_fwd_pair_kernel<5>;
+    if (exp == 8) k = mlp_fwd_pair_kernel<8>;
+    if (exp == 24) k = mlp_fwd_pair_kernel<24>;
+    if (exp == 40) k = mlp_fwd_pair_kernel<40>;
+    if (exp != 0 && exp != 2048) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+#endif
+    if (max_clusters[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        int sm_count = 0, n = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) {
+            // how many 2-CTA clusters the device keeps resident at once (a GPC with an odd SM count loses one)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(sm_count & ~1));
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = kSmemBytes;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            e = cudaOccupancyMaxActiveClusters(&n, mlp_fwd_pair_kernel<0>, &cfg);
+            if (e == cudaSuccess && n < 1) n = sm_count / 2;
+        }
+        if (e != cudaSuccess) {
+            nerf::set_last_error("nerf_mlp_fwd (CTA pairs) setup: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        max_clusters[dev] = n;
+    }
+    const long n_tiles = (P.M + kTileM - 1) / kTileM;
+    const long n_quads = (n_tiles + 3) / 4;
+    const long clusters = n_quads < max_clusters[dev] ? n_quads : max_clusters[dev];
+    k<<<(unsigned)(2 * clusters), kThreads, kSmemBytes, (cudaStream_t)stream>>>(P);
+    return nerf::check_launch("nerf_mlp_fwd (CTA pairs)");
 }
 
 int launch_fwd(const FwdParams& P, int variant, void* stream) {
@@ -1306,7 +1720,14 @@ extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail,
     if (rc) return rc;
     if (M == 0) return 0;
     memcpy(&P.ct, host_tail, sizeof(ConstTail));
-    return launch_fwd(P, 9, stream);
+    // The CTA-pair kernel (tcgen05 cta_group::2) is the production inference kernel; mlp_fwd_kernel produces the
+    // same bits and stays selectable for A/B runs (NERF_B200_FWD_PAIRS=0) and for devices that cannot
+    // co-schedule two-CTA clusters.
+    static const bool use_pairs = [] {
+        const char* v = getenv("NERF_B200_FWD_PAIRS");
+        return !(v && v[0] == '0');
+    }();
+    return use_pairs ? launch_fwd_pair(P, 0, stream) : launch_fwd(P, 9, stream);
 }
 
 // Test-support entry: additionally dumps the FP32 post-activation output of MMA layer
@@ -1339,10 +1760,18 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
         P.trace_out = stats_out + 148 * 8;
         variant -= 1000;
     }
-    if (variant == 9 || variant == 10 || (variant >= 13 && variant <= 23)) {   // host-tail kernels
+    if (variant == 9 || variant == 10 || (variant >= 13 && variant <= 23) || (variant >= 30 && variant <= 39)) {   // host-tail kernels
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
     }
+    if (variant == 30) return launch_fwd_pair(P, 0, stream);          // CTA-pair kernel
+    if (variant == 31) return launch_fwd_pair(P, 2048, stream);       // ... with the sampled wait profile
+    if (variant == 32) return launch_fwd_pair(P, 4, stream);          // timing: no TMEM loads in the hidden epilogues
+    if (variant == 33) return launch_fwd_pair(P, 1, stream);          // timing: no A-tile stores
+    if (variant == 34) return launch_fwd_pair(P, 8, stream);          // timing: no weight streaming
+    if (variant == 35) return launch_fwd_pair(P, 5, stream);          // timing: neither loads nor stores
+    if (variant == 36) return launch_fwd_pair(P, 24, stream);         // timing: no weight streaming, no per-chunk commits
+    if (variant == 37) return launch_fwd_pair(P, 40, stream);         // timing: no weight streaming, per-chunk commits without multicast
     return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }
 

@@ -328,6 +328,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// the form CUTLASS uses for arrives that cross a CTA pair (ClusterBarrier::arrive(cta_id)): default
+// semantics (.release.cta).  The .release.cluster form above is a cluster-scope fence for the whole thread:
+// ~2500 cycles per arrive with global stores in flight (measured in the CTA-pair field kernel).
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -387,6 +393,63 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
         "h"((uint16_t)3)
         : "memory");
+}
+
+// One K chunk of the CTA-pair kernel as ONE block: four tcgen05.mma (K = 4 x 16; the descriptors' low words
+// advance by 2 = 32 bytes) and up to two multicast commits, all predicated on an elected lane INSIDE the block.
+// Executed by a whole converged warp with warp-uniform operands: no branch around the tensor instructions, so the
+// compiler emits UIADD3 / UTCHMMA / UTCBAR with a uniform predicate and no divergence bookkeeping.
+// commit2_bar = 0: no second commit.
+__device__ __forceinline__ void mma_chunk_pair_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                     uint32_t idesc, uint32_t accumulate, uint32_t commit_bar,
+                                                     uint32_t commit2_bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pacc, ptrue, pc2;\n"
+        ".reg .b64 da, db;\n"
+        ".reg .b32 al, bl;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pacc, %5, 0;\n"
+        "setp.eq.b32 ptrue, 0, 0;\n"
+        "setp.ne.and.b32 pc2, %7, 0, pe;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, pacc;\n"
+        "add.u32 al, %1, 2;\n"
+        "add.u32 bl, %2, 2;\n"
+        "mov.b64 da, {al, %3};\n"
+        "mov.b64 db, {bl, %3};\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, ptrue;\n"
+        "add.u32 al, %1, 4;\n"
+        "add.u32 bl, %2, 4;\n"
+        "mov.b64 da, {al, %3};\n"
+        "mov.b64 db, {bl, %3};\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, ptrue;\n"
+        "add.u32 al, %1, 6;\n"
+        "add.u32 bl, %2, 6;\n"
+        "mov.b64 da, {al, %3};\n"
+        "mov.b64 db, {bl, %3};\n"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, ptrue;\n"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %8;\n"
+        "@pc2 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %8;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(commit_bar), "r"(commit2_bar), "h"((uint16_t)3)
+        : "memory");
+}
+// commit by the elected lane of a converged warp (no branch)
+__device__ __forceinline__ void mma_commit_pair_elect(uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+        "}\n" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// the same without multicast: arrives on the issuing (leader) CTA's barrier only
+__device__ __forceinline__ void mma_commit_pair_local(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 }  // namespace umma

@@ -13,6 +13,7 @@ from cv_nerf_b200 import _lib, kernels as K  # noqa: E402
 from tools.gpu_diag import packed_model, DEV  # noqa: E402
 
 lib = _lib.load()
+VARIANT = int(sys.argv[1]) if len(sys.argv) > 1 else 18     # 18: mlp_fwd_kernel, 31: the CTA-pair kernel
 p, packed = packed_model()
 n_rays, S = 160000, 192
 rays = torch.zeros(n_rays, 11, device=DEV)
@@ -28,12 +29,13 @@ st = torch.cuda.current_stream().cuda_stream
 for _ in range(2):
     buf.zero_()
     rc = lib.nerf_mlp_fwd_stats(packed.data_ptr(), rays.data_ptr(), z.data_ptr(), n_rays * S, S, vt.data_ptr(),
-                                raw.data_ptr(), 1018, buf.data_ptr(), st)
+                                raw.data_ptr(), 1000 + VARIANT, buf.data_ptr(), st)
     torch.cuda.synchronize()
     assert rc == 0, lib.nerf_b200_last_error()
 tr = buf[148 * 8:].cpu().tolist()
 pairs = max(tr[100], 1)
-cyc = buf[:148 * 8].view(148, 8)[:, 5].double().mean().item()
+c5 = buf[:148 * 8].view(148, 8)[:, 5].double()
+cyc = c5[c5 > 0].mean().item()
 print(f"sampled tile pairs: {pairs}; kernel cycles per CTA {cyc:.3e}")
 print("weight-slot wait, cycles per tile pair (both sub-tiles), by layer and chunk:")
 tot_w = 0
@@ -52,3 +54,7 @@ print("epilogue of the first warp of each group, accumulator complete -> A opera
 for l in range(8):
     print(f"  layer {l}: {tr[104 + l * 2] / pairs:7.0f} {tr[105 + l * 2] / pairs:7.0f}")
 print(f"  rgb epilogue + next tile's PE: {tr[101] / pairs:7.0f} {tr[102] / pairs:7.0f}")
+if VARIANT == 31:
+    n = 16 * pairs
+    print(f"hidden epilogue of the first warp (mean over 8 layers x 2 groups): body {tr[130] / n:.0f}, proxy + tcgen05 fences "
+          f"{tr[131] / n:.0f}, warp sync + remote arrive {tr[132] / n:.0f} cycles")

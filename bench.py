@@ -305,13 +305,13 @@ def run_ours(args):
                      "frac_note": "can exceed 1: `achieved` counts the reference's multiply-adds (l9 included) while the kernel "
                                   "executes 0.89x of them (executed_frac_of_peak), and `peak` is the sustained cuBLAS figure",
                      # DRAM bytes per launch: ncu --set full measured 135.3 MB read + 255.7 MB written for a
-                     # 19.2 M-row launch of this kernel (profiles/r02_fwd_ncu.txt) = 20.3 B/row, against
+                     # 19.2 M-row launch of this kernel (profiles/r02_fwd_ncu.txt) = 20.4 B/row, against
                      # ~23 B/row algorithmic (depth in, raw out, rays/view term per ray): no re-reads
                      "traffic": NCU_DRAM_BYTES_PER_ROW * kern_rows / max(len(kern), 1),
                      "traffic_unit": "bytes per launch",
                      "traffic_source": "ncu --set full capture of this kernel (profiles/r02_fwd_ncu.txt: dram__bytes_read.sum "
-                                       "+ dram__bytes_write.sum = 20.3 B per row) x rows per launch of this run; not re-measured inside bench.py",
-                     "kernel": "mlp_fwd_kernel",
+                                       "+ dram__bytes_write.sum = 20.4 B per row) x rows per launch of this run; not re-measured inside bench.py",
+                     "kernel": "mlp_fwd_kernel" if os.environ.get("NERF_B200_FWD_PAIRS", "1")[:1] == "0" else "mlp_fwd_pair_kernel",
                      # `achieved` counts the REFERENCE's multiply-adds (593 408 per sample).  The kernel
                      # executes fewer: l9 has no activation and is folded into l10 (csrc/mlp_layout.h), 527 872 per sample
                      "executed_tflops": achieved * EXECUTED_MAC_PER_SAMPLE / 593408.,
@@ -334,7 +334,7 @@ def run_ours(args):
 
 
 EXECUTED_MAC_PER_SAMPLE = 593408 - 65536 - 32768 + 32768     # l9 (256x256) folded into l10[:, :256] (128x256)
-NCU_DRAM_BYTES_PER_ROW = (134.947e6 + 255.647e6) / 19.2e6     # profiles/r02_fwd_ncu.txt
+NCU_DRAM_BYTES_PER_ROW = (136.243e6 + 255.897e6) / 19.2e6     # profiles/r02_fwd_ncu.txt (mlp_fwd_pair_kernel)
 TRAIN_FLOP_PER_RAY = (N_COARSE + N_COARSE + N_FINE) * 2 * (593408 + 593408 + 557696)
 
 

@@ -535,10 +535,12 @@ __host__ __device__ constexpr int chunk_at(int l, bool rev, int idx) {
 //                                                     bit 15  A operand is the PE tile (layouts with PE tiles)
 constexpr int kPlanMaxPairs = 3;
 constexpr int kPlanPerPair = 68;
-struct RingPlan {
-    unsigned short e[kPlanMaxPairs * kPlanPerPair];
+template <int MAXP>
+struct RingPlanT {
+    unsigned short e[MAXP * kPlanPerPair];
     unsigned short period, pad;
 };
+using RingPlan = RingPlanT<kPlanMaxPairs>;
 struct RingPlans {
     RingPlan p[3][2];      // [ring depth - 1][tile parity]
 };
@@ -548,13 +550,14 @@ enum : unsigned {
     kPlanPeChunk = 1u << 10, kPlanFreesBlock0 = 1u << 11, kPlanPeSrc = 1u << 15
 };
 
-constexpr RingPlan make_ring_plan(int ring, bool rev0, bool reuse = true, bool both_forward = false) {
-    RingPlan t{};
+template <int MAXP = kPlanMaxPairs>
+constexpr RingPlanT<MAXP> make_ring_plan(int ring, bool rev0, bool reuse = true, bool both_forward = false) {
+    RingPlanT<MAXP> t{};
     int fifo[8] = {0, 1, 2, 3, 4, 5, 6, 7};
     int head = 0, count = ring;
     int where[5] = {-1, -1, -1, -1, -1};
     t.period = 0;
-    for (int pair = 0; pair < 6; ++pair) {
+    for (int pair = 0; pair < 2 * MAXP; ++pair) {
         int q = 0;
         for (int l = 0; l < kNumMmaLayers; ++l) {
             const int n = layer_chunks(l);
@@ -581,7 +584,7 @@ constexpr RingPlan make_ring_plan(int ring, bool rev0, bool reuse = true, bool b
                                  (idx == n - 1 ? kPlanLast : 0u) | ((l == 5 && c == 0) ? kPlanPeChunk : 0u) |
                                  ((l == 5 && c == 1) ? kPlanFreesBlock0 : 0u) | ((unsigned)a_block << 12) |
                                  ((l == 0 || (l == 5 && c == 0)) ? kPlanPeSrc : 0u);
-                    if (pair < kPlanMaxPairs) t.e[pair * kPlanPerPair + q] = (unsigned short)e;
+                    if (pair < MAXP) t.e[pair * kPlanPerPair + q] = (unsigned short)e;
                     if (release) {
                         fifo[(head + count) & 7] = where[c];
                         ++count;
@@ -615,19 +618,23 @@ static_assert(ring_plans_ok(make_ring_plans()), "the ring plan must repeat withi
 
 __constant__ RingPlans c_ring_plans = make_ring_plans();
 
-// CTA-pair kernel: five 16 KB slots (each CTA stages its half of a chunk).  With five slots the second sub-tile
-// finds EVERY chunk of the layer resident: 34 fills per tile pair, each chunk of the model once.
+// CTA-pair kernel: five 16 KB slots (each CTA stages its half of a chunk).  From five slots on the second
+// sub-tile finds EVERY chunk of the layer resident: 34 fills per tile pair, each chunk of the model once.  (A
+// sixth slot -- two chunks of the next layer fetched ahead instead of one -- measured 1.4 % SLOWER: 3.292e7
+// against 3.246e7 cycles per CTA.)
 constexpr int kPairRing = 5;
+constexpr int kPairPlanMaxPairs = 3;
+using PairPlan = RingPlanT<kPairPlanMaxPairs>;
 struct PairPlans {
-    RingPlan p[2];         // [tile parity]
+    PairPlan p[2];         // [tile parity]
 };
 constexpr PairPlans make_pair_plans() {
     PairPlans r{};
-    for (int par = 0; par < 2; ++par) r.p[par] = make_ring_plan(kPairRing, par != 0);
+    for (int par = 0; par < 2; ++par) r.p[par] = make_ring_plan<kPairPlanMaxPairs>(kPairRing, par != 0);
     return r;
 }
-static_assert(make_pair_plans().p[0].period >= 1 && make_pair_plans().p[0].period <= kPlanMaxPairs &&
-              make_pair_plans().p[1].period >= 1 && make_pair_plans().p[1].period <= kPlanMaxPairs, "pair plan period");
+static_assert(make_pair_plans().p[0].period >= 1 && make_pair_plans().p[0].period <= kPairPlanMaxPairs &&
+              make_pair_plans().p[1].period >= 1 && make_pair_plans().p[1].period <= kPairPlanMaxPairs, "pair plan period");
 __constant__ PairPlans c_pair_plans = make_pair_plans();
 #ifdef NERF_B200_EXPERIMENTS
 constexpr RingPlans make_ring_plans_noreuse() {      // A/B: the same chunk orders, every use copies its chunk again
@@ -1241,17 +1248,20 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
         umma::tmem_alloc_pair(umma::smem_u32(tmem_slot), 512);
         umma::tmem_relinquish_pair();
     }
+    // the plan goes where the device-tail kernels stage their biases (unused here: the tail is in the parameters)
+    constexpr uint32_t kOffPairPlan = kOffBias;
+    static_assert(sizeof(PairPlan) <= 2 * 1024, "pair plan region");
     {
-        const RingPlan& src = c_pair_plans.p[P.tile0 & 1];
-        for (int i = threadIdx.x; i < (int)(sizeof(RingPlan) / 2); i += blockDim.x)
-            reinterpret_cast<unsigned short*>(smem + kOffPlan)[i] = reinterpret_cast<const unsigned short*>(&src)[i];
+        const PairPlan& src = c_pair_plans.p[P.tile0 & 1];
+        for (int i = threadIdx.x; i < (int)(sizeof(PairPlan) / 2); i += blockDim.x)
+            reinterpret_cast<unsigned short*>(smem + kOffPairPlan)[i] = reinterpret_cast<const unsigned short*>(&src)[i];
     }
-    const uint32_t plan_addr = sbase + kOffPlan;
+    const uint32_t plan_addr = sbase + kOffPairPlan;
     umma::tc_fence_before();
     umma::cluster_sync_all();          // barriers of BOTH CTAs initialised before any remote arrive
     umma::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int plan_period = (int)reinterpret_cast<const RingPlan*>(smem + kOffPlan)->period;
+    const int plan_period = (int)reinterpret_cast<const PairPlan*>(smem + kOffPairPlan)->period;
 
     if (warp == 0) {
         // ===================== producer: this CTA's half of every weight chunk =====================
@@ -1449,8 +1459,8 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                 const long long t_epi = esampled ? clock64() : 0;
                 if (esampled && l == kNumMmaLayers - 1) t_rgb = t_epi;
                 if (l < kNumMmaLayers - 1) {
-                    if (half == 0) epilogue_hidden_ct<8, EXP & 7, 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
-                    else epilogue_hidden_ct<8, EXP & 7, 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
+                    if (half == 0) epilogue_hidden_ct<8, EXP & (7 | 64 | 16384), 0>(l, tacc, 0, a_row_addr, swz, sigma, P.ct);
+                    else epilogue_hidden_ct<8, EXP & (7 | 64 | 16384), 128>(l, tacc, 128, a_row_addr, swz, sigma, P.ct);
                     if ((EXP & 2048) && esampled) {
                         // split of the hand-over: epilogue body / proxy + tcgen05 fences / warp sync + remote arrive
                         const long long t1 = clock64();
@@ -1577,6 +1587,8 @@ int launch_fwd_pair(const FwdParams& P, int exp, void* stream) {
     if (exp == 8) k = mlp_fwd_pair_kernel<8>;
     if (exp == 24) k = mlp_fwd_pair_kernel<24>;
     if (exp == 40) k = mlp_fwd_pair_kernel<40>;
+    if (exp == 64) k = mlp_fwd_pair_kernel<64>;
+    if (exp == 16384) k = mlp_fwd_pair_kernel<16384>;
     if (exp != 0 && exp != 2048) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
@@ -1772,6 +1784,8 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
     if (variant == 35) return launch_fwd_pair(P, 5, stream);          // timing: neither loads nor stores
     if (variant == 36) return launch_fwd_pair(P, 24, stream);         // timing: no weight streaming, no per-chunk commits
     if (variant == 37) return launch_fwd_pair(P, 40, stream);         // timing: no weight streaming, per-chunk commits without multicast
+    if (variant == 38) return launch_fwd_pair(P, 16384, stream);      // A/B: 32-column TMEM loads in the hidden epilogue
+    if (variant == 39) return launch_fwd_pair(P, 64, stream);         // A/B: three accumulator buffers in the hidden epilogue
     return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }
 

@@ -1198,7 +1198,8 @@ __global__ void __maxnreg__(112) mlp_fwd_kernel_r112(const __grid_constant__ Fwd
 //              and the output bits -- are those of mlp_fwd_kernel
 //   warp 0     (both CTAs) producer of the CTA's own 16 KB half-chunks: ring of five, plan c_pair_plans
 //   warp 1     leader: MMA issuer (tcgen05.mma.cta_group::2; commits multicast to both CTAs);
-//              peer: relays "my half-chunk has landed" to the leader's w_peer barriers
+//              peer: relays "my half-chunk has landed" to the leader's slot barrier (count 2 there: own copy +
+//              relay, so the issuing warp waits once per fill)
 //   warps 2-17 the two epilogue groups of mlp_fwd_kernel (PE in the A tile, host tail); a warp signals "my part
 //              of the A tile is written" with one arrive on the LEADER's barrier (remote from the peer)
 constexpr uint32_t kPairOffW = kOffPE;                 // no PE tiles: 96 KB for the ring
@@ -1212,6 +1213,8 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = umma::smem_u32(smem);
     if ((sbase & 1023u) != 0) __trap();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = umma::cluster_ctarank();
     constexpr int R = kPairRing;
     const uint32_t bar_w_full = sbase + kOffBar;              // [R] this CTA's half-chunk has landed
     const uint32_t bar_w_empty = bar_w_full + 8 * R;          // [R] the pair's MMAs are done with the slot (multicast commit)
@@ -1219,12 +1222,9 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
     const uint32_t bar_a_ready = bar_w_peer + 8 * R;          // [2] leader only: both CTAs' A tiles written
     const uint32_t bar_acc_full = bar_a_ready + 16;           // [2] accumulators complete (multicast commit)
     const uint32_t bar_pe_free = bar_acc_full + 16;           // [2] l6's MMAs on A block 0 (h5) completed (multicast commit)
-    const uint32_t bar_unused = bar_pe_free + 16;             // takes the commits of chunks that keep their slot
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (3 * R + 7));
-    static_assert(8 * (3 * R + 7) + 4 <= 256, "barrier region");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * (3 * R + 6));
+    static_assert(8 * (3 * R + 6) + 4 <= 256, "barrier region");
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = umma::cluster_ctarank();
     const long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
     const long n_quads = (n_tiles + 3) / 4;
@@ -1232,11 +1232,12 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < R; ++s) {
-            umma::mbar_init(bar_w_full + 8 * s, 1);
+            // leader: the slot is full when its own copy has landed (producer's arrive + bytes) AND the peer's
+            // relay has arrived: one barrier, one wait per fill in the issuing warp
+            umma::mbar_init(bar_w_full + 8 * s, (rank == 0 && !(EXP & (1 << 18))) ? 2 : 1);
             umma::mbar_init(bar_w_empty + 8 * s, 1);
             umma::mbar_init(bar_w_peer + 8 * s, 1);
         }
-        umma::mbar_init(bar_unused, 1);
         for (int g = 0; g < 2; ++g) {
             umma::mbar_init(bar_a_ready + 8 * g, 2 * kEpiWarpsPerGroup);   // one arrive per warp and CTA
             umma::mbar_init(bar_acc_full + 8 * g, 1);
@@ -1298,7 +1299,7 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
             // ===================== peer: relay slot arrivals to the leader =====================
             uint32_t parity = 0;
             int pp = 0;
-            const uint32_t leader_w_peer = umma::map_to_cta(bar_w_peer, 0);
+            const uint32_t leader_w_peer = umma::map_to_cta((EXP & (1 << 18)) ? bar_w_peer : bar_w_full, 0);
             for (long quad = cluster_id; quad < n_quads; quad += n_clusters) {
                 uint32_t q_addr = plan_addr + (uint32_t)pp * (kPlanPerPair * 2);
                 for (int i = 0; i < kPlanPerPair; ++i, q_addr += 2) {
@@ -1343,51 +1344,51 @@ mlp_fwd_pair_kernel(const __grid_constant__ FwdParams P) {
                     const int l = seg >> 1;
                     const uint32_t g = (uint32_t)seg & 1u;
                     const uint32_t d_base = tmem_u + g * 256;
-                    const uint32_t idesc = layer_halves(l) == 2 ? kIdescPairN256 : kIdescPairN128;
                     const uint32_t a_seg = a_lo0 + g * (65536 >> 4);
-                    {
+                    const uint32_t u_a_ready = bars_u + 8 * (3 * R) + 8 * g, u_acc_full = u_a_ready + 16, u_pe_free = u_a_ready + 32;
+                    const uint32_t idesc = layer_halves(l) == 2 ? kIdescPairN256 : kIdescPairN128;
+                    // waits until sub-tile g's A operand is written (and its accumulator read)
+                    auto wait_a = [&]() {
                         const long long t0 = sampled ? clock64() : 0;
-                        wait(bars_u + 8 * (3 * R) + 8 * g, (n_ready >> g) & 1u);          // bar_a_ready[g]
+                        wait(u_a_ready, (n_ready >> g) & 1u);
                         if (sampled && issuer) atomicAdd((unsigned long long*)P.trace_out + 64 + l * 2 + g, (unsigned long long)(clock64() - t0));
                         n_ready ^= 1u << g;
                         umma::tc_fence_after();
-                    }
+                    };
+                    wait_a();
                     uint32_t accumulate = 0u;
                     bool last;
 #pragma unroll 1
                     do {
                         q_addr += 2;
+                        // the next entry is fetched under this chunk's MMAs (the last fetch reads the pad word)
                         const uint32_t e_next = uniform(umma::ld_shared_u16(q_addr));
                         const uint32_t slot = (e >> kPlanSlotShift) & kPlanSlotMask;
                         const uint32_t b_lo = w_lo + slot * (kStageBytes >> 4);
                         const uint32_t a_lo = a_seg + ((e >> 12) & 3u) * (16384 >> 4);
-                        const uint32_t release_bar = (e & kPlanRelease) ? bars_u + 8 * R + 8 * slot : bars_u + 8 * (3 * R + 6);   // bar_w_empty[slot] / bar_unused
-                        const uint32_t ph_full = (parity >> slot) & 1u;
+                        const uint32_t release_bar = ((e & kPlanRelease) && !(EXP & 16)) ? bars_u + 8 * R + 8 * slot : 0u;   // bar_w_empty[slot]
                         last = (e & kPlanLast) != 0;
-                        if (e & kPlanPeChunk) {
-                            // l6: both CTAs have restored the PE block into block 0 of their A tiles
-                            wait(bars_u + 8 * (3 * R) + 8 * g, (n_ready >> g) & 1u);
-                            n_ready ^= 1u << g;
-                            umma::tc_fence_after();
-                        }
-                        if ((e & kPlanFirstUse) && !(EXP & 8)) {
+                        if (e & kPlanPeChunk) wait_a();      // l6: both CTAs have restored the PE block into block 0 of their A tiles
+                        if (e & kPlanFirstUse) {
+                            const uint32_t ph_full = (parity >> slot) & 1u;
                             parity ^= 1u << slot;
-                            const long long t1 = sampled ? clock64() : 0;
-                            wait(bars_u + 8 * slot, ph_full);                  // own half: bar_w_full[slot]
-                            wait(bars_u + 8 * (2 * R) + 8 * slot, ph_full);    // the peer's half: bar_w_peer[slot]
-                            if (sampled && issuer) {
-                                atomicAdd((unsigned long long*)P.trace_out + l * 5 + (e & 7u), (unsigned long long)(clock64() - t1));
-                                if (seg == 0) atomicAdd((unsigned long long*)P.trace_out + 100, 1ull);
+                            if (!(EXP & 8)) {
+                                const long long t1 = sampled ? clock64() : 0;
+                                wait(bars_u + 8 * slot, ph_full);                  // bar_w_full[slot]: own half landed + the peer's relay
+                                if (EXP & (1 << 18)) wait(bars_u + 8 * (2 * R) + 8 * slot, ph_full);    // (A/B: the relay on a barrier of its own)
+                                if (sampled && issuer) {
+                                    atomicAdd((unsigned long long*)P.trace_out + l * 5 + (e & 7u), (unsigned long long)(clock64() - t1));
+                                    if (seg == 0) atomicAdd((unsigned long long*)P.trace_out + 100, 1ull);
+                                }
                             }
                         }
-                        // four MMAs, the slot's release (or a barrier nobody waits on) and, after the chunk that frees
-                        // A block 0 in l6, bar_pe_free[g]
+                        // four MMAs, the slot's release and, after the chunk that frees A block 0 in l6, bar_pe_free[g]
                         umma::mma_chunk_pair_elect(d_base, a_lo, b_lo, kDescHi, idesc, accumulate, release_bar,
-                                                   (e & kPlanFreesBlock0) ? bars_u + 8 * (3 * R + 4) + 8 * g : 0u);
+                                                   (e & kPlanFreesBlock0) ? u_pe_free : 0u);
                         accumulate = 1u;
                         e = e_next;
                     } while (!last);
-                    umma::mma_commit_pair_elect(bars_u + 8 * (3 * R + 2) + 8 * g);      // bar_acc_full[g]
+                    umma::mma_commit_pair_elect(u_acc_full);
                 }
                 if (++pp == plan_period) pp = 0;
             }
@@ -1589,6 +1590,7 @@ int launch_fwd_pair(const FwdParams& P, int exp, void* stream) {
     if (exp == 40) k = mlp_fwd_pair_kernel<40>;
     if (exp == 64) k = mlp_fwd_pair_kernel<64>;
     if (exp == 16384) k = mlp_fwd_pair_kernel<16384>;
+    if (exp == (1 << 18)) k = mlp_fwd_pair_kernel<(1 << 18)>;
     if (exp != 0 && exp != 2048) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
@@ -1772,7 +1774,7 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
         P.trace_out = stats_out + 148 * 8;
         variant -= 1000;
     }
-    if (variant == 9 || variant == 10 || (variant >= 13 && variant <= 23) || (variant >= 30 && variant <= 39)) {   // host-tail kernels
+    if (variant == 9 || variant == 10 || (variant >= 13 && variant <= 23) || (variant >= 30 && variant <= 45)) {   // host-tail kernels
         cudaError_t e = cudaMemcpy(&P.ct, (const uint8_t*)packed + kWeightBytes, sizeof(ConstTail), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return (int)e;
     }
@@ -1786,6 +1788,7 @@ extern "C" int nerf_mlp_fwd_stats(const void* packed, const float* rays, const f
     if (variant == 37) return launch_fwd_pair(P, 40, stream);         // timing: no weight streaming, per-chunk commits without multicast
     if (variant == 38) return launch_fwd_pair(P, 16384, stream);      // A/B: 32-column TMEM loads in the hidden epilogue
     if (variant == 39) return launch_fwd_pair(P, 64, stream);         // A/B: three accumulator buffers in the hidden epilogue
+    if (variant == 45) return launch_fwd_pair(P, 1 << 18, stream);            // A/B: the peer's relay on a barrier of its own (two waits per fill)
     return launch_fwd(P, variant < 1 ? 1 : variant, stream);
 }
 

@@ -399,18 +399,19 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
 // advance by 2 = 32 bytes) and up to two multicast commits, all predicated on an elected lane INSIDE the block.
 // Executed by a whole converged warp with warp-uniform operands: no branch around the tensor instructions, so the
 // compiler emits UIADD3 / UTCHMMA / UTCBAR with a uniform predicate and no divergence bookkeeping.
-// commit2_bar = 0: no second commit.
+// commit_bar / commit2_bar = 0: no such commit.
 __device__ __forceinline__ void mma_chunk_pair_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
                                                      uint32_t idesc, uint32_t accumulate, uint32_t commit_bar,
                                                      uint32_t commit2_bar) {
     asm volatile(
         "{\n"
-        ".reg .pred pe, pacc, ptrue, pc2;\n"
+        ".reg .pred pe, pacc, ptrue, pc1, pc2;\n"
         ".reg .b64 da, db;\n"
         ".reg .b32 al, bl;\n"
         "elect.sync _|pe, 0xffffffff;\n"
         "setp.ne.b32 pacc, %5, 0;\n"
         "setp.eq.b32 ptrue, 0, 0;\n"
+        "setp.ne.and.b32 pc1, %6, 0, pe;\n"
         "setp.ne.and.b32 pc2, %7, 0, pe;\n"
         "mov.b64 da, {%1, %3};\n"
         "mov.b64 db, {%2, %3};\n"
@@ -430,7 +431,7 @@ __device__ __forceinline__ void mma_chunk_pair_elect(uint32_t d_tmem, uint32_t a
         "mov.b64 da, {al, %3};\n"
         "mov.b64 db, {bl, %3};\n"
         "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, ptrue;\n"
-        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %8;\n"
+        "@pc1 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %8;\n"
         "@pc2 tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %8;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate), "r"(commit_bar), "r"(commit2_bar), "h"((uint16_t)3)

@@ -1567,12 +1567,13 @@ FwdKernel fwd_variant(int v) {
     }
 }
 
-// CTA-pair kernel: clusters of two CTAs, one cluster per TPC.  Returns NERF_ERR_UNSUPPORTED-like negative
-// codes through arg_error only for real errors; the caller falls back to nothing (there is no other path
-// for `variant`), so a device that cannot co-schedule the clusters reports the launch error.
+// CTA-pair kernel: clusters of two CTAs, one cluster per TPC.  kPairsUnavailable: the device cannot keep a
+// single two-CTA cluster of this kernel resident (the occupancy query says so once per device); the caller then
+// runs mlp_fwd_kernel, which computes the same bits.
+constexpr int kPairsUnavailable = -1000;
 int launch_fwd_pair(const FwdParams& P, int exp, void* stream) {
     constexpr int kMaxDevices = 64;
-    static int max_clusters[kMaxDevices] = {};
+    static int max_clusters[kMaxDevices] = {};      // 0 not asked yet, -1 unavailable
     int dev = 0;
     cudaError_t e0 = cudaGetDevice(&dev);
     if (e0 != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
@@ -1613,7 +1614,11 @@ int launch_fwd_pair(const FwdParams& P, int exp, void* stream) {
             cfg.attrs = &attr;
             cfg.numAttrs = 1;
             e = cudaOccupancyMaxActiveClusters(&n, mlp_fwd_pair_kernel<0>, &cfg);
-            if (e == cudaSuccess && n < 1) n = sm_count / 2;
+            if (e != cudaSuccess || n < 1) {       // no room for a cluster (or no cluster launch at all): not an error
+                (void)cudaGetLastError();
+                e = cudaSuccess;
+                n = -1;
+            }
         }
         if (e != cudaSuccess) {
             nerf::set_last_error("nerf_mlp_fwd (CTA pairs) setup: %s", cudaGetErrorString(e));
@@ -1621,6 +1626,7 @@ int launch_fwd_pair(const FwdParams& P, int exp, void* stream) {
         }
         max_clusters[dev] = n;
     }
+    if (max_clusters[dev] < 0) return kPairsUnavailable;
     const long n_tiles = (P.M + kTileM - 1) / kTileM;
     const long n_quads = (n_tiles + 3) / 4;
     const long clusters = n_quads < max_clusters[dev] ? n_quads : max_clusters[dev];
@@ -1735,13 +1741,17 @@ extern "C" int nerf_mlp_fwd_host_tail(const void* packed, const void* host_tail,
     if (M == 0) return 0;
     memcpy(&P.ct, host_tail, sizeof(ConstTail));
     // The CTA-pair kernel (tcgen05 cta_group::2) is the production inference kernel; mlp_fwd_kernel produces the
-    // same bits and stays selectable for A/B runs (NERF_B200_FWD_PAIRS=0) and for devices that cannot
-    // co-schedule two-CTA clusters.
+    // same bits, stays selectable for A/B runs (NERF_B200_FWD_PAIRS=0) and takes over by itself on a device
+    // that cannot co-schedule two-CTA clusters of this size.
     static const bool use_pairs = [] {
         const char* v = getenv("NERF_B200_FWD_PAIRS");
         return !(v && v[0] == '0');
     }();
-    return use_pairs ? launch_fwd_pair(P, 0, stream) : launch_fwd(P, 9, stream);
+    if (use_pairs) {
+        rc = launch_fwd_pair(P, 0, stream);
+        if (rc != kPairsUnavailable) return rc;
+    }
+    return launch_fwd(P, 9, stream);
 }
 
 // Test-support entry: additionally dumps the FP32 post-activation output of MMA layer

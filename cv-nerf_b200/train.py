@@ -126,7 +126,6 @@ class TrainStep:
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.side = torch.cuda.Stream(device=dev)      # small gradient kernels next to the dW kernel
         self.profile = None                            # a list collects (start, after backward, after update) events per step
-        self.side2 = torch.cuda.Stream(device=dev)                    # second persistent-kernel stream (schedules 3, 4)
 
     def crop_window(self, precrop_frac=None):
         """Pre-crop window of main.py:354-361 as (row0, col0, rows, cols)."""
@@ -202,6 +201,11 @@ class TrainStep:
                 side.wait_stream(main)
                 K.viewdir_term_bwd(dz, rows, rays, s, False, self.blob[idx], stream=side)
                 K.mlp_bwd_dw(act, dz, rows, self.blob[idx])
+                if idx == 0:
+                    # the coarse network's unfold (below) needs its dW and view-column kernels only: it runs on
+                    # the side stream under the fine network's dZ chain
+                    side.wait_stream(main)
+                    K.mlp_bwd_unfold(self.blob[0], self.params[0], stream=side)
         else:
             for idx, net, graw, act, rows, s, dz in jobs:
                 K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=dz)
@@ -210,7 +214,8 @@ class TrainStep:
         # l9 is folded into l10 (csrc/mlp_layout.h): its gradients and those of l10's first 256 columns
         # follow from the G = dZ10^T h8 the dW kernel left in the blob and from db10 (view-column kernel)
         for idx in range(2):
-            K.mlp_bwd_unfold(self.blob[idx], self.params[idx])
+            if idx == 1 or sched != 2:
+                K.mlp_bwd_unfold(self.blob[idx], self.params[idx])
         return self.loss
 
     @torch.no_grad()

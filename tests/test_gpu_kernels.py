@@ -303,3 +303,35 @@ def test_field_kernel_variants_agree(rows, S):
     # host tail, activation-saving, probe -- all compared above).  The round-1 design alternatives (CTA
     # pairs, TS form, mixed orientation) left the tree when l9 was folded into l10; the remaining A/B
     # variants of the experiments build are compared bit for bit by tools/gpu_diag.py --ab.
+
+
+@pytest.mark.parametrize("cut_tiles", [1, 2, 5, 8])
+def test_field_row_shards_are_bit_identical(cut_tiles):
+    """A row range split at a multiple of 128 rows and computed by two launches that pass `row0` equals
+    the one-launch result bit for bit, on both field kernels (the K-chunk order of a row follows the parity
+    of its GLOBAL 128-row tile: csrc/mlp_fwd.cu chunk_at); model.py:110-131 chunks the same way with
+    identical results."""
+    K = _K()
+    torch.manual_seed(7)
+    p, _ = O.init_field_params(2, 1.0, 5.0)
+    from cv_nerf_b200.model import Model
+    net = load_model_params(Model(), p).to(DEV)
+    packed = net.packed()
+    ht = K.model_host_tail(packed)
+    S = 64
+    rows = 128 * 13 + 40
+    n_rays = (rows + S - 1) // S
+    pts = (torch.rand(rows, 3) * 2 - 1).to(DEV)
+    dirs = torch.nn.functional.normalize(torch.randn(n_rays, 3), dim=-1).to(DEV)
+    vt_full = K.viewdir_term(packed, dirs)                       # [n_rays, 128]
+    vt_rows = vt_full.repeat_interleave(S, dim=0)[:rows].contiguous()   # one view term per row: any cut is valid
+    cut = 128 * cut_tiles
+    for tail in (None, ht):                                      # single-CTA kernel / CTA-pair kernel
+        whole = K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, 1, vt_rows, 1, host_tail=tail)
+        a = K.mlp_fwd(packed, K.IN_POINTS, pts[:cut].contiguous(), None, cut, 1, vt_rows[:cut].contiguous(), 1, host_tail=tail)
+        b = K.mlp_fwd(packed, K.IN_POINTS, pts[cut:].contiguous(), None, rows - cut, 1, vt_rows[cut:].contiguous(), 1,
+                      host_tail=tail, row0=cut)
+        assert torch.equal(torch.cat([a, b]), whole), (torch.cat([a, b]) - whole).abs().max().item()
+    # and the two kernels agree with each other
+    assert torch.equal(K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, 1, vt_rows, 1, host_tail=ht),
+                       K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, 1, vt_rows, 1))

@@ -335,3 +335,32 @@ def test_field_row_shards_are_bit_identical(cut_tiles):
     # and the two kernels agree with each other
     assert torch.equal(K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, 1, vt_rows, 1, host_tail=ht),
                        K.mlp_fwd(packed, K.IN_POINTS, pts, None, rows, 1, vt_rows, 1))
+
+
+def test_pair_kernel_repeats_bit_identically():
+    """The CTA-pair kernel hands operands and accumulators between two SMs (remote mbarrier arrives with
+    CTA-scope release, multicast commits); a missing ordering would show as a rare wrong tile.  Twenty-five
+    launches over several waves of tile quads must all equal the single-CTA kernel's output bit for bit."""
+    K = _K()
+    torch.manual_seed(11)
+    p, _ = O.init_field_params(2, 1.0, 5.0)
+    from cv_nerf_b200.model import Model
+    net = load_model_params(Model(), p).to(DEV)
+    packed = net.packed()
+    ht = K.model_host_tail(packed)
+    S = 192
+    n_rays = 6000                                            # 1.15 M rows = 2250 tile quads: ~30 per cluster
+    rows = n_rays * S
+    rays = torch.zeros(n_rays, 11, device=DEV)
+    rays[:, 0:3] = torch.randn(n_rays, 3, device=DEV) * .3
+    rays[:, 3:6] = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV), dim=-1)
+    rays[:, 6], rays[:, 7] = 2., 6.
+    rays[:, 8:11] = rays[:, 3:6]
+    z = K.sample_coarse(rays, S)
+    vt = K.viewdir_term(packed, rays)
+    ref = K.mlp_fwd(packed, K.IN_RAYS, rays, z, rows, S, vt, S)              # single-CTA kernel, device tail
+    bad = 0
+    for _ in range(25):
+        out = K.mlp_fwd(packed, K.IN_RAYS, rays, z, rows, S, vt, S, host_tail=ht)
+        bad += int(not torch.equal(out, ref))
+    assert bad == 0, f"{bad} of 25 launches differ"

@@ -1,8 +1,10 @@
 """GPU diagnostics for the fused field kernel (run on the B200 box):
-    python tools/gpu_diag.py [--rows 1000] [--time]
-Prints per-layer error statistics of the kernel's probe output against the CPU emulation of the
-same rounding points, with enough structure (worst rows / columns) to localise layout bugs, and
-optionally times the kernel on a lego-400x400-sized workload."""
+    python tools/gpu_diag.py --time                 times both field kernels on a lego-sized workload
+    python tools/gpu_diag.py --ab 9,30 [--rounds N] interleaved A/B of debug-entry variants (experiments build):
+                                                    milliseconds, cycles per CTA, bit-identity against the first
+    python tools/gpu_diag.py --stats                wait fractions of the probe build
+The per-layer error report against the CPU emulation of the kernel's rounding points lives with the tests
+(python tests/diag_field_layers.py): only tests may use the oracle."""
 import argparse
 import os
 import sys
@@ -13,59 +15,18 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import nerf_oracle as O                      # noqa: E402  (diagnostics only)
-from tests.helpers import emulate_field, vterm_reference   # noqa: E402
 import cv_nerf_b200                                       # noqa: E402
+from cv_nerf_b200.model import Model                      # noqa: E402
 
 K = cv_nerf_b200.kernels
 DEV = "cuda"
 
 
 def packed_model(seed=0):
-    coarse, _ = O.init_field_params(seed, 1.0, 5.0)
-    order = ("l1", "l2", "l3", "l4", "l5", "l6", "l7", "l8", "l9", "l_alpha", "l10", "l11")
-    params = []
-    for n in order:
-        params += [coarse[n + ".weight"].to(DEV), coarse[n + ".bias"].to(DEV)]
-    return coarse, K.pack_model(params)
-
-
-def layer_report(rows):
-    p, packed = packed_model()
-    gen = torch.Generator().manual_seed(rows)
-    pts = torch.randn(rows, 3, generator=gen) * 2.
-    dirs = torch.nn.functional.normalize(torch.randn(rows, 3, generator=gen), dim=-1)
-    x = torch.cat([O.freq_encode(pts, 10), O.freq_encode(dirs, 4)], -1)
-    vt = vterm_reference(p, dirs)
-    xd = x.to(DEV).contiguous()
-    vtd = K.viewdir_term(packed, x[:, 63:].contiguous().to(DEV), embedded=True)
-    print(f"vterm max err {(vtd.cpu() - vt).abs().max().item():.3e}")
-    ok = True
-    for layer in range(9):
-        raw, probe = K.mlp_fwd(packed, K.IN_EMBEDDED, xd, None, rows, 1, vtd, 1, in_stride=90, probe_layer=layer)
-        torch.cuda.synchronize()
-        want_raw, want = emulate_field(p, x[:, :63], vt, probe=layer)
-        width = want.shape[1]
-        got = probe.cpu()[:, :width]
-        err = (got - want).abs()
-        print(f"layer {layer}: max err {err.max().item():.3e}  mean err {err.mean().item():.3e}  "
-              f"max|want| {want.abs().max().item():.3f}  nan {int(torch.isnan(got).sum())}")
-        if err.max().item() > 2e-3 or torch.isnan(got).any():
-            ok = False
-            row_err, col_err = err.amax(1), err.amax(0)
-            bad_rows = (row_err > 2e-3).nonzero().flatten()
-            bad_cols = (col_err > 2e-3).nonzero().flatten()
-            print(f"   bad rows {bad_rows.numel()}/{rows}: first {bad_rows[:16].tolist()}")
-            print(f"   bad cols {bad_cols.numel()}/{width}: first {bad_cols[:32].tolist()}")
-            r = int(row_err.argmax())
-            print(f"   worst row {r}: got {got[r, :8].tolist()}")
-            print(f"                want {want[r, :8].tolist()}")
-            break
-    raw_err = (raw.cpu() - want_raw).abs()
-    print(f"raw: max err {raw_err.max().item():.3e} per-channel {raw_err.amax(0).tolist()}")
-    ref = O.field_mlp(p, x)
-    print(f"raw vs fp32 reference: max {(raw.cpu() - ref).abs().max().item():.3e}")
-    return ok
+    """A default-initialised field network (the reference's nn.Linear init) and its packed blob."""
+    torch.manual_seed(seed)
+    net = Model().to(DEV)
+    return net, net.packed()
 
 
 def timing():
@@ -107,6 +68,9 @@ def ab(variants, rounds=6):
     a process, so variants are timed round-robin and averaged)."""
     from cv_nerf_b200 import _lib
     lib = _lib.load()
+    if not _lib.has_experiments():
+        sys.exit("needs the experiments build: make -C cv-nerf_b200/csrc experiments && "
+                 "NERF_B200_LIB=$PWD/cv-nerf_b200/libnerf_b200_exp.so python tools/gpu_diag.py ...")
     p, packed = packed_model()
     n_rays, S = 160000, 192
     rays = torch.zeros(n_rays, 11, device=DEV)
@@ -154,6 +118,9 @@ def pipeline_stats(variants=(9, 15, 16, 14)):
     """Per-role wait-cycle breakdown of the field kernel (debug entry nerf_mlp_fwd_stats)."""
     from cv_nerf_b200 import _lib
     lib = _lib.load()
+    if not _lib.has_experiments():
+        sys.exit("needs the experiments build: make -C cv-nerf_b200/csrc experiments && "
+                 "NERF_B200_LIB=$PWD/cv-nerf_b200/libnerf_b200_exp.so python tools/gpu_diag.py ...")
     p, packed = packed_model()
     n_rays, S = 160000, 192
     rays = torch.zeros(n_rays, 11, device=DEV)
@@ -199,7 +166,6 @@ def pipeline_stats(variants=(9, 15, 16, 14)):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rows", type=int, default=1000)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--stats", action="store_true")
     ap.add_argument("--ab", type=str, default="", help="comma-separated debug-entry variants to time round-robin")
@@ -211,9 +177,8 @@ if __name__ == "__main__":
     if a.stats:
         pipeline_stats()
         sys.exit(0)
-    t = time.time()
     print("device:", torch.cuda.get_device_name(0), "SMs", cv_nerf_b200._lib.load().nerf_b200_sm_count())
-    ok = layer_report(128) and layer_report(a.rows)
-    print("LAYERS", "OK" if ok else "FAILED", f"({time.time() - t:.1f}s)")
-    if a.time and ok:
+    if a.time:
         timing()
+    else:
+        print("nothing to do: --time, --ab or --stats (per-layer error report: python tests/diag_field_layers.py)")

@@ -14,6 +14,9 @@ from tools.gpu_diag import packed_model, DEV  # noqa: E402
 
 variant = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 lib = _lib.load()
+if not _lib.has_experiments():
+    sys.exit("needs the experiments build: make -C cv-nerf_b200/csrc experiments && "
+             "NERF_B200_LIB=$PWD/cv-nerf_b200/libnerf_b200_exp.so python " + sys.argv[0])
 p, packed = packed_model()
 n_rays, S = 160000, 192
 rays = torch.zeros(n_rays, 11, device=DEV)

@@ -13,6 +13,9 @@ from cv_nerf_b200 import _lib, kernels as K  # noqa: E402
 from tools.gpu_diag import packed_model, DEV  # noqa: E402
 
 lib = _lib.load()
+if not _lib.has_experiments():
+    sys.exit("needs the experiments build: make -C cv-nerf_b200/csrc experiments && "
+             "NERF_B200_LIB=$PWD/cv-nerf_b200/libnerf_b200_exp.so python " + sys.argv[0])
 VARIANT = int(sys.argv[1]) if len(sys.argv) > 1 else 18     # 18: mlp_fwd_kernel, 31: the CTA-pair kernel
 p, packed = packed_model()
 n_rays, S = 160000, 192

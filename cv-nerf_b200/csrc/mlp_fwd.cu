@@ -1580,8 +1580,9 @@ int launch_fwd_pair(const FwdParams& P, int exp, void* stream) {
         nerf::set_last_error("nerf_mlp_fwd (CTA pairs) setup: %s", e0 != cudaSuccess ? cudaGetErrorString(e0) : "device index");
         return e0 != cudaSuccess ? (int)e0 : NERF_ERR_UNSUPPORTED;
     }
-    FwdKernel k = exp == 2048 ? mlp_fwd_pair_kernel<2048> : mlp_fwd_pair_kernel<0>;
+    FwdKernel k = mlp_fwd_pair_kernel<0>;
 #ifdef NERF_B200_EXPERIMENTS
+    if (exp == 2048) k = mlp_fwd_pair_kernel<2048>;      // + sampled wait profile
     // timing-only variants (wrong numerics): bit0 no A-tile stores, bit2 no TMEM loads, bit3 no weight streaming
     if (exp == 1) k = mlp_fwd_pair_kernel<1>;
     if (exp == 4) k = mlp_fwd_pair_kernel<4>;
@@ -1592,14 +1593,15 @@ int launch_fwd_pair(const FwdParams& P, int exp, void* stream) {
     if (exp == 64) k = mlp_fwd_pair_kernel<64>;
     if (exp == 16384) k = mlp_fwd_pair_kernel<16384>;
     if (exp == (1 << 18)) k = mlp_fwd_pair_kernel<(1 << 18)>;
-    if (exp != 0 && exp != 2048) {
+    if (exp != 0) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
     }
+#else
+    if (exp != 0) return nerf::arg_error("nerf_mlp_fwd (CTA pairs): variant");
 #endif
     if (max_clusters[dev] == 0) {
         cudaError_t e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fwd_pair_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         int sm_count = 0, n = 0;
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) {

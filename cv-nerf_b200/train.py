@@ -126,6 +126,7 @@ class TrainStep:
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.side = torch.cuda.Stream(device=dev)      # small gradient kernels next to the dW kernel
         self.profile = None                            # a list collects (start, after backward, after update) events per step
+        self._early_done = False                       # forward_backward(early_update=True) has updated the coarse network
 
     def crop_window(self, precrop_frac=None):
         """Pre-crop window of main.py:354-361 as (row0, col0, rows, cols)."""
@@ -135,9 +136,12 @@ class TrainStep:
         return (self.h // 2 - dh, self.w // 2 - dw, 2 * dh, 2 * dw)
 
     @torch.no_grad()
-    def forward_backward(self, rays, target, draws=None):
+    def forward_backward(self, rays, target, draws=None, early_update=False):
         """rays [n,11], target [n,3] -> loss tensor; gradients of both networks accumulated into
-        self.blob (zeroed first).  ``draws``: main.RenderDraws with injected random numbers."""
+        self.blob (zeroed first).  ``draws``: main.RenderDraws with injected random numbers.
+        ``early_update`` (used by step()): the coarse network's gradient exchange, Adam step and re-pack run
+        on the side stream as soon as its gradients are complete, under the fine network's dZ / dW kernels;
+        apply_gradients() then finishes with the fine network."""
         n = rays.shape[0]
         if n > self.n_rays:
             raise NerfB200Error(f"TrainStep was sized for {self.n_rays} rays per step, got {n}")
@@ -206,6 +210,10 @@ class TrainStep:
                     # the side stream under the fine network's dZ chain
                     side.wait_stream(main)
                     K.mlp_bwd_unfold(self.blob[0], self.params[0], stream=side)
+                    if early_update:
+                        with torch.cuda.stream(side):
+                            self._update_net(0, self.it + 1, True)
+                        self._early_done = True
         else:
             for idx, net, graw, act, rows, s, dz in jobs:
                 K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=dz)
@@ -218,33 +226,48 @@ class TrainStep:
                 K.mlp_bwd_unfold(self.blob[idx], self.params[idx])
         return self.loss
 
-    @torch.no_grad()
-    def apply_gradients(self, allreduce=True):
-        """all-reduce (data parallel), Adam from the blobs, weight re-pack, learning-rate decay."""
-        self.it += 1
+    def _update_net(self, idx, it, allreduce):
+        """Gradient exchange (data parallel), Adam from the blob and re-pack of network idx (0 coarse, 1 fine)
+        on the CURRENT stream.  Peer path: barrier (all ranks' blobs of this network written), one launch that
+        reads every rank's blob over NVLink, barrier (the blobs may be zeroed for the next step); every
+        network has its own pair of barrier channels, so the two updates may run on different streams."""
+        dev = self.dev
         if self.world > 1 and allreduce and self.symm is not None:
-            # fused exchange + Adam over peer memory: barrier (all blobs written), one launch per
-            # network reading every rank's blob, barrier (blobs may be zeroed for the next step)
-            stream = torch.cuda.current_stream(self.dev).cuda_stream
+            stream = torch.cuda.current_stream(dev).cuda_stream
             g_bytes = self.blob.shape[1] * 4
-            self.symm.barrier(channel=0)
-            for idx in range(2):
-                peers = [int(ptr) + idx * g_bytes for ptr in self.symm.buffer_ptrs]
-                K.adam_step_blob_peers(peers, [p.data for p in self.params[idx]], self.m[idx], self.v[idx], self.lr,
-                                       self.betas, self.eps, self.it, 1. / self.world, stream)
-            self.symm.barrier(channel=1)
+            self.symm.barrier(channel=2 * idx)
+            peers = [int(ptr) + idx * g_bytes for ptr in self.symm.buffer_ptrs]
+            K.adam_step_blob_peers(peers, [p.data for p in self.params[idx]], self.m[idx], self.v[idx], self.lr,
+                                   self.betas, self.eps, it, 1. / self.world, stream)
+            self.symm.barrier(channel=2 * idx + 1)
         else:
             if self.world > 1 and allreduce:
-                torch.distributed.all_reduce(self.blob, group=self.pg)
+                torch.distributed.all_reduce(self.blob[idx], group=self.pg)
+            # without a reduction the blob holds this rank's own mean gradient: no 1/world
+            K.adam_step_blob(self.blob[idx], [p.data for p in self.params[idx]], self.m[idx], self.v[idx],
+                             self.lr, self.betas, self.eps, it,
+                             grad_scale=1. / self.world if allreduce else 1.)
+        net = self.coarse if idx == 0 else self.fine
+        buf = net.packed_buffers()
+        K.pack_models_train([self.params[idx]], [buf[0]], [buf[1]])
+
+    @torch.no_grad()
+    def apply_gradients(self, allreduce=True):
+        """all-reduce (data parallel), Adam from the blobs, weight re-pack, learning-rate decay -- for the
+        networks forward_backward(early_update=True) has not already updated."""
+        self.it += 1
+        early, self._early_done = self._early_done, False
+        if early or (self.world > 1 and allreduce):
+            for idx in ((1,) if early else (0, 1)):
+                self._update_net(idx, self.it, allreduce)
+        else:
             for idx in range(2):
-                # without a reduction the blob holds this rank's own mean gradient: no 1/world
                 K.adam_step_blob(self.blob[idx], [p.data for p in self.params[idx]], self.m[idx], self.v[idx],
-                                 self.lr, self.betas, self.eps, self.it,
-                                 grad_scale=1. / self.world if allreduce else 1.)
+                                 self.lr, self.betas, self.eps, self.it, grad_scale=1.)
+            # re-pack both networks' forward and transposed blobs in one launch
+            bufs = [net.packed_buffers() for net in (self.coarse, self.fine)]
+            K.pack_models_train(self.params, [b[0] for b in bufs], [b[1] for b in bufs])
         _model.bump_param_epoch()
-        # re-pack both networks' forward and transposed blobs in one launch
-        bufs = [net.packed_buffers() for net in (self.coarse, self.fine)]
-        K.pack_models_train(self.params, [b[0] for b in bufs], [b[1] for b in bufs])
         self.coarse.mark_packed(); self.fine.mark_packed()
         # main.py:392-394: the decayed rate takes effect from the next iteration on
         self.lr = decayed_learning_rate(self.it, self.lr_decay * 1000, self.lr0)
@@ -258,7 +281,7 @@ class TrainStep:
         if prof is not None:        # bench.py: CUDA events around the two halves of the step (no synchronisation here)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
-        loss = self.forward_backward(rays, target, draws)
+        loss = self.forward_backward(rays, target, draws, early_update=True)
         if prof is not None:
             ev[1].record()
         self.apply_gradients()

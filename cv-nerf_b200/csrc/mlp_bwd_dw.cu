@@ -234,22 +234,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_dw_kernel(const __grid_co
     }
 }
 
-// Deterministic mode, second launch: every blob element adds its CTAs' partial sums in CTA order.
+// Deterministic mode, second launch: every blob element adds its CTAs' partial sums in CTA order.  Four
+// consecutive columns per thread (16-byte loads; every partial of an element is an independent load, only the
+// additions are ordered): the launch is latency-bound, 56 us with one scalar element per thread.
 __global__ void __launch_bounds__(256) dw_reduce_kernel(const __grid_constant__ DwParams P) {
     const LayerJob& J = P.jobs[blockIdx.y];
     const int rows = J.a_blocks * 64, cols = J.b_blocks * 64;
-    const int n_w = rows * cols, n_items = n_w + (J.bias_off >= 0 ? rows : 0);
+    const int n_w4 = rows * cols / 4, n_items = n_w4 + (J.bias_off >= 0 ? rows : 0);
     for (int item = blockIdx.x * 256 + threadIdx.x; item < n_items; item += gridDim.x * 256) {
-        const bool is_w = item < n_w;
-        const int r = is_w ? item / cols : item - n_w, c = is_w ? item % cols : 0;
+        const bool is_w = item < n_w4;
+        const int r = is_w ? (item * 4) / cols : item - n_w4, c = is_w ? (item * 4) % cols : 0;
         const size_t local = is_w ? (size_t)r * 256 + c : (size_t)256 * 256 + r;
-        float sum = 0.f;
+        const float* src = P.partial + (size_t)J.first_cta * kPartFloats + local;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
         for (int part = 0; part < J.parts; ++part) {
             if (P.n_tiles * (part + 1) / J.parts <= P.n_tiles * part / J.parts) continue;     // this CTA had no tiles
-            sum += P.partial[(size_t)(J.first_cta + part) * kPartFloats + local];
+            if (is_w) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)part * kPartFloats));
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            } else {
+                sum.x += __ldg(src + (size_t)part * kPartFloats);
+            }
         }
-        float* dst = is_w ? P.grad + J.out_off + (size_t)r * J.out_pitch + c : P.grad + J.bias_off + r;
-        *dst += sum;
+        if (is_w) {
+            float4* dst = reinterpret_cast<float4*>(P.grad + J.out_off + (size_t)r * J.out_pitch + c);
+            float4 d = *dst;
+            d.x += sum.x; d.y += sum.y; d.z += sum.z; d.w += sum.w;
+            *dst = d;
+        } else {
+            P.grad[J.bias_off + r] += sum.x;
+        }
     }
 }
 

@@ -164,31 +164,62 @@ class TrainStep:
             noise_c = d_nc * self.noise if d_nc is not None else K.RngNoise(float(self.noise), rng, K.RNG_NOISE_C)
             noise_f = d_nf * self.noise if d_nf is not None else K.RngNoise(float(self.noise), rng, K.RNG_NOISE_F)
 
+        # NERF_B200_BWD_SCHED: 2 (default) = the schedule described below; 0 / 1 = A/B timing alternatives
+        sched = int(os.environ.get("NERF_B200_BWD_SCHED", "2"))
+        main = torch.cuda.current_stream(dev)
+        side = self.side
         pk_c, pk_f = self.coarse.packed(), self.fine.packed()
         rows_c, rows_f = n * self.s_c, n * self.s_f
         vt_c = K.viewdir_term(pk_c, rays)
         raw_c = K.mlp_fwd(pk_c, K.IN_RAYS, rays, z_c, rows_c, self.s_c, vt_c, self.s_c, act_save=self.act_c)
         rgb_c, w_c = K.composite_fwd(raw_c.view(n, self.s_c, 4), z_c, rays, noise_c, self.white_bkg)
+
+        def loss_and_grad_raw(idx, raw, z, rgb, noise, s):
+            _, g = K.mse_loss_grad(rgb, target, loss=self.loss)
+            return K.composite_bwd(raw.view(n, s, 4), z, rays, noise, self.white_bkg, g)
+
+        graw_c = None
+        if sched == 2:
+            # The coarse network's loss, compositing backward and head gradients need nothing from the fine
+            # pass: they run on the side stream under the fine forward, as does the zeroing of the blobs.
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.loss.zero_()
+                self.blob.zero_()
+                graw_c = loss_and_grad_raw(0, raw_c, z_c, rgb_c, noise_c, self.s_c)
+                graw_c_ready = side.record_event()
+                K.mlp_bwd_heads(self.act_c, graw_c.view(rows_c, 4), rows_c, self.blob[0], stream=side)
+            for t in (raw_c, rgb_c, z_c):
+                t.record_stream(side)
+            graw_c.record_stream(main)
         z_f = K.resample_merge(z_c, w_c, d_u) if d_u is not None else K.resample_merge(z_c, w_c, rng=rng, n_fine=self.n_fine)
         vt_f = K.viewdir_term(pk_f, rays)
         raw_f = K.mlp_fwd(pk_f, K.IN_RAYS, rays, z_f, rows_f, self.s_f, vt_f, self.s_f, act_save=self.act_f)
-        rgb_f, _ = K.composite_fwd(raw_f.view(n, self.s_f, 4), z_f, rays, noise_f, self.white_bkg, want_weights=False)
-
-        self.loss.zero_()
-        _, g_f = K.mse_loss_grad(rgb_f, target, loss=self.loss)
-        _, g_c = K.mse_loss_grad(rgb_c, target, loss=self.loss)
-        graw_f = K.composite_bwd(raw_f.view(n, self.s_f, 4), z_f, rays, noise_f, self.white_bkg, g_f)
-        graw_c = K.composite_bwd(raw_c.view(n, self.s_c, 4), z_c, rays, noise_c, self.white_bkg, g_c)
+        if sched == 2:
+            # ... and the fine network's compositing, loss and compositing backward run on the side stream under
+            # the coarse dZ chain, which starts right behind the fine forward
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rgb_f, _ = K.composite_fwd(raw_f.view(n, self.s_f, 4), z_f, rays, noise_f, self.white_bkg, want_weights=False)
+                graw_f = loss_and_grad_raw(1, raw_f, z_f, rgb_f, noise_f, self.s_f)
+                graw_f_ready = side.record_event()
+                K.mlp_bwd_heads(self.act_f, graw_f.view(rows_f, 4), rows_f, self.blob[1], stream=side)
+            for t in (raw_f, z_f):
+                t.record_stream(side)
+            graw_f.record_stream(main)
+        else:
+            rgb_f, _ = K.composite_fwd(raw_f.view(n, self.s_f, 4), z_f, rays, noise_f, self.white_bkg, want_weights=False)
+            self.loss.zero_()
+            graw_f = loss_and_grad_raw(1, raw_f, z_f, rgb_f, noise_f, self.s_f)
+            graw_c = loss_and_grad_raw(0, raw_c, z_c, rgb_c, noise_c, self.s_c)
+            self.blob.zero_()
+            side.wait_stream(main)
 
         # Gradient kernels.  Main stream: dZ chain and dW per network (tensor-core kernels, one CTA per
-        # SM).  Side stream: the CUDA-core kernels, placed under the kernel that leaves them room -- the
-        # l_alpha/l11 heads (inputs: saved activations + grad_raw) start at once and run beside the
-        # tensor-bound dZ chains, which use about half of the HBM bandwidth; the view columns of a network
-        # follow its dZ chain.  Beside the HBM-bound dW kernel they only took bandwidth from it.
-        self.blob.zero_()
-        main = torch.cuda.current_stream(dev)
-        side = self.side
-        side.wait_stream(main)
+        # SM).  Side stream: the CUDA-core kernels, placed under the kernel that leaves them room -- loss,
+        # compositing backward and the l_alpha/l11 heads (inputs: saved activations + grad_raw) as above;
+        # the view columns of a network follow its dZ chain.  Beside the HBM-bound dW kernel they only took
+        # bandwidth from it.
         jobs = ((0, self.coarse, graw_c.view(rows_c, 4), self.act_c, rows_c, self.s_c, self.dz_c),
                 (1, self.fine, graw_f.view(rows_f, 4), self.act_f, rows_f, self.s_f, self.dz))
         # NERF_B200_BWD_SCHED (A/B timing, tools/time_bwd_schedules.py): 0 everything on one stream,
@@ -196,11 +227,9 @@ class TrainStep:
         # are within run-to-run noise of each other.  (Round 2 also tried running the two networks' dZ / dW
         # kernels side by side on disjoint SM sets -- write-bound beside read-bound: 5.05-5.58 ms against
         # 5.03-5.09 ms for this schedule, profiles/r02_bwd_schedules.txt -- and dropped it.)
-        sched = int(os.environ.get("NERF_B200_BWD_SCHED", "2"))
         if sched == 2:
             for idx, net, graw, act, rows, s, dz in jobs:
-                K.mlp_bwd_heads(act, graw, rows, self.blob[idx], stream=side)
-            for idx, net, graw, act, rows, s, dz in jobs:
+                main.wait_event(graw_c_ready if idx == 0 else graw_f_ready)
                 K.mlp_bwd_dz(net.packed_bwd(), graw, act, rows, dz=dz)
                 side.wait_stream(main)
                 K.viewdir_term_bwd(dz, rows, rays, s, False, self.blob[idx], stream=side)
